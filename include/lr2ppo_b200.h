@@ -1,0 +1,188 @@
+/*
+ * lr2ppo_b200 — C ABI of the B200-native (sm_100a) kernels behind the LR2PPO
+ * training / evaluation hot path.
+ *
+ * Conventions:
+ *   - every pointer is a DEVICE pointer unless the name ends in `_host`;
+ *   - memory is caller-owned: kernels never allocate or free;
+ *   - `stream` is a cudaStream_t passed as void*; all work is asynchronous on it;
+ *   - return 0 on success, a negative LR2_ERR_* code otherwise; no exceptions, no exit;
+ *   - "bf16" buffers hold __nv_bfloat16, "f32" float, "i64" long long;
+ *   - citations `ref:` point into the reference tree (ChazzyGordon/LR2PPO) and name
+ *     the Python code path the entry point replaces.
+ *
+ * The reference is pure Python/PyTorch: its "FFI" for this path is the set of
+ * ATen calls inside the cited functions.  The binding a maintainer adds is the
+ * ctypes layer in lr2ppo_b200/_lib.py.
+ */
+#ifndef LR2PPO_B200_H
+#define LR2PPO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LR2_ABI_VERSION 1
+
+/* error codes */
+#define LR2_OK 0
+#define LR2_ERR_BAD_SHAPE (-1)
+#define LR2_ERR_BAD_DTYPE (-2)
+#define LR2_ERR_MISALIGNED (-3)
+#define LR2_ERR_WRONG_ARCH (-4)
+#define LR2_ERR_CUDA (-5)
+#define LR2_ERR_TMA (-6)
+#define LR2_ERR_UNSUPPORTED (-7)
+
+/* GEMM epilogues (output coordinates r = row, c = column of the written tensor) */
+#define LR2_EPI_NONE 0          /* out = acc (+ beta*out_old for f32 outputs)                */
+#define LR2_EPI_BIAS 1          /* out = acc + bias[c]                                        */
+#define LR2_EPI_BIAS_GELU 2     /* pre = acc + bias[c]; C2 = pre; out = dropout(gelu_erf(pre)) */
+#define LR2_EPI_BIAS_DROP_RES 3 /* out = dropout(acc + bias[c]) + aux[r,c]                    */
+#define LR2_EPI_DGELU 4         /* out = acc * gelu_erf'(aux[r,c]) * dropout_mask             */
+#define LR2_EPI_ADD 5           /* out = acc + aux[r,c]                                       */
+
+int lr2_abi_version(void);
+const char* lr2_last_error_string(int code);
+/* 0 when the current device is compute capability 10.x, LR2_ERR_WRONG_ARCH otherwise. */
+int lr2_check_device(void);
+
+/* ---------------------------------------------------------------- dense --
+ * D[M,N] = A[M,K] * B[N,K]^T, bf16 x bf16 -> fp32 (tcgen05.mma, TMEM accumulators, TMA loads).
+ * a_mn_major / b_mn_major = 0: operand stored row-major [rows, K] (pitch lda/ldb elements);
+ *                         = 1: operand stored row-major [K, rows].
+ * transposed_out = 1 writes element (m, n) at C[n*ldc + m] (epilogue tensors follow the
+ * written orientation).  splits > 1 = split-K through `workspace`
+ * (lr2_gemm_workspace_bytes).  block_n in {0 (auto), 64, 128, 256}.
+ * ref: every nn.Linear on the path — finetune/ppo.py:154-170 (Mlp), :207-208 (out_layer),
+ *      finetune/xit.py:103-147 (FeedForwardBlock, MultiHeadAttention projections),
+ *      tencentpretrain/layers/multi_headed_attn.py:27-76, position_ffn.py:12-15 — and their
+ *      autograd backward (dgrad / wgrad).
+ */
+long long lr2_gemm_workspace_bytes(int M, int N, int splits, int transposed_out, long long ldc);
+int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
+                  void* C, long long ldc, int c_is_f32, int transposed_out, int M, int N, int K, int epilogue,
+                  const float* bias, const void* aux, long long ldaux, void* C2, float beta, float drop_p,
+                  unsigned long long seed, unsigned int site, int splits, void* workspace, int block_n,
+                  void* stream);
+
+/* ------------------------------------------------------------ layernorm --
+ * mode 0: torch nn.LayerNorm (biased variance, eps inside sqrt)   ref: finetune/xit.py:31-41,71-74,96-100
+ * mode 1: TencentPretrain LayerNorm gamma*(x-mean)/(std_unbiased+eps)+beta
+ *                                                                  ref: tencentpretrain/layers/layer_norm.py:16-21
+ * Rows of y may be re-grouped: out_row = (row / g_in) * g_out + row % g_in + g_off (g_in <= 0: identity);
+ * this is how the final XiT LayerNorm writes straight into the [items, 196+16, 768] concat buffer
+ * (ref: finetune/ppo.py:224 torch.cat).  stats[2*row] = mean, stats[2*row+1] = 1/sigma.
+ */
+int lr2_layernorm_fwd(const void* x_bf16, const float* gamma, const float* beta, void* y_bf16, float* stats,
+                      long long rows, int D, float eps, int mode, int g_in, int g_out, int g_off, void* stream);
+/* dx = LN'(dy) (+ add_bf16 if non-null).  dy rows use the same re-grouping as y in fwd.
+ * dxm (optional) = dx * dropout_mask(seed, site)/(1-p): the gradient that flows into the
+ * dropout-ed branch feeding this LayerNorm's input.  dgamma/dbeta are accumulated through
+ * `partials` (>= lr2_layernorm_bwd_partials_floats(D) floats). */
+long long lr2_layernorm_bwd_partials_floats(int D);
+int lr2_layernorm_bwd(const void* dy_bf16, const void* x_bf16, const float* gamma, const float* stats,
+                      const void* add_bf16, void* dx_bf16, void* dxm_bf16, float* dgamma, float* dbeta,
+                      float* partials, long long rows, int D, float eps, int mode, int g_in, int g_out, int g_off,
+                      float drop_p, unsigned long long seed, unsigned int site, void* stream);
+
+/* -------------------------------------------------- XiT attention core --
+ * Per (item, head): P = softmax(pre_scale * Q K^T); O = (post_scale * P) V, Skv <= 16.
+ * XiT uses pre_scale = 1, post_scale = 1/sqrt(emb)  (softmax-then-scale quirk, no mask)
+ *                                                                  ref: finetune/xit.py:125-148
+ * q: [items, Sq, H*dh] pitch ldq; k, v: [items, Skv, H*dh] pitch ldkv; o pitch ldo. dh % 8 == 0, dh <= 128.
+ */
+int lr2_xattn_fwd(const void* q, long long ldq, const void* k, const void* v, long long ldkv, void* o,
+                  long long ldo, int items, int Sq, int Skv, int H, int dh, float pre_scale, float post_scale,
+                  void* stream);
+int lr2_xattn_bwd(const void* q, long long ldq, const void* k, const void* v, long long ldkv, const void* d_o,
+                  long long ldo, void* dq, long long lddq, void* dk, void* dv, long long lddkv, int items, int Sq,
+                  int Skv, int H, int dh, float pre_scale, float post_scale, void* stream);
+
+/* ------------------------------------------------------ glue kernels --- */
+/* dst[b, j, :] = bf16(src[b, index[b, j], :]); index == NULL -> identity (T_dst == T_src).
+ * ref: finetune/ppo.py:268-271 (text_emb[batch_index, index]) fused with the fp32 -> bf16 cast. */
+int lr2_cast_gather_bf16(const float* src, const long long* index, void* dst_bf16, int bs, int T_src, int T_dst,
+                         long long row_elems, void* stream);
+/* grouped row copy: dst[(g*dst_gstride + dst_off + r), :] (+)= src[(g*src_gstride + src_off + r), :]
+ * ref: finetune/ppo.py:224 (cat of x and img_feature) and its backward split. */
+int lr2_rows_copy_bf16(const void* src, long long src_gstride, long long src_off, void* dst, long long dst_gstride,
+                       long long dst_off, long long groups, long long rows_per_group, int D, int accumulate,
+                       void* stream);
+/* out[c] (+)= sum_r x[r, c]  (bias gradients).  partials >= lr2_colsum_partials_floats(cols) floats. */
+long long lr2_colsum_partials_floats(int cols);
+int lr2_colsum_bf16(const void* x, long long ldx, long long rows, int cols, float* out, float* partials,
+                    int accumulate, void* stream);
+/* out[r] = dot(x[r*row_stride + row_off, :], w) + b[0]       ref: finetune/ppo.py:228,293-295 (head, last token) */
+int lr2_rowdot_fwd(const void* x_bf16, long long row_stride, long long row_off, const float* w, const float* b,
+                   float* out, int rows, int D, void* stream);
+/* dx (all rows*row_stride rows, zero where not selected), dw[D], db[1] */
+int lr2_rowdot_bwd(const void* x_bf16, long long row_stride, long long row_off, const float* w, const float* dout,
+                   void* dx_bf16, float* dw, float* db, int rows, int D, void* stream);
+/* x[b, t, :] += pos[t, :]                                    ref: finetune/ppo.py:286-289 */
+int lr2_add_pos_fwd(void* x_bf16, const float* pos, int bs, int T, int D, void* stream);
+int lr2_add_pos_bwd(const void* dx_bf16, float* dpos, int bs, int T, int D, void* stream);
+int lr2_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream);
+int lr2_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream);
+
+/* ------------------------------------------------------------- PPO rows --
+ * Stage-3 update losses, forward + analytic backward in one launch.
+ * ref: finetune/ppo.py:38-55 (RankLoss), :431-432 (log), :544-575 (KL, entropy, advantage, policy loss).
+ * s, s_old: [B, n] f32; reward, v_old: [B]; pi: [B, n] i64 (= next_state[:, -n:]).
+ * out_scalars[0..3] = {policy_loss, rank_loss, hinge_cnt, sum|adv|}; per-row outputs [B] each;
+ * ds = d policy_loss / d s  [B, n].
+ */
+int lr2_ppo_policy_loss(const float* s, const float* s_old, const float* reward, const float* v_old,
+                        const long long* pi, int B, int n, float w_kl, float w_ent, float margin, float adv_eps,
+                        float* out_scalars, float* kl, float* ent, float* reward_adj, float* adv, float* ds,
+                        void* stream);
+/* ref: finetune/ppo.py:494-498.  out_loss[0] = mean(max((vc-R)^2,(V-R)^2)); dv = d loss / d V. */
+int lr2_clipped_value_loss(const float* v, const float* ret, const float* v_old, int B, float clip, float* out_loss,
+                           float* dv, void* stream);
+/* ref: finetune/reward_pair_dataloader.py:355-358 (margin 1), finetune/reward_trad.py:273 (margin 0.01).
+ * out[0] = mean(relu(margin-(c-r))), out[1] = mean(c > r). */
+int lr2_pair_hinge_loss(const float* chosen, const float* reject, int B, float margin, float* out, float* dchosen,
+                        float* dreject, void* stream);
+/* ref: finetune/pointwise.py:229 nn.SmoothL1Loss(beta=0.3) on (logits, int64 targets). */
+int lr2_smooth_l1_loss(const float* logits, const long long* tgt, long long n, float beta, float* out_loss,
+                       float* dlogits, void* stream);
+/* Rollout: idx = stable argsort_desc(scores); next_state = [0..n_prefix-1, state[idx]].
+ * ref: finetune/ppo.py:865-874.  state may be NULL (= arange(n)).  next_state: [B, n_prefix+n] i64. */
+int lr2_ppo_rollout(const float* scores, const long long* state, int B, int n, int n_prefix, long long* next_state,
+                    long long* order, void* stream);
+/* Sequential masked-softmax (Plackett-Luce) ranking sampler with caller-supplied uniforms u[B, n] in [0,1).
+ * greedy != 0 ignores u and takes the arg-max at every position (== lr2_ppo_rollout order).
+ * Outputs perm [B, n] i64 and logprob [B] f32.  north_star extension; oracle: oracle/ppo_rows.c. */
+int lr2_rank_sample(const float* scores, const float* u, int B, int n, int greedy, long long* perm, float* logprob,
+                    void* stream);
+/* GAE(gamma, lambda) reverse scan: delta_t = r_t + gamma*V_{t+1}*nd_t - V_t; A_t = delta_t + gamma*lambda*nd_t*A_{t+1}.
+ * rewards [B,T], values [B,T+1], notdone [B,T] or NULL; adv, ret [B,T].  T=1, V_1=0 -> r - V (ref: finetune/ppo.py:560). */
+int lr2_gae_scan(const float* rewards, const float* values, const float* notdone, int B, int T, float gamma,
+                 float lam, float* adv, float* ret, void* stream);
+
+/* ----------------------------------------------------------------- NDCG --
+ * Per query q (row pitch ld, length len[q] or N): sort scores descending (stable), gather labels,
+ * ideal = labels sorted descending, DCG@k accumulated sequentially in fp32 exactly like
+ * ref: ndcg.py:28-32,54-65 with callers finetune/ppo.py:651-659.
+ * log2_table[i] = fp32 log2(i+2).  ks [nk] i64.  ndcg [B, nk] f32.  order [B, ld] i64 (optional).
+ */
+int lr2_ndcg_at_k(const float* scores, const long long* labels, const int* lens, int B, int N, long long ld,
+                  const long long* ks, int nk, const float* log2_table, float* ndcg, long long* order,
+                  void* stream);
+
+/* ---------------------------------------------------------------- AdamW --
+ * HF-style AdamW without bias correction, decay applied after the Adam update with lr*wd.
+ * ref: tencentpretrain/utils/optimizers.py:344-402.
+ * The tensor table lives in device memory: for tensor t, ptrs[6*t+0..5] =
+ *   {p f32, g, m f32, v f32, shadow bf16 or NULL, unused}; meta[4*t+0..3] = {n, wd (float bits), g_is_bf16, 0}.
+ * chunks[2*c+0..1] = {tensor id, element offset}; each chunk covers lr2_adamw_chunk_elems() elements.
+ * hyper (device) = {lr, beta1, beta2, eps, 1-beta1, 1-beta2, grad_scale}.
+ */
+int lr2_adamw_chunk_elems(void);
+int lr2_adamw_multi(const void* const* ptrs, const long long* meta, const long long* chunks, long long num_chunks,
+                    const float* hyper, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LR2PPO_B200_H */

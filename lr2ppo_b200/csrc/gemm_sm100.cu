@@ -1,0 +1,607 @@
+// lr2_gemm_bf16: persistent, warp-specialised tcgen05/TMEM GEMM for sm_100a.
+//
+//   D[M,N] = A[M,K] * B[N,K]^T      bf16 operands, fp32 accumulation in TMEM
+//
+// Operands arrive through TMA (128-byte swizzle) and may each be K-major
+// (row-major [rows,K]) or MN-major (row-major [K,rows]) so that forward,
+// dgrad and wgrad of every Linear on the LR2PPO hot path
+// (reference finetune/ppo.py:154-170 Mlp, finetune/xit.py:103-147 FFN/Q/K/V/O)
+// run without a transpose pass.  The epilogue fuses bias, exact-erf GELU,
+// dropout (Philox), residual add and GELU-backward, writes bf16 or fp32, and can
+// write the tile transposed (used by the skinny out_layer.fc1 GEMM where the
+// 500 M-parameter weight is the 128-row "A" operand and the <=256 items are "N").
+// Split-K writes fp32 slabs that lr2_splitk_reduce folds with the same epilogue.
+//
+// Roles per CTA (192 threads): warp0 = TMA producer, warp1 = TMEM alloc + MMA
+// issuer (one elected lane), warps2-5 = epilogue (TMEM -> registers -> global).
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the MMAs of
+// tile i+1.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <cstring>
+#include "common.cuh"
+#include "../../include/lr2ppo_b200.h"
+
+namespace lr2 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+
+struct GemmParams {
+  int M, N, K;
+  int splits;          // split-K factor (>=1)
+  int kb_per_split;    // k-blocks per split
+  int epi;             // LR2_EPI_*
+  int transposed_out;  // output element (m,n) is written at C[n*ldc + m]
+  int c_f32;           // output dtype: 1 = fp32, 0 = bf16
+  void* C;
+  long long ldc;
+  bf16* C2;            // optional pre-activation output (EPI_BIAS_GELU), same shape/ld as C
+  const float* bias;   // indexed by output column
+  const bf16* aux;     // residual / pre-activation, same shape as output
+  long long ldaux;
+  float beta;          // fp32 out only: out += beta * C_old
+  float drop_p;        // 0 = no dropout
+  unsigned long long seed;
+  unsigned int site;
+  float* ws;           // split-K workspace [splits][out_rows*ldc]
+  long long ws_slab;   // elements per slab
+};
+
+// ------------------------------------------------------------------ PTX --
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (-> cudaErrorLaunchFailure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor layout:
+// start>>4 @0, LBO>>4 @16, SBO>>4 @32, version=1 @46, layout_type=2 (SWIZZLE_128B) @61).
+__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32 (1@4), A=B=bf16 (1@7, 1@10), majors @15/@16, N>>3 @17, M>>4 @24.
+__host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+// -------------------------------------------------------------- epilogue --
+// One output row r, 8 consecutive output columns c..c+7 (c % 8 == 0, c + 8 <= ncols).
+__device__ __forceinline__ void epi_store8(const GemmParams& p, float (&v)[8], long long r, int c) {
+  const long long off = r * p.ldc + c;
+  if (p.epi == LR2_EPI_NONE) {
+    if (p.c_f32 && p.beta != 0.f) {
+      const float4* o = reinterpret_cast<const float4*>((const float*)p.C + off);
+      float4 a = o[0], b = o[1];
+      v[0] += p.beta * a.x; v[1] += p.beta * a.y; v[2] += p.beta * a.z; v[3] += p.beta * a.w;
+      v[4] += p.beta * b.x; v[5] += p.beta * b.y; v[6] += p.beta * b.z; v[7] += p.beta * b.w;
+    }
+  } else {
+    if (p.bias != nullptr && (p.epi == LR2_EPI_BIAS || p.epi == LR2_EPI_BIAS_GELU || p.epi == LR2_EPI_BIAS_DROP_RES)) {
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
+      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+    }
+    float a[8];
+    if (p.epi == LR2_EPI_BIAS_DROP_RES || p.epi == LR2_EPI_DGELU || p.epi == LR2_EPI_ADD) {
+      const uint4 u = *reinterpret_cast<const uint4*>(p.aux + r * p.ldaux + c);
+      float2 t;
+      t = unpack_bf16x2(u.x); a[0] = t.x; a[1] = t.y;
+      t = unpack_bf16x2(u.y); a[2] = t.x; a[3] = t.y;
+      t = unpack_bf16x2(u.z); a[4] = t.x; a[5] = t.y;
+      t = unpack_bf16x2(u.w); a[6] = t.x; a[7] = t.y;
+    }
+    uint32_t keep = 0xFFu;
+    float dscale = 1.f;
+    if (p.drop_p > 0.f) {
+      const uint32_t th = dropout_thresh(p.drop_p);
+      const uint64_t lin = (uint64_t)off;  // ldc-strided linear index; multiple of 8
+      keep = dropout_keep4(p.seed, p.site, lin >> 2, th) | (dropout_keep4(p.seed, p.site, (lin >> 2) + 1, th) << 4);
+      dscale = 1.f / (1.f - p.drop_p);
+    }
+    if (p.epi == LR2_EPI_BIAS_GELU) {
+      if (p.C2 != nullptr) {
+        uint4 u;
+        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+        u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+        *reinterpret_cast<uint4*>(p.C2 + off) = u;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        // GELU is evaluated on the bf16-rounded pre-activation so that backward
+        // (which only has the stored bf16 copy) differentiates the same function.
+        const float x = __bfloat162float(__float2bfloat16(v[i]));
+        v[i] = ((keep >> i) & 1u) ? gelu_erf(x) * dscale : 0.f;
+      }
+    } else if (p.epi == LR2_EPI_BIAS_DROP_RES) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = (((keep >> i) & 1u) ? v[i] * dscale : 0.f) + a[i];
+    } else if (p.epi == LR2_EPI_DGELU) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * gelu_erf_grad(a[i]) * dscale : 0.f;
+    } else if (p.epi == LR2_EPI_ADD) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += a[i];
+    }
+  }
+  if (p.c_f32) {
+    float4* o = reinterpret_cast<float4*>((float*)p.C + off);
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+  } else {
+    uint4 u;
+    u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+    u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>((bf16*)p.C + off) = u;
+  }
+}
+
+// Scalar epilogue (transposed tiles and ragged edges). No dropout on this path.
+__device__ __forceinline__ void epi_store1(const GemmParams& p, float v, long long r, int c) {
+  const long long off = r * p.ldc + c;
+  if (p.epi == LR2_EPI_NONE) {
+    if (p.c_f32 && p.beta != 0.f) v += p.beta * ((const float*)p.C)[off];
+  } else {
+    if (p.bias != nullptr && (p.epi == LR2_EPI_BIAS || p.epi == LR2_EPI_BIAS_GELU || p.epi == LR2_EPI_BIAS_DROP_RES))
+      v += __ldg(p.bias + c);
+    float a = 0.f;
+    if (p.epi == LR2_EPI_BIAS_DROP_RES || p.epi == LR2_EPI_DGELU || p.epi == LR2_EPI_ADD)
+      a = __bfloat162float(p.aux[r * p.ldaux + c]);
+    if (p.epi == LR2_EPI_BIAS_GELU) {
+      if (p.C2 != nullptr) p.C2[off] = __float2bfloat16(v);
+      v = gelu_erf(__bfloat162float(__float2bfloat16(v)));
+    } else if (p.epi == LR2_EPI_BIAS_DROP_RES || p.epi == LR2_EPI_ADD) {
+      v += a;
+    } else if (p.epi == LR2_EPI_DGELU) {
+      v *= gelu_erf_grad(a);
+    }
+  }
+  if (p.c_f32) ((float*)p.C)[off] = v;
+  else ((bf16*)p.C)[off] = __float2bfloat16(v);
+}
+
+// ---------------------------------------------------------------- kernel --
+template <int BN>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+            const GemmParams p) {
+  using L = SmemLayout<BN>;
+  constexpr int STAGES = L::STAGES;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* full_bar = bars;                  // [STAGES]
+  uint64_t* empty_bar = bars + STAGES;        // [STAGES]
+  uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (p.M + BM - 1) / BM;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int total_work = m_tiles * n_tiles * p.splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ======================= TMA producer =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const int split = w % p.splits;
+        const int t = w / p.splits;
+        const int mt = t % m_tiles, nt = t / m_tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d(sa + j * (64 * BK * 2), &tmap_a, &full_bar[stage], mt * BM + j * 64, kb * BK);
+          } else {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BK, mt * BM);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              tma_load_2d(sb + j * (64 * BK * 2), &tmap_b, &full_bar[stage], nt * BN + j * 64, kb * BK);
+          } else {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BK, nt * BN);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer =========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+        const int split = w % p.splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + p.kb_per_split);
+        const int buf = it & 1;
+        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        mbar_wait(&tempty_bar[buf], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: 16 bf16 = 32 B along the swizzled 128-B row.
+            // MN-major: 16 k-rows = two 8-row (1024 B) swizzle atoms.
+            const uint64_t ad = A_MN ? make_sdesc(sa + k * 2048, 64 * BK * 2, 1024) : make_sdesc(sa + k * 32, 16, 1024);
+            const uint64_t bd = B_MN ? make_sdesc(sb + k * 2048, 64 * BK * 2, 1024) : make_sdesc(sb + k * 32, 16, 1024);
+            umma_bf16(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    // ======================= epilogue warps =====================
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    int it = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      const int split = w % p.splits;
+      const int t = w / p.splits;
+      const int mt = t % m_tiles, nt = t / m_tiles;
+      const int buf = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&tfull_bar[buf], acc_phase);
+      tc_fence_after();
+      const int m = mt * BM + quad * 32 + lane;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
+      GemmParams q = p;
+      if (p.splits > 1) {  // raw fp32 partial into this split's slab
+        q.epi = LR2_EPI_NONE; q.c_f32 = 1; q.beta = 0.f; q.drop_p = 0.f;
+        q.C = p.ws + (long long)split * p.ws_slab;
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)c0, r);
+        const int n0 = nt * BN + c0;
+        if (n0 >= p.N) continue;
+        if (!p.transposed_out) {
+          if (m < p.M) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const int n = n0 + g * 8;
+              if (n + 8 <= p.N) {
+                float v[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+                epi_store8(q, v, m, n);
+              } else {
+                for (int i = 0; i < 8; ++i)
+                  if (n + i < p.N) epi_store1(q, __uint_as_float(r[g * 8 + i]), m, n + i);
+              }
+            }
+          }
+        } else {
+          if (m < p.M) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n0 + i < p.N) epi_store1(q, __uint_as_float(r[i]), n0 + i, m);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// Fold split-K slabs and apply the epilogue. One thread per 8 output columns.
+__global__ void splitk_reduce_kernel(GemmParams p, long long out_rows, int out_cols) {
+  const int cols8 = out_cols / 8;
+  const long long total = out_rows * cols8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols8;
+    const int c = (int)(i % cols8) * 8;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int s = 0; s < p.splits; ++s) {
+      const float4* src = reinterpret_cast<const float4*>(p.ws + (long long)s * p.ws_slab + r * p.ldc + c);
+      const float4 a = src[0], b = src[1];
+      v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
+      v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
+    }
+    epi_store8(p, v, r, c);
+  }
+}
+
+// ------------------------------------------------------------ host side --
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static std::mutex g_mu;
+
+static int ensure_encode() {
+  if (g_encode) return LR2_OK;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || fn == nullptr) return LR2_ERR_TMA;
+  g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  return LR2_OK;
+}
+
+struct MapKey {
+  const void* ptr; long long d0, d1, stride; int b0, b1;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && d0 == o.d0 && d1 == o.d1 && stride == o.stride && b0 == o.b0 && b1 == o.b1;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.ptr);
+    h = h * 1000003u ^ (size_t)k.d0; h = h * 1000003u ^ (size_t)k.d1; h = h * 1000003u ^ (size_t)k.stride;
+    h = h * 1000003u ^ (size_t)(k.b0 * 1024 + k.b1);
+    return h;
+  }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// 2-D bf16 tensor map: inner dim d0 (contiguous), outer dim d1 with row pitch `stride` elements;
+// box = b0 x b1, 128-byte swizzle, OOB -> zero fill.
+static int get_tmap(const void* ptr, long long d0, long long d1, long long stride, int b0, int b1, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  int rc = ensure_encode();
+  if (rc != LR2_OK) return rc;
+  MapKey key{ptr, d0, d1, stride, b0, b1};
+  auto it = g_maps.find(key);
+  if (it != g_maps.end()) { *out = it->second; return LR2_OK; }
+  cuuint64_t gdim[2] = {(cuuint64_t)d0, (cuuint64_t)d1};
+  cuuint64_t gstr[1] = {(cuuint64_t)stride * 2};
+  cuuint32_t box[2] = {(cuuint32_t)b0, (cuuint32_t)b1};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = g_encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return LR2_ERR_TMA;
+  if (g_maps.size() > 4096) g_maps.clear();
+  g_maps.emplace(key, m);
+  *out = m;
+  return LR2_OK;
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using L = SmemLayout<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return LR2_ERR_CUDA;
+    configured = true;
+  }
+  const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+  const int total = m_tiles * n_tiles * p.splits;
+  const int grid = total < num_sms() ? total : num_sms();
+  gemm_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
+  LR2_RETURN_LAUNCH();
+}
+
+template <int BN>
+static int launch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                        cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch<BN, false, false>(ta, tb, p, s);
+  if (!a_mn && b_mn) return launch<BN, false, true>(ta, tb, p, s);
+  if (a_mn && !b_mn) return launch<BN, true, false>(ta, tb, p, s);
+  return launch<BN, true, true>(ta, tb, p, s);
+}
+
+}  // namespace lr2
+
+using namespace lr2;
+
+extern "C" long long lr2_gemm_workspace_bytes(int M, int N, int splits, int transposed_out, long long ldc) {
+  if (splits <= 1) return 0;
+  const long long rows = transposed_out ? N : M;
+  return (long long)splits * rows * ldc * 4;
+}
+
+extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
+                             int b_mn_major, void* C, long long ldc, int c_is_f32, int transposed_out, int M, int N,
+                             int K, int epilogue, const float* bias, const void* aux, long long ldaux, void* C2,
+                             float beta, float drop_p, unsigned long long seed, unsigned int site, int splits,
+                             void* workspace, int block_n, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (M <= 0 || N <= 0 || K <= 0) return LR2_ERR_BAD_SHAPE;
+  if (epilogue < 0 || epilogue > LR2_EPI_ADD) return LR2_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15)
+    return LR2_ERR_MISALIGNED;
+  if ((lda % 8) || (ldb % 8)) return LR2_ERR_MISALIGNED;
+  const int out_cols = transposed_out ? M : N;
+  if (!transposed_out && ((ldc % 8) || (N % 8))) return LR2_ERR_MISALIGNED;
+  if (transposed_out && drop_p > 0.f) return LR2_ERR_UNSUPPORTED;
+  if (splits < 1) splits = 1;
+  const int num_kb = (K + BK - 1) / BK;
+  if (splits > num_kb) splits = num_kb;
+  int kb_per = (num_kb + splits - 1) / splits;
+  splits = (num_kb + kb_per - 1) / kb_per;  // no empty splits
+  if (splits > 1) {
+    if (workspace == nullptr) return LR2_ERR_BAD_SHAPE;
+    if ((ldc % 8) || (out_cols % 8)) return LR2_ERR_MISALIGNED;
+  }
+  int BN = block_n;
+  if (BN == 0) BN = (N <= 64) ? 64 : (N <= 128 ? 128 : ((N > 128 && N <= 256 && transposed_out) ? 256 : 128));
+  if (BN != 64 && BN != 128 && BN != 256) return LR2_ERR_UNSUPPORTED;
+
+  CUtensorMap ta, tb;
+  int rc;
+  // K-major operand [rows,K]: dims {K, rows}, box {64, tile_rows}; MN-major [K,rows]: dims {rows, K}, box {64, 64}.
+  rc = a_mn_major ? get_tmap(A, M, K, lda, 64, BK, &ta) : get_tmap(A, K, M, lda, BK, BM, &ta);
+  if (rc != LR2_OK) return rc;
+  rc = b_mn_major ? get_tmap(B, N, K, ldb, 64, BK, &tb) : get_tmap(B, K, N, ldb, BK, BN, &tb);
+  if (rc != LR2_OK) return rc;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = M; p.N = N; p.K = K;
+  p.splits = splits; p.kb_per_split = kb_per;
+  p.epi = epilogue; p.transposed_out = transposed_out; p.c_f32 = c_is_f32;
+  p.C = C; p.ldc = ldc; p.C2 = reinterpret_cast<bf16*>(C2);
+  p.bias = bias; p.aux = reinterpret_cast<const bf16*>(aux); p.ldaux = ldaux;
+  p.beta = beta; p.drop_p = drop_p; p.seed = seed; p.site = site;
+  p.ws = reinterpret_cast<float*>(workspace);
+  const long long out_rows = transposed_out ? N : M;
+  p.ws_slab = out_rows * ldc;
+
+  if (BN == 64) rc = launch_major<64>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
+  else if (BN == 128) rc = launch_major<128>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
+  else rc = launch_major<256>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
+  if (rc != LR2_OK) return rc;
+
+  if (splits > 1) {
+    const long long total = out_rows * (out_cols / 8);
+    int blocks = (int)((total + 255) / 256);
+    const int cap = num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p, out_rows, out_cols);
+    LR2_RETURN_LAUNCH();
+  }
+  return LR2_OK;
+}

@@ -1,0 +1,302 @@
+// Memory-bound glue kernels around the dense path: cast+gather, concat row copies,
+// bias-gradient column sums, the 768->1 heads, positional embedding add.
+// All are pure streaming kernels: 16-byte vector accesses, grid sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace lr2 {
+
+constexpr int GRID_CAP = 148 * 8;
+
+__device__ __forceinline__ void ld8f(const bf16* p, float (&v)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 t;
+  t = unpack_bf16x2(u.x); v[0] = t.x; v[1] = t.y;
+  t = unpack_bf16x2(u.y); v[2] = t.x; v[3] = t.y;
+  t = unpack_bf16x2(u.z); v[4] = t.x; v[5] = t.y;
+  t = unpack_bf16x2(u.w); v[6] = t.x; v[7] = t.y;
+}
+__device__ __forceinline__ void st8f(bf16* p, const float (&v)[8]) {
+  uint4 u;
+  u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+  u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ref: finetune/ppo.py:268-271 — text_emb[batch_index, index], fused with fp32->bf16.
+__global__ void cast_gather_kernel(const float* __restrict__ src, const long long* __restrict__ index,
+                                   bf16* __restrict__ dst, int bs, int T_src, int T_dst, long long row_elems) {
+  const long long vec_per_row = row_elems / 8;
+  const long long total = (long long)bs * T_dst * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long slot = i / vec_per_row, c = (i % vec_per_row) * 8;
+    const long long b = slot / T_dst, j = slot % T_dst;
+    const long long sj = index ? index[b * T_dst + j] : j;
+    const float4* s = reinterpret_cast<const float4*>(src + (b * T_src + sj) * row_elems + c);
+    const float4 a = s[0], e = s[1];
+    const float v[8] = {a.x, a.y, a.z, a.w, e.x, e.y, e.z, e.w};
+    st8f(dst + slot * row_elems + c, v);
+  }
+}
+
+__global__ void rows_copy_kernel(const bf16* __restrict__ src, long long src_gstride, long long src_off,
+                                 bf16* __restrict__ dst, long long dst_gstride, long long dst_off, long long groups,
+                                 long long rows_per_group, int D, int accumulate) {
+  const int vec = D / 8;
+  const long long total = groups * rows_per_group * vec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / vec;
+    const int c = (int)(i % vec) * 8;
+    const long long g = row / rows_per_group, r = row % rows_per_group;
+    const bf16* s = src + (g * src_gstride + src_off + r) * D + c;
+    bf16* d = dst + (g * dst_gstride + dst_off + r) * D + c;
+    if (accumulate) {
+      float a[8], b[8];
+      ld8f(s, a);
+      ld8f(d, b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] += b[k];
+      st8f(d, a);
+    } else {
+      *reinterpret_cast<uint4*>(d) = *reinterpret_cast<const uint4*>(s);
+    }
+  }
+}
+
+// Column sums: grid (col tiles of 256, row slabs). Thread owns 8 columns... each warp covers 256 columns,
+// the block's warps stride over rows; deterministic two-stage reduction.
+constexpr int CS_SLABS = 64;
+__global__ void __launch_bounds__(256)
+colsum_partial_kernel(const bf16* __restrict__ x, long long ldx, long long rows, int cols,
+                      float* __restrict__ partials) {
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 256 + lane * 8;
+  const long long rows_per = (rows + gridDim.y - 1) / gridDim.y;
+  const long long r0 = blockIdx.y * rows_per;
+  const long long r1 = min(rows, r0 + rows_per);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < cols) {
+    for (long long r = r0 + warp; r < r1; r += 8) {
+      float v[8];
+      ld8f(x + r * ldx + c, v);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += v[k];
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[warp][lane * 8 + k] = acc[k];
+  __syncthreads();
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc < cols) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    partials[(size_t)blockIdx.y * cols + cc] = s;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ partials, int slabs, int cols, float* __restrict__ out,
+                                    int accumulate) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = accumulate ? out[c] : 0.f;
+  for (int b = 0; b < slabs; ++b) s += partials[(size_t)b * cols + c];
+  out[c] = s;
+}
+
+// head: warp per row.  ref: finetune/ppo.py:228 / :293-295
+__global__ void rowdot_fwd_kernel(const bf16* __restrict__ x, long long row_stride, long long row_off,
+                                  const float* __restrict__ w, const float* __restrict__ b, float* __restrict__ out,
+                                  int rows, int D) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const bf16* xr = x + (r * row_stride + row_off) * D;
+  float acc = 0.f;
+  for (int c = lane * 8; c < D; c += 256) {
+    float v[8];
+    ld8f(xr + c, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += v[k] * __ldg(w + c + k);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[r] = acc + (b ? b[0] : 0.f);
+}
+
+// dx[all rows] = selected ? dout[r]*w : 0 ; dw[c] = sum_r dout[r]*x[sel(r), c]; db = sum dout
+__global__ void rowdot_bwd_dx_kernel(const float* __restrict__ w, const float* __restrict__ dout,
+                                     bf16* __restrict__ dx, long long row_stride, long long row_off, int rows, int D) {
+  const int vec = D / 8;
+  const long long total = (long long)rows * row_stride * vec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / vec;
+    const int c = (int)(i % vec) * 8;
+    const long long r = row / row_stride;
+    float v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (row % row_stride == row_off) {
+      const float g = dout[r];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = g * __ldg(w + c + k);
+    }
+    st8f(dx + row * D + c, v);
+  }
+}
+__global__ void rowdot_bwd_dw_kernel(const bf16* __restrict__ x, long long row_stride, long long row_off,
+                                     const float* __restrict__ dout, float* __restrict__ dw, float* __restrict__ db,
+                                     int rows, int D) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < D) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += dout[r] * __bfloat162float(x[(r * row_stride + row_off) * D + c]);
+    dw[c] = s;
+  }
+  if (c == 0 && db != nullptr) {
+    float s = 0.f;
+    for (int r = 0; r < rows; ++r) s += dout[r];
+    db[0] = s;
+  }
+}
+
+// ref: finetune/ppo.py:286-289
+__global__ void add_pos_fwd_kernel(bf16* __restrict__ x, const float* __restrict__ pos, int bs, int T, int D) {
+  const int vec = D / 8;
+  const long long total = (long long)bs * T * vec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / vec;
+    const int c = (int)(i % vec) * 8;
+    const int t = (int)(row % T);
+    float v[8];
+    ld8f(x + row * D + c, v);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] += __ldg(pos + (long long)t * D + c + k);
+    st8f(x + row * D + c, v);
+  }
+}
+__global__ void add_pos_bwd_kernel(const bf16* __restrict__ dx, float* __restrict__ dpos, int bs, int T, int D) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * D) return;
+  const int t = i / D, c = i % D;
+  float s = 0.f;
+  for (int b = 0; b < bs; ++b) s += __bfloat162float(dx[((long long)b * T + t) * D + c]);
+  dpos[i] = s;
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, bf16* __restrict__ dst, long long n) {
+  const long long n8 = n / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const float4* s = reinterpret_cast<const float4*>(src + i * 8);
+    const float4 a = s[0], e = s[1];
+    const float v[8] = {a.x, a.y, a.z, a.w, e.x, e.y, e.z, e.w};
+    st8f(dst + i * 8, v);
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n % 8)) {
+    const long long i = n8 * 8 + threadIdx.x;
+    dst[i] = __float2bfloat16(src[i]);
+  }
+}
+__global__ void cast_bf16_f32_kernel(const bf16* __restrict__ src, float* __restrict__ dst, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dst[i] = __bfloat162float(src[i]);
+}
+
+static int grid_for(long long work_items, int threads) {
+  long long b = (work_items + threads - 1) / threads;
+  if (b > GRID_CAP) b = GRID_CAP;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+}  // namespace lr2
+
+using namespace lr2;
+#define S_(x) reinterpret_cast<cudaStream_t>(x)
+
+extern "C" int lr2_cast_gather_bf16(const float* src, const long long* index, void* dst, int bs, int T_src,
+                                    int T_dst, long long row_elems, void* stream) {
+  if (bs <= 0 || T_src <= 0 || T_dst <= 0 || row_elems <= 0 || row_elems % 8) return LR2_ERR_BAD_SHAPE;
+  if (index == nullptr && T_src != T_dst) return LR2_ERR_BAD_SHAPE;
+  const long long total = (long long)bs * T_dst * (row_elems / 8);
+  cast_gather_kernel<<<grid_for(total, 256), 256, 0, S_(stream)>>>(src, index, reinterpret_cast<bf16*>(dst), bs,
+                                                                    T_src, T_dst, row_elems);
+  LR2_RETURN_LAUNCH();
+}
+
+extern "C" int lr2_rows_copy_bf16(const void* src, long long src_gstride, long long src_off, void* dst,
+                                  long long dst_gstride, long long dst_off, long long groups,
+                                  long long rows_per_group, int D, int accumulate, void* stream) {
+  if (groups <= 0 || rows_per_group <= 0 || D <= 0 || D % 8) return LR2_ERR_BAD_SHAPE;
+  const long long total = groups * rows_per_group * (D / 8);
+  rows_copy_kernel<<<grid_for(total, 256), 256, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(src), src_gstride,
+                                                                  src_off, reinterpret_cast<bf16*>(dst), dst_gstride,
+                                                                  dst_off, groups, rows_per_group, D, accumulate);
+  LR2_RETURN_LAUNCH();
+}
+
+extern "C" long long lr2_colsum_partials_floats(int cols) { return (long long)CS_SLABS * cols; }
+
+extern "C" int lr2_colsum_bf16(const void* x, long long ldx, long long rows, int cols, float* out, float* partials,
+                               int accumulate, void* stream) {
+  if (rows <= 0 || cols <= 0 || cols % 8 || ldx % 8) return LR2_ERR_BAD_SHAPE;
+  if (partials == nullptr) return LR2_ERR_BAD_SHAPE;
+  int slabs = (int)((rows + 63) / 64);
+  if (slabs > CS_SLABS) slabs = CS_SLABS;
+  if (slabs < 1) slabs = 1;
+  dim3 grid((cols + 255) / 256, slabs);
+  colsum_partial_kernel<<<grid, 256, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(x), ldx, rows, cols, partials);
+  if (cudaGetLastError() != cudaSuccess) return LR2_ERR_CUDA;
+  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, S_(stream)>>>(partials, slabs, cols, out, accumulate);
+  LR2_RETURN_LAUNCH();
+}
+
+extern "C" int lr2_rowdot_fwd(const void* x, long long row_stride, long long row_off, const float* w, const float* b,
+                              float* out, int rows, int D, void* stream) {
+  if (rows <= 0 || D <= 0 || D % 8 || row_stride <= 0 || row_off < 0 || row_off >= row_stride)
+    return LR2_ERR_BAD_SHAPE;
+  rowdot_fwd_kernel<<<(rows + 7) / 8, 256, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(x), row_stride, row_off, w,
+                                                             b, out, rows, D);
+  LR2_RETURN_LAUNCH();
+}
+
+extern "C" int lr2_rowdot_bwd(const void* x, long long row_stride, long long row_off, const float* w,
+                              const float* dout, void* dx, float* dw, float* db, int rows, int D, void* stream) {
+  if (rows <= 0 || D <= 0 || D % 8 || row_stride <= 0 || row_off < 0 || row_off >= row_stride)
+    return LR2_ERR_BAD_SHAPE;
+  if (dx != nullptr) {
+    const long long total = (long long)rows * row_stride * (D / 8);
+    rowdot_bwd_dx_kernel<<<grid_for(total, 256), 256, 0, S_(stream)>>>(w, dout, reinterpret_cast<bf16*>(dx),
+                                                                        row_stride, row_off, rows, D);
+    if (cudaGetLastError() != cudaSuccess) return LR2_ERR_CUDA;
+  }
+  if (dw != nullptr) {
+    rowdot_bwd_dw_kernel<<<(D + 127) / 128, 128, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(x), row_stride,
+                                                                   row_off, dout, dw, db, rows, D);
+  }
+  LR2_RETURN_LAUNCH();
+}
+
+extern "C" int lr2_add_pos_fwd(void* x, const float* pos, int bs, int T, int D, void* stream) {
+  if (bs <= 0 || T <= 0 || D <= 0 || D % 8) return LR2_ERR_BAD_SHAPE;
+  const long long total = (long long)bs * T * (D / 8);
+  add_pos_fwd_kernel<<<grid_for(total, 256), 256, 0, S_(stream)>>>(reinterpret_cast<bf16*>(x), pos, bs, T, D);
+  LR2_RETURN_LAUNCH();
+}
+extern "C" int lr2_add_pos_bwd(const void* dx, float* dpos, int bs, int T, int D, void* stream) {
+  if (bs <= 0 || T <= 0 || D <= 0) return LR2_ERR_BAD_SHAPE;
+  add_pos_bwd_kernel<<<(T * D + 255) / 256, 256, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(dx), dpos, bs, T, D);
+  LR2_RETURN_LAUNCH();
+}
+extern "C" int lr2_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
+  if (n <= 0) return LR2_ERR_BAD_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) return LR2_ERR_MISALIGNED;
+  cast_f32_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, S_(stream)>>>(src, reinterpret_cast<bf16*>(dst), n);
+  LR2_RETURN_LAUNCH();
+}
+extern "C" int lr2_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream) {
+  if (n <= 0) return LR2_ERR_BAD_SHAPE;
+  cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(src), dst, n);
+  LR2_RETURN_LAUNCH();
+}

@@ -1,0 +1,124 @@
+// NDCG@k: segmented (per-query) shared-memory bitonic sort + DCG with the reference's exact
+// arithmetic.  ref: ndcg.py:28-32,54-65; callers finetune/ppo.py:651-659 (torch.sort descending,
+// gold[idx], ideal = sort(gold) descending).
+//
+// Bit-exactness contract: gain_i = float(int64(2**rel_i - 1)), term_i = gain_i / log2_table[i]
+// (IEEE fp32 division), dcg = ((0 + term_0) + term_1) + ... strictly sequential in fp32,
+// ndcg_k = ideal_k <= 1e-6f ? 1 : pred_k / ideal_k.  Only the sort is parallel.
+// Algorithmic HBM bytes: N*(4+8) in + 4*nk out per query (+8N when `order` is requested).
+#include "common.cuh"
+
+namespace lr2 {
+
+__device__ __forceinline__ unsigned long long score_key(float s, unsigned int idx) {
+  s = s + 0.0f;  // -0.0 -> +0.0 so that both zeros tie (torch.sort semantics)
+  unsigned int u = __float_as_uint(s);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);  // ascending-order-preserving
+  u = ~u;                                           // descending
+  return ((unsigned long long)u << 32) | idx;      // ties: lower index first (stable)
+}
+__device__ __forceinline__ unsigned long long label_key(long long l) {
+  const unsigned long long asc = (unsigned long long)l ^ 0x8000000000000000ull;
+  return ~asc;  // descending labels
+}
+__device__ __forceinline__ long long label_from_key(unsigned long long k) {
+  return (long long)((~k) ^ 0x8000000000000000ull);
+}
+__device__ __forceinline__ float gain_of(long long rel) {
+  // int64 2**rel - 1 with wrap-around like torch integer pow, then int64 -> fp32 (round to nearest)
+  // (negative exponents raise in torch; they and rel >= 64 are defined here as 2**rel == 0)
+  long long g;
+  if (rel < 0 || rel >= 64) g = -1;
+  else g = (long long)((1ull << rel) - 1ull);
+  return (float)g;
+}
+
+template <typename K>
+__device__ __forceinline__ void bitonic_sort(K* keys, int npad) {
+  for (int k = 2; k <= npad; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const K a = keys[i], b = keys[ixj];
+          const bool up = ((i & k) == 0);
+          if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
+
+__global__ void ndcg_kernel(const float* __restrict__ scores, const long long* __restrict__ labels,
+                            const int* __restrict__ lens, int N, long long ld, const long long* __restrict__ ks,
+                            int nk, const float* __restrict__ log2_table, float* __restrict__ ndcg,
+                            long long* __restrict__ order, int npad) {
+  extern __shared__ __align__(16) unsigned char nsm[];
+  unsigned long long* skey = reinterpret_cast<unsigned long long*>(nsm);  // [npad] (score,idx) keys
+  unsigned long long* lkey = skey + npad;                                  // [npad] label keys
+  float* tp = reinterpret_cast<float*>(lkey + npad);                       // [npad] predicted terms -> prefix
+  float* ti = tp + npad;                                                   // [npad] ideal terms -> prefix
+  const int q = blockIdx.x;
+  const int n = lens ? min(lens[q], N) : N;
+  const float* sq = scores + (long long)q * ld;
+  const long long* lq = labels + (long long)q * ld;
+  for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+    if (i < n) { skey[i] = score_key(sq[i], (unsigned int)i); lkey[i] = label_key(lq[i]); }
+    else { skey[i] = ~0ull; lkey[i] = ~0ull; }
+  }
+  __syncthreads();
+  bitonic_sort(skey, npad);
+  bitonic_sort(lkey, npad);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned int idx = (unsigned int)(skey[i] & 0xFFFFFFFFull);
+    if (order != nullptr) order[(long long)q * ld + i] = idx;
+    const float lg = log2_table[i];
+    tp[i] = gain_of(lq[idx]) / lg;
+    ti[i] = gain_of(label_from_key(lkey[i])) / lg;
+  }
+  __syncthreads();
+  // strictly sequential fp32 prefix sums (two lists -> two warps)
+  if (threadIdx.x == 0) {
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) { acc = acc + tp[i]; tp[i] = acc; }
+  } else if (threadIdx.x == 32) {
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) { acc = acc + ti[i]; ti[i] = acc; }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < nk; j += blockDim.x) {
+    const long long k = ks[j];
+    const int cut = (int)((k < (long long)n) ? k : (long long)n);
+    const float p = cut > 0 ? tp[cut - 1] : 0.f;
+    const float t = cut > 0 ? ti[cut - 1] : 0.f;
+    ndcg[(long long)q * nk + j] = (t <= 1e-6f) ? 1.0f : p / t;
+  }
+}
+
+}  // namespace lr2
+
+using namespace lr2;
+
+extern "C" int lr2_ndcg_at_k(const float* scores, const long long* labels, const int* lens, int B, int N, long long ld,
+                             const long long* ks, int nk, const float* log2_table, float* ndcg, long long* order,
+                             void* stream) {
+  if (B <= 0 || N <= 0 || nk <= 0 || ld < N) return LR2_ERR_BAD_SHAPE;
+  if (N > 4096) return LR2_ERR_UNSUPPORTED;
+  int npad = 2;
+  while (npad < N) npad <<= 1;
+  const size_t smem = (size_t)npad * (8 + 8 + 4 + 4);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(ndcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return LR2_ERR_CUDA;
+    configured = smem;
+  }
+  int threads = npad / 2;
+  if (threads < 32) threads = 64;
+  if (threads > 512) threads = 512;
+  if (threads < 64) threads = 64;
+  ndcg_kernel<<<B, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(scores, labels, lens, N, ld, ks, nk,
+                                                                            log2_table, ndcg, order, npad);
+  LR2_RETURN_LAUNCH();
+}

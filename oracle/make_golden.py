@@ -1,0 +1,256 @@
+"""TEST INFRASTRUCTURE ONLY — generate tests/golden/* by RUNNING THE IMPORTED REFERENCE on CPU.
+
+    python -m oracle.make_golden          (in the build container; needs /root/reference)
+
+Outputs (committed):
+  tests/golden/rows.json        NDCG, RankLoss, clipped value loss, hinge, SmoothL1, rollout sort, AdamW,
+                                LR schedule, TencentPretrain LayerNorm — reference outputs on seeded inputs
+  tests/golden/ppo_update.json  finetune/ppo.py:train_model executed on stub actor/critic modules whose
+                                outputs are free parameters: pins losses, logged statistics and
+                                d(loss)/d(scores), d(value_loss)/d(values)
+  tests/golden/fusion.pt        reference Actor / Critic / Reward forward + selected gradients on
+                                seed-generated weights and inputs (weights are re-generated from the seed
+                                by tests/golden_util.py, they are not stored)
+"""
+import json
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader  # noqa: E402
+from tests import golden_util  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def tl(t):
+    return t.detach().cpu().tolist()
+
+
+def gen_rows():
+    ndcg = ref_loader.load("ndcg")
+    ppo = ref_loader.load("ppo")
+    out = {}
+    g = torch.Generator().manual_seed(1234)
+
+    # ---- NDCG through the reference's own call sequence (finetune/ppo.py:651-659) ----
+    cases = []
+    for n, hi in [(1, 3), (2, 3), (3, 3), (6, 3), (16, 3), (20, 3), (20, 5), (33, 5), (64, 3), (128, 5), (257, 3)]:
+        for rep in range(2):
+            scores = torch.randn(n, generator=g)
+            gold = torch.randint(0, hi, (n,), generator=g)
+            if rep == 1 and n > 3:
+                gold = torch.zeros(n, dtype=torch.int64) if n == 6 else gold
+            _, idx = torch.sort(scores, dim=-1, descending=True)
+            gold_re = gold[idx]
+            true_rel, _ = torch.sort(gold, dim=-1, descending=True)
+            meter = ndcg.AverageNDCGMeter()
+            vals = meter.return_ndcg_at_k(gold_re, true_rel)
+            cases.append(dict(scores=tl(scores), labels=tl(gold), order=tl(idx), ks=meter.ndcg_at_k,
+                              ndcg=[float(np.float32(v)) for v in tl(vals)]))
+    out["ndcg"] = cases
+
+    # ---- RankLoss (finetune/ppo.py:38-55) ----
+    cases = []
+    for B, n, margin in [(3, 2, 0.01), (24, 2, 0.01), (8, 5, 0.01), (5, 4, 1.0)]:
+        s = torch.randn(B, n, generator=g) * (0.02 if margin < 0.1 else 1.0)
+        order = torch.stack([torch.randperm(n, generator=g) for _ in range(B)])
+        cases.append(dict(scores=tl(s), order=tl(order), margin=margin, loss=float(ppo.RankLoss(margin)(s, order))))
+    s = torch.tensor([[3.0, 1.0], [2.0, 0.5]])
+    cases.append(dict(scores=tl(s), order=[[0, 1], [0, 1]], margin=0.01,
+                      loss=float(ppo.RankLoss(0.01)(s, torch.tensor([[0, 1], [0, 1]])))))  # all satisfied -> 0
+    out["rank_loss"] = cases
+
+    # ---- clipped value loss (finetune/ppo.py:494-498) ----
+    cases = []
+    for B, clip in [(2, 0.5), (24, 0.5), (24, 0.05), (7, 0.4)]:
+        v = torch.randn(B, generator=g); r = torch.randn(B, generator=g); vo = torch.randn(B, generator=g) * 0.3
+        vv = v.clone().requires_grad_(True)
+        loss = ppo.clipped_value_loss(vv, r, vo, clip)
+        loss.backward()
+        cases.append(dict(v=tl(v), ret=tl(r), v_old=tl(vo), clip=clip, loss=float(loss), dv=tl(vv.grad)))
+    out["value_loss"] = cases
+
+    # ---- pair hinge (finetune/reward_pair_dataloader.py:355-358) ----
+    cases = []
+    for B, margin in [(64, 1.0), (24, 0.01), (3, 1.0)]:
+        c = torch.randn(B, generator=g); r = torch.randn(B, generator=g)
+        cc = c.clone().requires_grad_(True); rr = r.clone().requires_grad_(True)
+        loss = torch.relu(margin - (cc - rr)).mean()   # line 355-356 with margin 1 / reward_trad.py:273
+        loss.backward()
+        acc = (c > r).float().mean()
+        cases.append(dict(chosen=tl(c), reject=tl(r), margin=margin, loss=float(loss), acc=float(acc),
+                          dchosen=tl(cc.grad), dreject=tl(rr.grad)))
+    out["pair_hinge"] = cases
+
+    # ---- SmoothL1 beta 0.3 (finetune/pointwise.py:229) ----
+    cases = []
+    for n in [40, 7]:
+        x = torch.randn(n, generator=g); t = torch.randint(0, 3, (n,), generator=g)
+        xx = x.clone().requires_grad_(True)
+        loss = torch.nn.SmoothL1Loss(beta=0.3)(xx.view(-1), t.view(-1))
+        loss.backward()
+        cases.append(dict(logits=tl(x), tgt=tl(t), beta=0.3, loss=float(loss), dlogits=tl(xx.grad)))
+    out["smooth_l1"] = cases
+
+    # ---- rollout sort + compose (finetune/ppo.py:865-874) ----
+    cases = []
+    for B, n in [(24, 2), (5, 7), (3, 20)]:
+        s = torch.randn(B, n, generator=g)
+        state = torch.arange(n).unsqueeze(0).repeat(B, 1)
+        _, idx = torch.sort(s, dim=-1, descending=True)
+        ns = torch.stack([torch.index_select(state[i], 0, idx[i]) for i in range(B)])
+        ns = torch.cat([torch.arange(2).unsqueeze(0).repeat(B, 1), ns], dim=1)
+        cases.append(dict(scores=tl(s), next_state=tl(ns)))
+    out["rollout"] = cases
+
+    # ---- AdamW (tencentpretrain/utils/optimizers.py:305-402) + linear schedule (:62-86) ----
+    opt_mod = ref_loader.load("tencentpretrain.utils.optimizers")
+    cases = []
+    for n, wd, lr, steps in [(1000, 0.01, 1e-3, 3), (37, 0.0, 5e-4, 2)]:
+        p0 = torch.randn(n, generator=g) * 0.02
+        grads = [torch.randn(n, generator=g) * 0.01 for _ in range(steps)]
+        p = torch.nn.Parameter(p0.clone())
+        opt = opt_mod.AdamW([{"params": [p], "weight_decay": wd}], lr=lr, correct_bias=False)
+        for gr in grads:
+            p.grad = gr.clone()
+            opt.step()
+        st = opt.state[p]
+        cases.append(dict(p0=tl(p0), grads=[tl(x) for x in grads], wd=wd, lr=lr, p=tl(p), m=tl(st["exp_avg"]),
+                          v=tl(st["exp_avg_sq"])))
+    out["adamw"] = cases
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = opt_mod.AdamW([p], lr=1e-3, correct_bias=False)
+    sch = opt_mod.get_linear_schedule_with_warmup(opt, 34130.1, 341301)
+    lrs = [opt.param_groups[0]["lr"]]
+    for _ in range(5):
+        opt.step(); sch.step(); lrs.append(opt.param_groups[0]["lr"])
+    out["schedule"] = dict(base_lr=1e-3, warmup=34130.1, total=341301, lrs=lrs)
+
+    # ---- TencentPretrain LayerNorm (tencentpretrain/layers/layer_norm.py:5-21) ----
+    ln_mod = ref_loader.load("tencentpretrain.layers.layer_norm")
+    ln = ln_mod.LayerNorm(64, eps=1e-6)
+    with torch.no_grad():
+        ln.gamma.copy_(torch.randn(64, generator=g)); ln.beta.copy_(torch.randn(64, generator=g))
+    x = torch.randn(5, 64, generator=g, requires_grad=True)
+    y = ln(x)
+    gy = torch.randn(5, 64, generator=g)
+    (y * gy).sum().backward()
+    out["tencent_ln"] = dict(x=tl(x), gamma=tl(ln.gamma), beta=tl(ln.beta), y=tl(y), gy=tl(gy), dx=tl(x.grad),
+                             dgamma=tl(ln.gamma.grad), dbeta=tl(ln.beta.grad))
+    with open(os.path.join(GOLD, "rows.json"), "w") as f:
+        json.dump(out, f)
+    print("rows.json written")
+
+
+class _StubActor(torch.nn.Module):
+    def __init__(self, scores):
+        super().__init__()
+        self.scores = torch.nn.Parameter(scores.clone())
+
+    def forward(self, text, img, tgts):
+        return torch.zeros(()), self.scores.view(-1)
+
+
+class _StubCritic(torch.nn.Module):
+    def __init__(self, values):
+        super().__init__()
+        self.values = torch.nn.Parameter(values.clone())
+
+    def forward(self, text, img, tgts, state):
+        return self.values * 1.0
+
+
+class _StubAC(torch.nn.Module):
+    def __init__(self, s, v):
+        super().__init__()
+        self.actor, self.critic = _StubActor(s), _StubCritic(v)
+
+
+def gen_ppo_update():
+    """Run the reference train_model (finetune/ppo.py:501-617) on stub networks."""
+    import argparse
+    import torch.distributed as dist
+    ppo = ref_loader.load("ppo")
+    if not dist.is_initialized():
+        f = tempfile.NamedTemporaryFile(delete=False)
+        dist.init_process_group("gloo", init_method=f"file://{f.name}", rank=0, world_size=1)
+    g = torch.Generator().manual_seed(77)
+    cases = []
+    for B, n, scale in [(24, 2, 0.05), (24, 2, 1.0), (6, 2, 0.3)]:
+        s_new = torch.randn(B, n, generator=g) * scale
+        s_old = s_new + torch.randn(B, n, generator=g) * scale * 0.3
+        reward = torch.randn(B, generator=g) * 0.5
+        v_old = torch.randn(B, generator=g) * 0.5
+        v_new = v_old + torch.randn(B, generator=g) * 0.7
+        state = torch.arange(n).unsqueeze(0).repeat(B, 1)
+        _, idx = torch.sort(s_old, dim=-1, descending=True)
+        next_state = torch.cat([torch.arange(2).unsqueeze(0).repeat(B, 1), idx], dim=1)
+        model = _StubAC(s_new, v_new)
+        args = argparse.Namespace(is_master=False, mode="reg", kl_div_loss_weight=0.001, entropy_weight=0.001,
+                                  value_clip=0.5)
+        opt = torch.optim.SGD(model.actor.parameters(), lr=0.0)
+        copt = torch.optim.SGD(model.critic.parameters(), lr=0.0)
+        sch = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0)
+        csch = torch.optim.lr_scheduler.LambdaLR(copt, lambda s: 1.0)
+        dummy = torch.zeros(1)
+        mem = [[state, next_state, s_old.clone(), reward.clone(), v_old.clone(), dummy, dummy, dummy]]
+        stats = ppo.train_model(args, model, opt, copt, sch, csch, mem, 0)
+        names = ["policy_loss", "value_loss", "kl", "old_value", "value", "rewards_ori", "rewards", "advantages",
+                 "rank_loss", "entropy"]
+        cases.append(dict(s_new=tl(s_new), s_old=tl(s_old), reward=tl(reward), v_old=tl(v_old), v_new=tl(v_new),
+                          next_state=tl(next_state), w_kl=0.001, w_ent=0.001, value_clip=0.5,
+                          stats={k: float(v) for k, v in zip(names, stats)},
+                          ds=tl(model.actor.scores.grad), dv=tl(model.critic.values.grad)))
+    with open(os.path.join(GOLD, "ppo_update.json"), "w") as f:
+        json.dump(cases, f)
+    print("ppo_update.json written")
+
+
+def gen_fusion():
+    """Reference Actor / Critic / Reward (finetune/ppo.py:196-350) forward + backward on seeded tensors."""
+    ppo = ref_loader.load("ppo")
+    cfg = golden_util.FUSION_CFG
+    args = ref_loader.ppo_args(seq_length=cfg["seq_length"], max_imgs=cfg["max_imgs"])
+    out = {"cfg": cfg}
+    for kind in ("actor", "critic", "reward"):
+        cls = {"actor": ppo.Actor, "critic": ppo.Critic, "reward": ppo.Reward}[kind]
+        model = cls(args, args)
+        golden_util.init_params_(model, golden_util.SEEDS[kind])
+        model.eval()
+        text, img, tgts, index = golden_util.make_inputs(kind)
+        if kind == "actor":
+            _, logits = model(text, img, tgts)
+        else:
+            logits = model(text, img, tgts, index)
+        gw = golden_util.out_grad(kind, logits.numel())
+        (logits * gw).sum().backward()
+        rec = {"logits": logits.detach().clone()}
+        for name, p in model.named_parameters():
+            gr = p.grad
+            rec["gnorm/" + name] = gr.double().norm().float()
+            if gr.numel() <= 4096:
+                rec["grad/" + name] = gr.clone()
+            else:
+                rec["grad/" + name] = golden_util.grad_sample(gr).clone()
+        out[kind] = rec
+        print(kind, "logits", logits[:4].tolist())
+        del model
+    torch.save(out, os.path.join(GOLD, "fusion.pt"))
+    print("fusion.pt written")
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    which = sys.argv[1:] or ["rows", "ppo_update", "fusion"]
+    if "rows" in which:
+        gen_rows()
+    if "ppo_update" in which:
+        gen_ppo_update()
+    if "fusion" in which:
+        gen_fusion()

@@ -1,0 +1,101 @@
+"""Seeded tensors shared by oracle/make_golden.py (generator) and the parity tests (consumers).
+Weights are never stored: both sides regenerate them on the CPU from the same seeds."""
+import torch
+
+FUSION_CFG = dict(seq_length=196, max_imgs=16, feat=768, bs=2, tags=2)
+SEEDS = dict(actor=101, critic=202, reward=303)
+INPUT_SEED = 9001
+
+
+def init_params_(model, seed):
+    """Deterministic init in named_parameters() order: matrices N(0, 0.02) as in finetune/ppo.py:363-365,
+    LayerNorm scales 1 + 0.1 N(0,1), other vectors 0.02 N(0,1)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            r = torch.randn(p.shape, generator=g)
+            if p.dim() >= 2:
+                p.copy_(r * 0.02)
+            elif name.endswith("weight") and ("ln_" in name or ".fn.0." in name or name.startswith(("xit.1", "xitt.1"))):
+                p.copy_(1.0 + 0.1 * r)
+            else:
+                p.copy_(r * 0.02)
+
+
+def make_inputs(kind, cfg=FUSION_CFG):
+    g = torch.Generator().manual_seed(INPUT_SEED + SEEDS[kind])
+    bs, T, S, I, E = cfg["bs"], cfg["tags"], cfg["seq_length"], cfg["max_imgs"], cfg["feat"]
+    text = torch.randn(bs, T, S, E, generator=g)
+    img = torch.randn(bs, T, I, E, generator=g)
+    tgts = torch.randint(0, 3, (bs, T), generator=g)
+    if kind == "actor":
+        index = None
+    elif kind == "critic":
+        index = torch.stack([torch.randperm(T, generator=g) for _ in range(bs)])
+    else:
+        perm = torch.stack([torch.randperm(T, generator=g) for _ in range(bs)])
+        index = torch.cat([torch.arange(T).unsqueeze(0).repeat(bs, 1), perm], dim=1)
+    return text, img, tgts, index
+
+
+def out_grad(kind, n):
+    g = torch.Generator().manual_seed(SEEDS[kind] + 5)
+    return torch.randn(n, generator=g)
+
+
+def grad_sample(gr, k=4096):
+    flat = gr.reshape(-1)
+    step = max(1, flat.numel() // k)
+    return flat[::step][:k]
+
+
+def _xit_specs(pre, E=768):
+    H = 4 * E
+    a = pre + ".0.0.0.fn."
+    f = pre + ".0.0.1.fn."
+    out = []
+    for ln in ("ln_x", "ln_y"):
+        out += [(a + f"0.{ln}.weight", (E,)), (a + f"0.{ln}.bias", (E,))]
+    for lin in ("keys", "queries", "values", "projection"):
+        out += [(a + f"1.{lin}.weight", (E, E)), (a + f"1.{lin}.bias", (E,))]
+    out += [(f + "0.weight", (E,)), (f + "0.bias", (E,)), (f + "1.0.weight", (H, E)), (f + "1.0.bias", (H,)),
+            (f + "1.3.weight", (E, H)), (f + "1.3.bias", (E,)), (pre + ".1.0.weight", (E,)), (pre + ".1.0.bias", (E,))]
+    return out
+
+
+def _mlp_specs(pre, i, h, o):
+    return [(pre + ".fc1.weight", (h, i)), (pre + ".fc1.bias", (h,)), (pre + ".fc2.weight", (o, h)),
+            (pre + ".fc2.bias", (o,))]
+
+
+def param_specs(kind, cfg=FUSION_CFG):
+    """(name, shape) in the reference's named_parameters() order (finetune/ppo.py:196-212, 247-263)."""
+    E = cfg["feat"]
+    specs = _mlp_specs("text_proj", E, 4 * E, E) + _mlp_specs("img_proj", E, 4 * E, E)
+    if kind != "actor":
+        specs += [("pos_emb.weight", (4, E))]
+    specs += _xit_specs("xit", E)
+    if kind != "actor":
+        specs += _xit_specs("xitt", E)
+    specs += _mlp_specs("out_layer", (cfg["seq_length"] + cfg["max_imgs"]) * E, 4 * E, E)
+    specs += [("head.weight", (1, E)), ("head.bias", (1,))]
+    return specs
+
+
+def _is_ln_scale(name):
+    return name.endswith("weight") and ("ln_" in name or ".fn.0." in name or name.startswith(("xit.1", "xitt.1")))
+
+
+def make_state_dict(kind, cfg=FUSION_CFG):
+    """Same draws as init_params_ on the reference module, without needing the reference."""
+    g = torch.Generator().manual_seed(SEEDS[kind])
+    sd = {}
+    for name, shape in param_specs(kind, cfg):
+        r = torch.randn(shape, generator=g)
+        if len(shape) >= 2:
+            sd[name] = r * 0.02
+        elif _is_ln_scale(name):
+            sd[name] = 1.0 + 0.1 * r
+        else:
+            sd[name] = r * 0.02
+    return sd

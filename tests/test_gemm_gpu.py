@@ -1,0 +1,123 @@
+"""tcgen05 GEMM parity (floating point -> torch fp32 reference of the same op, tolerance in each test)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from lr2ppo_b200 import ops
+
+
+def _rel(d, ref):
+    return ((d.float() - ref).abs().max() / ref.abs().max().clamp_min(1e-6)).item()
+
+
+def _mk(rows, k, mn, gen):
+    t = torch.randn((k, rows) if mn else (rows, k), generator=gen, device="cuda", dtype=torch.float32)
+    return t.to(torch.bfloat16)
+
+
+def _ref(a, b, a_mn, b_mn):
+    A = a.float().t() if a_mn else a.float()
+    B = b.float().t() if b_mn else b.float()
+    return A @ B.t()
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (256, 256, 512, 128), (200, 136, 72, 0),
+                                       (384, 64, 320, 64), (300, 256, 192, 256), (1000, 768, 768, 0)])
+def test_gemm_majors(M, N, K, bn, a_mn, b_mn):
+    # MN-major operands need the rows dimension to be a multiple of 8 (16-byte pitch)
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K)
+    a = _mk(M, K, a_mn, g)
+    b = _mk(N, K, b_mn, g)
+    out = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32, block_n=bn)
+    ref = _ref(a, b, a_mn, b_mn)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 2e-3, f"rel err {_rel(out, ref)}"   # bf16 products are exact in fp32; only sum order differs
+
+
+def test_gemm_persistent_many_tiles():
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = _mk(9408, 768, False, g)
+    b = _mk(3072, 768, False, g)
+    out = ops.gemm(a, b, out_dtype=torch.float32)
+    ref = a.float() @ b.float().t()
+    assert _rel(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("splits", [2, 5, 16])
+@pytest.mark.parametrize("transposed", [False, True])
+def test_gemm_splitk_transposed(splits, transposed):
+    g = torch.Generator(device="cuda").manual_seed(splits)
+    M, N, K = 384, 48, 4096
+    a = _mk(M, K, False, g)
+    b = _mk(N, K, False, g)
+    bias_len = M if transposed else N
+    bias = torch.randn(bias_len, generator=g, device="cuda")
+    if transposed:
+        out = ops.gemm(a, b, transposed_out=True, splits=splits, out_dtype=torch.float32, epilogue=ops.EPI_BIAS,
+                       bias=bias, out=torch.empty((N, M), device="cuda"))
+        ref = (a.float() @ b.float().t()).t() + bias[None, :]
+    else:
+        out = ops.gemm(a, b, splits=splits, out_dtype=torch.float32, epilogue=ops.EPI_BIAS, bias=bias)
+        ref = a.float() @ b.float().t() + bias[None, :]
+    assert _rel(out, ref) < 2e-3
+
+
+def test_gemm_bias_gelu_and_pre():
+    g = torch.Generator(device="cuda").manual_seed(3)
+    a = _mk(520, 768, False, g)
+    w = (_mk(3072, 768, False, g).float() * 0.05).to(torch.bfloat16)
+    bias = torch.randn(3072, generator=g, device="cuda") * 0.1
+    pre = torch.empty((520, 3072), dtype=torch.bfloat16, device="cuda")
+    out = ops.gemm(a, w, epilogue=ops.EPI_BIAS_GELU, bias=bias, c2=pre)
+    ref_pre = a.float() @ w.float().t() + bias
+    ref = torch.nn.functional.gelu(ref_pre)
+    assert _rel(pre, ref_pre) < 1e-2   # bf16 output rounding
+    assert _rel(out, ref) < 1e-2
+
+
+def test_gemm_residual_dgelu_add():
+    g = torch.Generator(device="cuda").manual_seed(4)
+    a = _mk(260, 256, False, g)
+    w = _mk(768, 256, False, g)
+    bias = torch.randn(768, generator=g, device="cuda")
+    res = _mk(260, 768, False, g)
+    out = ops.gemm(a, w, epilogue=ops.EPI_BIAS_DROP_RES, bias=bias, aux=res)
+    ref = a.float() @ w.float().t() + bias + res.float()
+    assert _rel(out, ref) < 1e-2
+    out = ops.gemm(a, w, epilogue=ops.EPI_ADD, aux=res)
+    assert _rel(out, a.float() @ w.float().t() + res.float()) < 1e-2
+    pre = (res.float() * 0.5).to(torch.bfloat16)
+    out = ops.gemm(a, w, epilogue=ops.EPI_DGELU, aux=pre)
+    x = pre.float().requires_grad_(True)
+    torch.nn.functional.gelu(x).sum().backward()
+    assert _rel(out, (a.float() @ w.float().t()) * x.grad) < 1e-2
+
+
+def test_gemm_beta_accumulate():
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a = _mk(128, 192, True, g)
+    b = _mk(256, 192, True, g)
+    c0 = torch.randn(128, 256, generator=g, device="cuda")
+    out = c0.clone()
+    ops.gemm(a, b, a_mn=True, b_mn=True, out=out, beta=1.0)
+    assert _rel(out, a.float().t() @ b.float() + c0) < 2e-3
+
+
+def test_gemm_dropout_consistent_and_unbiased():
+    g = torch.Generator(device="cuda").manual_seed(6)
+    a = _mk(512, 128, False, g)
+    w = _mk(768, 128, False, g)
+    res = torch.zeros((512, 768), dtype=torch.bfloat16, device="cuda")
+    p = 0.1
+    o1 = ops.gemm(a, w, epilogue=ops.EPI_BIAS_DROP_RES, aux=res, drop_p=p, seed=1234, site=2)
+    o2 = ops.gemm(a, w, epilogue=ops.EPI_BIAS_DROP_RES, aux=res, drop_p=p, seed=1234, site=2)
+    o3 = ops.gemm(a, w, epilogue=ops.EPI_BIAS_DROP_RES, aux=res, drop_p=p, seed=1235, site=2)
+    assert torch.equal(o1, o2)
+    assert not torch.equal(o1, o3)
+    ref = a.float() @ w.float().t()
+    kept = o1 != 0
+    frac = 1.0 - kept.float().mean().item()
+    assert abs(frac - p) < 0.01, frac
+    assert _rel(o1.float()[kept], (ref / (1 - p))[kept]) < 1e-2
