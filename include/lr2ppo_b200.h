@@ -176,7 +176,8 @@ int lr2_ndcg_at_k(const float* scores, const long long* labels, const int* lens,
  * The tensor table lives in device memory: for tensor t, ptrs[6*t+0..5] =
  *   {p f32, g, m f32, v f32, shadow bf16 or NULL, unused}; meta[4*t+0..3] = {n, wd (float bits), g_is_bf16, 0}.
  * chunks[2*c+0..1] = {tensor id, element offset}; each chunk covers lr2_adamw_chunk_elems() elements.
- * hyper (device) = {lr, beta1, beta2, eps, 1-beta1, 1-beta2, grad_scale}.
+ * hyper (device, 8 floats) = {step_size, beta1, beta2, eps, 1-beta1, 1-beta2, grad_scale, lr_for_decay}
+ * (step_size == lr when correct_bias is False, as in every LR2PPO script).
  */
 int lr2_adamw_chunk_elems(void);
 int lr2_adamw_multi(const void* const* ptrs, const long long* meta, const long long* chunks, long long num_chunks,

@@ -11,12 +11,12 @@ constexpr int AW_THREADS = 256;
 constexpr int AW_CHUNK = 4096;  // elements per CTA (4 float4 per thread)
 
 __device__ __forceinline__ void adamw_elem(float& p, float g, float& m, float& v, float lr, float b1, float b2,
-                                           float eps, float omb1, float omb2, float wd) {
+                                           float eps, float omb1, float omb2, float wd, float lr_decay) {
   m = m * b1 + g * omb1;
   v = v * b2 + (g * g) * omb2;
   const float denom = sqrtf(v) + eps;
   p = p - lr * (m / denom);
-  if (wd > 0.f) p = p - (lr * wd) * p;
+  if (wd > 0.f) p = p - (lr_decay * wd) * p;
 }
 
 __global__ void __launch_bounds__(AW_THREADS)
@@ -33,7 +33,7 @@ adamw_multi_kernel(const void* const* __restrict__ ptrs, const long long* __rest
   const float wd = __int_as_float((int)meta[4 * t + 1]);
   const bool g_bf16 = meta[4 * t + 2] != 0;
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], omb1 = hyper[4], omb2 = hyper[5],
-              gscale = hyper[6];
+              gscale = hyper[6], lr_decay = hyper[7];
   const long long end = min(n, off + AW_CHUNK);
   const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) |
                          reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(g)) & 15) == 0 &&
@@ -53,10 +53,10 @@ adamw_multi_kernel(const void* const* __restrict__ ptrs, const long long* __rest
       } else {
         gv = *reinterpret_cast<const float4*>((const float*)g + i);
       }
-      adamw_elem(pv.x, gv.x * gscale, mv.x, vv.x, lr, b1, b2, eps, omb1, omb2, wd);
-      adamw_elem(pv.y, gv.y * gscale, mv.y, vv.y, lr, b1, b2, eps, omb1, omb2, wd);
-      adamw_elem(pv.z, gv.z * gscale, mv.z, vv.z, lr, b1, b2, eps, omb1, omb2, wd);
-      adamw_elem(pv.w, gv.w * gscale, mv.w, vv.w, lr, b1, b2, eps, omb1, omb2, wd);
+      adamw_elem(pv.x, gv.x * gscale, mv.x, vv.x, lr, b1, b2, eps, omb1, omb2, wd, lr_decay);
+      adamw_elem(pv.y, gv.y * gscale, mv.y, vv.y, lr, b1, b2, eps, omb1, omb2, wd, lr_decay);
+      adamw_elem(pv.z, gv.z * gscale, mv.z, vv.z, lr, b1, b2, eps, omb1, omb2, wd, lr_decay);
+      adamw_elem(pv.w, gv.w * gscale, mv.w, vv.w, lr, b1, b2, eps, omb1, omb2, wd, lr_decay);
       *reinterpret_cast<float4*>(p + i) = pv;
       *reinterpret_cast<float4*>(m + i) = mv;
       *reinterpret_cast<float4*>(v + i) = vv;
@@ -71,7 +71,7 @@ adamw_multi_kernel(const void* const* __restrict__ ptrs, const long long* __rest
     for (long long i = off + threadIdx.x; i < end; i += AW_THREADS) {
       float pv = p[i], mv = m[i], vv = v[i];
       const float gv = (g_bf16 ? __bfloat162float(((const bf16*)g)[i]) : ((const float*)g)[i]) * gscale;
-      adamw_elem(pv, gv, mv, vv, lr, b1, b2, eps, omb1, omb2, wd);
+      adamw_elem(pv, gv, mv, vv, lr, b1, b2, eps, omb1, omb2, wd, lr_decay);
       p[i] = pv; m[i] = mv; v[i] = vv;
       if (sh != nullptr) sh[i] = __float2bfloat16(pv);
     }

@@ -1,0 +1,374 @@
+"""Fusion-model engine: explicit forward / backward of the LR2PPO fusion network as a fixed sequence of
+C-ABI kernel launches on bf16 activations (fp32 master weights, bf16 shadow weights, fp32 gradients).
+
+It runs the computation of the reference's Actor / Critic / Reward / Classifier forward
+(finetune/ppo.py:214-244, 265-297, 318-350; finetune/pointwise.py:207-236;
+finetune/reward_pair_dataloader.py:251-283) and of torch autograd's backward through them:
+
+    text_proj, img_proj (Mlp)      -> tcgen05 GEMM + bias + erf-GELU epilogues
+    XiT block                      -> LayerNorm kernels, Q/K/V/O GEMMs, tiny-KV attention kernel,
+                                      FFN GEMMs with GELU / dropout / residual epilogues
+    cat + out_layer (162816->3072) -> the final LayerNorm writes straight into the concat buffer;
+                                      fc1 is a swapped, split-K, transposed-output GEMM that streams
+                                      the 1 GB bf16 weight once
+    pos_emb + xitt + head          -> same kernels on [bs, T<=4] tokens
+
+Nothing here computes on the host and there is no fallback path.
+"""
+import math
+
+import torch
+
+from . import ops
+from .ops import EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_DROP_RES, EPI_DGELU, EPI_ADD
+
+bf16 = torch.bfloat16
+f32 = torch.float32
+
+XIT_HEADS = 8          # finetune/xit.py:114 (num_heads default)
+XIT_DROP = 0.1         # finetune/xit.py:26,28 (drop_p, forward_drop_p)
+LN_EPS = 1e-5          # nn.LayerNorm default
+
+
+class ShadowBank:
+    """bf16 copies of fp32 parameters, re-cast when the parameter was modified through torch
+    (tracked with Tensor._version); FusedAdamW refreshes them in place itself."""
+
+    def __init__(self):
+        self._sh = {}
+
+    def get(self, p):
+        ent = self._sh.get(id(p))
+        if ent is None or ent[1] != p._version or ent[2] != p.data_ptr():
+            sh = ent[0] if ent is not None and ent[0].shape == p.shape and ent[0].device == p.device else \
+                torch.empty(p.shape, dtype=bf16, device=p.device)
+            ops.to_bf16(p.detach().contiguous(), out=sh)
+            ent = (sh, p._version, p.data_ptr())
+            self._sh[id(p)] = ent
+        return ent[0]
+
+    def items(self):
+        return self._sh.items()
+
+
+class _Lin:
+    """weight [out, in] (bf16 shadow) + fp32 bias of one nn.Linear."""
+
+    def __init__(self, bank, lin):
+        self.mod = lin
+        self.w = bank.get(lin.weight)
+        self.b = lin.bias.detach()
+
+
+def _grad_buf(p):
+    """fp32 gradient buffer of parameter p, and beta (1 = accumulate into an existing .grad)."""
+    if p.grad is None:
+        p.grad = torch.empty_like(p, memory_format=torch.contiguous_format)
+        return p.grad, 0.0
+    return p.grad, 1.0
+
+
+class _GradSink:
+    """Tracks which parameters already received a gradient during one backward call."""
+
+    def __init__(self):
+        self.fresh = set()
+
+    def buf(self, p):
+        if p.grad is None:
+            p.grad = torch.empty_like(p, memory_format=torch.contiguous_format)
+            self.fresh.add(id(p))
+            return p.grad, 0.0
+        if id(p) in self.fresh:  # allocated in this call but already written -> accumulate
+            return p.grad, 1.0
+        return p.grad, 1.0
+
+    def put_vec(self, p, val):
+        """val: fp32 tensor shaped like p (small vectors: biases, LayerNorm params, head)."""
+        if p.grad is None:
+            p.grad = val.reshape(p.shape).clone()
+        else:
+            p.grad.add_(val.reshape(p.shape))
+
+
+def _wgrad(sink, lin, dy, x):
+    """dW[out,in] (+)= dy[M,out]^T @ x[M,in]; db (+)= colsum(dy).  Both operands MN-major -> no transposes."""
+    gw, beta = sink.buf(lin.weight)
+    m_out, k_in = lin.weight.shape
+    rows = dy.shape[0]
+    # few output tiles and a long reduction -> split-K to fill the SMs
+    tiles = ((m_out + 127) // 128) * ((k_in + 127) // 128)
+    splits = 1
+    if beta == 0.0 and tiles < 120 and rows >= 1024:
+        splits = max(1, min(16, 148 // tiles, rows // 512))
+    ops.gemm(dy, x, a_mn=True, b_mn=True, out=gw, beta=beta, splits=splits)
+    sink.put_vec(lin.bias, ops.colsum(dy))
+
+
+def _dgrad(dy, lin_w, **kw):
+    """dx[M,in] = dy[M,out] @ W[out,in]   (W is the MN-major B operand)."""
+    return ops.gemm(dy, lin_w, b_mn=True, **kw)
+
+
+class XitWeights:
+    def __init__(self, bank, xit):
+        blk = xit[0][0]
+        att_seq, ffn_seq = blk[0].fn, blk[1].fn
+        self.lnb = att_seq[0]
+        mha = att_seq[1]
+        self.mha = mha
+        self.heads = mha.num_heads
+        self.emb = mha.emb_size
+        self.q, self.k, self.v, self.o = (_Lin(bank, m) for m in (mha.queries, mha.keys, mha.values, mha.projection))
+        self.ln2 = ffn_seq[0]
+        self.f1, self.f2 = _Lin(bank, ffn_seq[1][0]), _Lin(bank, ffn_seq[1][3])
+        self.ln3 = xit[1][0]
+        self.p_att = att_seq[2].p
+        self.p_ffn_in = ffn_seq[1][2].p
+        self.p_ffn_out = ffn_seq[2].p
+
+
+def xit_forward(W, x, y, items, Sq, Skv, train, seed, site_base, save, out=None, regroup=None):
+    """XiT block on x [items*Sq, E] (queries) and y [items*Skv, E] (keys/values).
+    ref: finetune/xit.py:9-148.  Returns (output or `out`, ctx)."""
+    E = W.emb
+    p1 = W.p_att if train else 0.0
+    p2 = W.p_ffn_in if train else 0.0
+    p3 = W.p_ffn_out if train else 0.0
+    lx, st_x = ops.layernorm_fwd(x, W.lnb.ln_x.weight.detach(), W.lnb.ln_x.bias.detach(), W.lnb.ln_x.eps, 0,
+                                 want_stats=save)
+    ly, st_y = ops.layernorm_fwd(y, W.lnb.ln_y.weight.detach(), W.lnb.ln_y.bias.detach(), W.lnb.ln_y.eps, 0,
+                                 want_stats=save)
+    q = ops.gemm(lx, W.q.w, epilogue=EPI_BIAS, bias=W.q.b)
+    k = ops.gemm(ly, W.k.w, epilogue=EPI_BIAS, bias=W.k.b)
+    v = ops.gemm(ly, W.v.w, epilogue=EPI_BIAS, bias=W.v.b)
+    post = 1.0 / math.sqrt(E)     # softmax first, then / sqrt(emb): finetune/xit.py:142-143
+    a = ops.xattn_fwd(q.view(items, Sq, E), k.view(items, Skv, E), v.view(items, Skv, E), W.heads, 1.0, post)
+    a = a.view(items * Sq, E)
+    x1 = ops.gemm(a, W.o.w, epilogue=EPI_BIAS_DROP_RES, bias=W.o.b, aux=x, drop_p=p1, seed=seed, site=site_base + 1)
+    l2, st2 = ops.layernorm_fwd(x1, W.ln2.weight.detach(), W.ln2.bias.detach(), W.ln2.eps, 0, want_stats=save)
+    pre2 = torch.empty((items * Sq, W.f1.w.shape[0]), dtype=bf16, device=x.device) if save else None
+    h2 = ops.gemm(l2, W.f1.w, epilogue=EPI_BIAS_GELU, bias=W.f1.b, c2=pre2, drop_p=p2, seed=seed, site=site_base + 2)
+    x2 = ops.gemm(h2, W.f2.w, epilogue=EPI_BIAS_DROP_RES, bias=W.f2.b, aux=x1, drop_p=p3, seed=seed,
+                  site=site_base + 3)
+    xo, st3 = ops.layernorm_fwd(x2, W.ln3.weight.detach(), W.ln3.bias.detach(), W.ln3.eps, 0, out=out,
+                                regroup=regroup, want_stats=save)
+    ctx = None
+    if save:
+        ctx = dict(x=x, y=y, lx=lx, ly=ly, st_x=st_x, st_y=st_y, q=q, k=k, v=v, a=a, x1=x1, st2=st2, l2=l2,
+                   pre2=pre2, h2=h2, x2=x2, st3=st3, p=(p1, p2, p3), seed=seed, site_base=site_base,
+                   dims=(items, Sq, Skv), regroup=regroup)
+    return xo, ctx
+
+
+def xit_backward(W, ctx, dout, sink, need_dx=True, need_dy=True, dy_extra=None):
+    """Backward of xit_forward.  dout: gradient wrt the block output (row-regrouped like the output).
+    Returns (dx, dy): gradients wrt the query-side and key/value-side inputs (dy includes dy_extra)."""
+    items, Sq, Skv = ctx["dims"]
+    E = W.emb
+    p1, p2, p3 = ctx["p"]
+    seed, sb = ctx["seed"], ctx["site_base"]
+    post = 1.0 / math.sqrt(E)
+    # final LayerNorm; dx2m = gradient into the (dropout-ed) FFN output
+    dx2, dx2m, dg, db = ops.layernorm_bwd(dout, ctx["x2"], W.ln3.weight.detach(), ctx["st3"], W.ln3.eps, 0,
+                                          regroup=ctx["regroup"], drop_p=p3, seed=seed, site=sb + 3,
+                                          want_masked=True)
+    sink.put_vec(W.ln3.weight, dg); sink.put_vec(W.ln3.bias, db)
+    # FFN
+    _wgrad(sink, W.f2.mod, dx2m, ctx["h2"])
+    dh2p = _dgrad(dx2m, W.f2.w, epilogue=EPI_DGELU, aux=ctx["pre2"], drop_p=p2, seed=seed, site=sb + 2)
+    _wgrad(sink, W.f1.mod, dh2p, ctx["l2"])
+    dl2 = _dgrad(dh2p, W.f1.w)
+    dx1, dx1m, dg, db = ops.layernorm_bwd(dl2, ctx["x1"], W.ln2.weight.detach(), ctx["st2"], W.ln2.eps, 0, add=dx2,
+                                          drop_p=p1, seed=seed, site=sb + 1, want_masked=True)
+    sink.put_vec(W.ln2.weight, dg); sink.put_vec(W.ln2.bias, db)
+    # attention
+    _wgrad(sink, W.o.mod, dx1m, ctx["a"])
+    da = _dgrad(dx1m, W.o.w)
+    dq, dk, dv = ops.xattn_bwd(ctx["q"].view(items, Sq, E), ctx["k"].view(items, Skv, E),
+                               ctx["v"].view(items, Skv, E), da.view(items, Sq, E), W.heads, 1.0, post)
+    dq = dq.view(items * Sq, E); dk = dk.view(items * Skv, E); dv = dv.view(items * Skv, E)
+    _wgrad(sink, W.q.mod, dq, ctx["lx"])
+    _wgrad(sink, W.k.mod, dk, ctx["ly"])
+    _wgrad(sink, W.v.mod, dv, ctx["ly"])
+    dxin = dyin = None
+    if need_dy:
+        dly = _dgrad(dk, W.k.w)
+        dly = _dgrad(dv, W.v.w, epilogue=EPI_ADD, aux=dly)
+        dyin, _, dg, db = ops.layernorm_bwd(dly, ctx["y"], W.lnb.ln_y.weight.detach(), ctx["st_y"], W.lnb.ln_y.eps, 0,
+                                            add=dy_extra)
+    else:
+        dly = _dgrad(dk, W.k.w)
+        dly = _dgrad(dv, W.v.w, epilogue=EPI_ADD, aux=dly)
+        _, _, dg, db = ops.layernorm_bwd(dly, ctx["y"], W.lnb.ln_y.weight.detach(), ctx["st_y"], W.lnb.ln_y.eps, 0)
+    sink.put_vec(W.lnb.ln_y.weight, dg); sink.put_vec(W.lnb.ln_y.bias, db)
+    dlx = _dgrad(dq, W.q.w)
+    dxin, _, dg, db = ops.layernorm_bwd(dlx, ctx["x"], W.lnb.ln_x.weight.detach(), ctx["st_x"], W.lnb.ln_x.eps, 0,
+                                        add=dx1)
+    sink.put_vec(W.lnb.ln_x.weight, dg); sink.put_vec(W.lnb.ln_x.bias, db)
+    return dxin, dyin
+
+
+def mlp_forward(l1, l2, x, save):
+    """Mlp: fc2(gelu(fc1 x)).  ref: finetune/ppo.py:164-170 (drop p = 0)."""
+    pre = torch.empty((x.shape[0], l1.w.shape[0]), dtype=bf16, device=x.device) if save else None
+    h = ops.gemm(x, l1.w, epilogue=EPI_BIAS_GELU, bias=l1.b, c2=pre)
+    y = ops.gemm(h, l2.w, epilogue=EPI_BIAS, bias=l2.b)
+    return y, (x, pre, h) if save else None
+
+
+def mlp_backward(l1, l2, ctx, dy, sink, need_dx=False):
+    x, pre, h = ctx
+    _wgrad(sink, l2.mod, dy, h)
+    dhp = _dgrad(dy, l2.w, epilogue=EPI_DGELU, aux=pre)
+    _wgrad(sink, l1.mod, dhp, x)
+    return _dgrad(dhp, l1.w) if need_dx else None
+
+
+class FusionEngine:
+    """Forward / backward of one fusion model (`kind` in actor | critic): `module` supplies the fp32
+    parameters under the reference's attribute names (text_proj, img_proj, xit, out_layer, head
+    [, pos_emb, xitt])."""
+
+    def __init__(self, module, kind):
+        self.m = module
+        self.kind = kind
+        self.bank = ShadowBank()
+        self._calls = 0
+
+    # weights are re-wrapped per call (cheap) so that parameter updates are always seen
+    def _weights(self):
+        m, bank = self.m, self.bank
+        W = dict(tp1=_Lin(bank, m.text_proj.fc1), tp2=_Lin(bank, m.text_proj.fc2),
+                 ip1=_Lin(bank, m.img_proj.fc1), ip2=_Lin(bank, m.img_proj.fc2),
+                 xit=XitWeights(bank, m.xit), o1=_Lin(bank, m.out_layer.fc1), o2=_Lin(bank, m.out_layer.fc2))
+        if self.kind == "critic":
+            W["xitt"] = XitWeights(bank, m.xitt)
+        return W
+
+    def forward(self, text, img, index=None, train=False, save=False, seed=None):
+        """text [bs, Tsrc, S, E] fp32, img [bs, Tsrc, I, E] fp32, index [bs, T] int64 or None.
+        Returns (logits fp32, ctx).  actor: logits [bs*T, n_out]; critic: [bs]."""
+        m = self.m
+        W = self._weights()
+        bs, Tsrc, S, E = text.shape
+        I = img.shape[2]
+        T = index.shape[1] if index is not None else Tsrc
+        items = bs * T
+        if seed is None:
+            self._calls += 1
+            seed = (torch.initial_seed() * 1000003 + self._calls) & 0x7FFFFFFFFFFFFFFF
+        xt = ops.cast_gather(text.reshape(bs, Tsrc, S * E), index).view(items * S, E)
+        xi = ops.cast_gather(img.reshape(bs, Tsrc, I * E), index).view(items * I, E)
+        tf, c_tp = mlp_forward(W["tp1"], W["tp2"], xt, save)
+        imf, c_ip = mlp_forward(W["ip1"], W["ip2"], xi, save)
+        cat = torch.empty((items, (S + I) * E), dtype=bf16, device=text.device)
+        cat_rows = cat.view(items * (S + I), E)
+        _, c_x = xit_forward(W["xit"], tf, imf, items, S, I, train, seed, 0, save, out=cat_rows,
+                             regroup=(S, S + I, 0))
+        ops.rows_copy(imf, I, 0, cat_rows, S + I, S, items, I, E)
+        # out_layer.fc1: weight is the 128-row MMA operand, items are N; split-K streams the weight once
+        o1 = W["o1"]
+        hid = o1.w.shape[0]
+        pre3 = torch.empty((items, hid), dtype=bf16, device=text.device) if save else None
+        if items <= 256:
+            bn = 64 if items <= 64 else (128 if items <= 128 else 256)
+            kblocks = (cat.shape[1] + 63) // 64
+            m_tiles = (hid + 127) // 128
+            splits = max(1, min(kblocks, 148 // m_tiles))
+            y1 = torch.empty((items, hid), dtype=bf16, device=text.device)
+            ops.gemm(o1.w, cat, out=y1, transposed_out=True, epilogue=EPI_BIAS_GELU, bias=o1.b, c2=pre3,
+                     splits=splits, block_n=bn)
+        else:
+            y1 = ops.gemm(cat, o1.w, epilogue=EPI_BIAS_GELU, bias=o1.b, c2=pre3, splits=4)
+        feat = ops.gemm(y1, W["o2"].w, epilogue=EPI_BIAS, bias=W["o2"].b)
+        ctx = None
+        if self.kind == "actor":
+            n_out = m.head.weight.shape[0]
+            if n_out == 1:
+                logits = ops.rowdot_fwd(feat, m.head.weight.detach().view(-1), m.head.bias.detach(), items)
+            else:
+                logits = _small_linear(feat, m.head, self.bank)
+            if save:
+                ctx = dict(W=W, dims=(bs, T, S, I, E, items), c_tp=c_tp, c_ip=c_ip, c_x=c_x, cat=cat, pre3=pre3,
+                           y1=y1, feat=feat, imf=imf)
+            return logits, ctx
+        # critic / reward: + pos_emb, self-attention over the T items, head on the LAST token
+        ops.add_pos_fwd(feat, m.pos_emb.weight.detach()[:T].contiguous(), bs, T)
+        z, c_t = xit_forward(W["xitt"], feat, feat, bs, T, T, train, seed, 3, save)
+        logits = ops.rowdot_fwd(z, m.head.weight.detach().view(-1), m.head.bias.detach(), bs, T, T - 1)
+        if save:
+            ctx = dict(W=W, dims=(bs, T, S, I, E, items), c_tp=c_tp, c_ip=c_ip, c_x=c_x, cat=cat, pre3=pre3, y1=y1,
+                       feat=feat, imf=imf, c_t=c_t, z=z)
+        return logits, ctx
+
+    def backward(self, ctx, dlogits):
+        """Accumulates fp32 gradients into module.parameters().grad (allocating when None)."""
+        m = self.m
+        W = ctx["W"]
+        bs, T, S, I, E, items = ctx["dims"]
+        sink = _GradSink()
+        dlogits = dlogits.contiguous().to(f32)
+        if self.kind == "actor":
+            if m.head.weight.shape[0] == 1:
+                dfeat, dw, dbias = ops.rowdot_bwd(ctx["feat"], m.head.weight.detach().view(-1), dlogits.view(-1),
+                                                  items)
+                sink.put_vec(m.head.weight, dw); sink.put_vec(m.head.bias, dbias)
+            else:
+                dfeat = _small_linear_bwd(ctx["feat"], m.head, self.bank, dlogits.view(items, -1), sink)
+        else:
+            dz, dw, dbias = ops.rowdot_bwd(ctx["z"], m.head.weight.detach().view(-1), dlogits.view(-1), bs, T, T - 1)
+            sink.put_vec(m.head.weight, dw); sink.put_vec(m.head.bias, dbias)
+            dxa, dya = xit_backward(W["xitt"], ctx["c_t"], dz, sink)
+            # x == y for xitt: total input gradient = dxa + dya
+            dfeat = ops.gemm_free_add(dxa, dya) if False else _add_bf16(dxa, dya)
+            dpos = ops.add_pos_bwd(dfeat, bs, T)
+            gp = torch.zeros_like(m.pos_emb.weight)
+            gp[:T] = dpos
+            sink.put_vec(m.pos_emb.weight, gp)
+        # out_layer
+        _wgrad(sink, W["o2"].mod, dfeat, ctx["y1"])
+        dy1p = _dgrad(dfeat, W["o2"].w, epilogue=EPI_DGELU, aux=ctx["pre3"])
+        _wgrad(sink, W["o1"].mod, dy1p, ctx["cat"])
+        dcat = torch.empty_like(ctx["cat"])
+        if items <= 256:
+            bn = 64 if items <= 64 else (128 if items <= 128 else 256)
+            # dcat^T[K1, items] = W1^T[K1, hid] @ dy1p^T : W1 is the MN-major A operand, output written transposed
+            ops.gemm(W["o1"].w, dy1p, a_mn=True, out=dcat, transposed_out=True, block_n=bn)
+        else:
+            ops.gemm(dy1p, W["o1"].w, b_mn=True, out=dcat)
+        dcat_rows = dcat.view(items * (S + I), E)
+        dimf = torch.empty((items * I, E), dtype=bf16, device=dcat.device)
+        ops.rows_copy(dcat_rows, S + I, S, dimf, I, 0, items, I, E)
+        dtf, dimf = xit_backward(W["xit"], ctx["c_x"], dcat_rows, sink, dy_extra=dimf)
+        mlp_backward(W["tp1"], W["tp2"], ctx["c_tp"], dtf, sink)
+        mlp_backward(W["ip1"], W["ip2"], ctx["c_ip"], dimf, sink)
+
+
+def _add_bf16(a, b):
+    """a + b for two bf16 [rows, D] tensors through the grouped row-copy kernel (accumulate mode)."""
+    out = a.clone()
+    rows, D = a.shape
+    ops.rows_copy(b, rows, 0, out, rows, 0, 1, rows, D, accumulate=True)
+    return out
+
+
+def _small_linear(x, lin, bank):
+    """n_out > 1 heads (mode 'cls': 768 -> 3): one rowdot per output."""
+    outs = [ops.rowdot_fwd(x, lin.weight.detach()[j].contiguous(), lin.bias.detach()[j:j + 1].contiguous(),
+                           x.shape[0]) for j in range(lin.weight.shape[0])]
+    return torch.stack(outs, dim=1)
+
+
+def _small_linear_bwd(x, lin, bank, dlogits, sink):
+    n_out = lin.weight.shape[0]
+    dx = None
+    gw = torch.empty_like(lin.weight)
+    gb = torch.empty_like(lin.bias)
+    for j in range(n_out):
+        dxj, dw, dbias = ops.rowdot_bwd(x, lin.weight.detach()[j].contiguous(), dlogits[:, j].contiguous(), x.shape[0])
+        gw[j] = dw
+        gb[j] = dbias[0]
+        dx = dxj if dx is None else _add_bf16(dx, dxj)
+    sink.put_vec(lin.weight, gw); sink.put_vec(lin.bias, gb)
+    return dx

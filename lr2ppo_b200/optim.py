@@ -1,0 +1,164 @@
+"""AdamW + LR schedules with the reference's API (tencentpretrain/utils/optimizers.py:62-86, 305-402),
+running as ONE multi-tensor CUDA launch per parameter group (lr2_adamw_multi).
+
+`FusedAdamW(params, lr, betas, eps, weight_decay, correct_bias)` takes the same arguments and
+param-group dicts as the reference AdamW, is a torch.optim.Optimizer (so LambdaLR schedulers work
+unchanged), keeps `exp_avg` / `exp_avg_sq` per parameter, and can refresh bf16 shadow copies of the
+weights (read by the GEMMs) in the same pass.
+"""
+import math
+import struct
+
+import torch
+from torch.optim import Optimizer
+from torch.optim.lr_scheduler import LambdaLR
+
+from . import _lib
+from ._lib import check
+
+
+def _f2i(x):
+    return struct.unpack("<i", struct.pack("<f", float(x)))[0]
+
+
+class FusedAdamW(Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True,
+                 shadow_bf16=False, grad_scale=1.0):
+        if lr < 0.0:
+            raise ValueError("Invalid learning rate: {} - should be >= 0.0".format(lr))
+        if not 0.0 <= betas[0] < 1.0:
+            raise ValueError("Invalid beta parameter: {} - should be in [0.0, 1.0[".format(betas[0]))
+        if not 0.0 <= betas[1] < 1.0:
+            raise ValueError("Invalid beta parameter: {} - should be in [0.0, 1.0[".format(betas[1]))
+        if not 0.0 <= eps:
+            raise ValueError("Invalid epsilon value: {} - should be >= 0.0".format(eps))
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, correct_bias=correct_bias)
+        super().__init__(params, defaults)
+        self._shadow = shadow_bf16
+        self.grad_scale = grad_scale
+        self._tables = {}      # group index -> dict
+        self._shadows = {}     # id(p) -> bf16 tensor (may be registered externally)
+        self._grad_src = {}    # id(p) -> tensor used as gradient instead of p.grad (e.g. bf16 wgrad buffers)
+
+    # -- extras -----------------------------------------------------------
+    def register_shadow(self, p, shadow):
+        """Use `shadow` (bf16, same shape) as the low-precision copy refreshed at every step."""
+        self._shadows[id(p)] = shadow
+        self._tables.clear()
+
+    def register_grad(self, p, grad):
+        """Read the gradient of `p` from `grad` (fp32 or bf16 buffer owned by the caller)."""
+        self._grad_src[id(p)] = grad
+        self._tables.clear()
+
+    def shadow_of(self, p):
+        return self._shadows.get(id(p))
+
+    def state_for(self, p):
+        return self.state[p]
+
+    # -- internals --------------------------------------------------------
+    def _grad_of(self, p):
+        g = self._grad_src.get(id(p))
+        return g if g is not None else p.grad
+
+    def _build(self, gi, group):
+        L = _lib.load()
+        chunk = L.lr2_adamw_chunk_elems()
+        ps = [p for p in group["params"] if self._grad_of(p) is not None]
+        if not ps:
+            return None
+        dev = ps[0].device
+        ptrs, meta, chunks, gptrs = [], [], [], []
+        for t, p in enumerate(ps):
+            if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                raise _lib.Lr2Error("FusedAdamW needs contiguous fp32 CUDA parameters (no CPU fallback)")
+            st = self.state[p]
+            if len(st) == 0:
+                st["step"] = 0
+                st["exp_avg"] = torch.zeros_like(p.data)
+                st["exp_avg_sq"] = torch.zeros_like(p.data)
+            sh = self._shadows.get(id(p))
+            if sh is None and self._shadow:
+                sh = p.data.to(torch.bfloat16)
+                self._shadows[id(p)] = sh
+            g = self._grad_of(p)
+            if g.dtype not in (torch.float32, torch.bfloat16) or not g.is_contiguous() or g.numel() != p.numel():
+                raise _lib.Lr2Error("gradient must be contiguous fp32/bf16 of the parameter's size")
+            ptrs += [p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                     sh.data_ptr() if sh is not None else 0, 0]
+            meta += [p.numel(), _f2i(group["weight_decay"]), int(g.dtype == torch.bfloat16), 0]
+            gptrs.append(g.data_ptr())
+            for off in range(0, p.numel(), chunk):
+                chunks += [t, off]
+        tab = dict(params=ps, gptrs=gptrs, n_chunks=len(chunks) // 2,
+                   ptrs=torch.tensor(ptrs, dtype=torch.int64, device=dev),
+                   meta=torch.tensor(meta, dtype=torch.int64, device=dev),
+                   chunks=torch.tensor(chunks, dtype=torch.int64, device=dev),
+                   hyper=torch.zeros(8, dtype=torch.float32, device=dev), hyper_host=None)
+        return tab
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        L = _lib.load()
+        for gi, group in enumerate(self.param_groups):
+            tab = self._tables.get(gi)
+            if tab is not None:
+                cur = [self._grad_of(p) for p in tab["params"]]
+                if any(g is None for g in cur) or [g.data_ptr() for g in cur] != tab["gptrs"] or \
+                        len(tab["params"]) != sum(1 for p in group["params"] if self._grad_of(p) is not None):
+                    tab = None
+            if tab is None:
+                tab = self._build(gi, group)
+                self._tables[gi] = tab
+            if tab is None:
+                continue
+            beta1, beta2 = group["betas"]
+            lr = group["lr"]
+            step_size = lr
+            for p in tab["params"]:
+                self.state[p]["step"] += 1
+            if group["correct_bias"]:
+                t = self.state[tab["params"][0]]["step"]
+                step_size = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+            hv = (step_size, beta1, beta2, group["eps"], 1.0 - beta1, 1.0 - beta2, self.grad_scale, lr)
+            if tab["hyper_host"] != hv:
+                tab["hyper"].copy_(torch.tensor(hv, dtype=torch.float32))
+                tab["hyper_host"] = hv
+            check(L.lr2_adamw_multi(tab["ptrs"].data_ptr(), tab["meta"].data_ptr(), tab["chunks"].data_ptr(),
+                                    tab["n_chunks"], tab["hyper"].data_ptr(), _lib.stream()), "lr2_adamw_multi")
+        return loss
+
+
+AdamW = FusedAdamW
+
+
+def get_linear_schedule_with_warmup(optimizer, num_warmup_steps, num_training_steps, last_epoch=-1):
+    """ref: tencentpretrain/utils/optimizers.py:62-86 (LambdaLR; lambda(0) is applied at construction)."""
+    def lr_lambda(current_step):
+        if current_step < num_warmup_steps:
+            return float(current_step) / float(max(1, num_warmup_steps))
+        return max(0.0, float(num_training_steps - current_step) /
+                   float(max(1, num_training_steps - num_warmup_steps)))
+    return LambdaLR(optimizer, lr_lambda, last_epoch)
+
+
+def get_constant_schedule(optimizer, last_epoch=-1):
+    return LambdaLR(optimizer, lambda _: 1, last_epoch=last_epoch)
+
+
+def get_constant_schedule_with_warmup(optimizer, num_warmup_steps, last_epoch=-1):
+    def lr_lambda(current_step):
+        if current_step < num_warmup_steps:
+            return float(current_step) / float(max(1.0, num_warmup_steps))
+        return 1.0
+    return LambdaLR(optimizer, lr_lambda, last_epoch=last_epoch)
+
+
+str2optimizer = {"adamw": FusedAdamW}
+str2scheduler = {"linear": get_linear_schedule_with_warmup, "constant": get_constant_schedule,
+                 "constant_with_warmup": get_constant_schedule_with_warmup}
