@@ -170,6 +170,13 @@ int lr2_ndcg_at_k(const float* scores, const long long* labels, const int* lens,
                   const long long* ks, int nk, const float* log2_table, float* ndcg, long long* order,
                   void* stream);
 
+/* Same arithmetic on two relevance lists that are ALREADY in rank order — the exact signature of
+ * AverageNDCGMeter.return_ndcg_at_k(predicted_relevance, true_relevances) (ref: ndcg.py:54-65).
+ * pred_rel, true_rel: [B, N] i64; scratch: 2*B*nk floats. */
+int lr2_ndcg_presorted(const long long* pred_rel, const long long* true_rel, const int* lens, int B, int N,
+                       const long long* ks, int nk, const float* log2_table, float* ndcg, float* scratch,
+                       void* stream);
+
 /* ---------------------------------------------------------------- AdamW --
  * HF-style AdamW without bias correction, decay applied after the Adam update with lr*wd.
  * ref: tencentpretrain/utils/optimizers.py:344-402.

@@ -122,3 +122,50 @@ extern "C" int lr2_ndcg_at_k(const float* scores, const long long* labels, const
                                                                             log2_table, ndcg, order, npad);
   LR2_RETURN_LAUNCH();
 }
+
+// Pre-sorted variant with the reference meter's own signature (ndcg.py:54-65): both relevance lists are
+// given in rank order; one thread per (query, list) runs the sequential fp32 DCG.
+namespace lr2 {
+__global__ void ndcg_presorted_kernel(const long long* __restrict__ pred, const long long* __restrict__ ideal,
+                                      const int* __restrict__ lens, int B, int N, const long long* __restrict__ ks,
+                                      int nk, const float* __restrict__ log2_table, float* __restrict__ ndcg,
+                                      float* __restrict__ scratch /* [B][2][nk] */) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 2 * B) {
+    const int q = t >> 1, which = t & 1;
+    const int n = lens ? min(lens[q], N) : N;
+    const long long* rel = (which ? ideal : pred) + (long long)q * N;
+    float* out = scratch + ((long long)q * 2 + which) * nk;
+    // ks need not be sorted: one sequential pass per k would be O(nk*N); instead walk once and
+    // record the running sum whenever i+1 equals a cut.
+    for (int j = 0; j < nk; ++j) out[j] = 0.f;
+    float acc = 0.f;
+    for (int i = 0; i < n; ++i) {
+      acc = acc + gain_of(rel[i]) / log2_table[i];
+      for (int j = 0; j < nk; ++j) {
+        const long long cut = ks[j] < (long long)n ? ks[j] : (long long)n;
+        if ((long long)(i + 1) == cut) out[j] = acc;
+      }
+    }
+  }
+}
+__global__ void ndcg_ratio_kernel(const float* __restrict__ scratch, int B, int nk, float* __restrict__ ndcg) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * nk) return;
+  const int q = t / nk, j = t % nk;
+  const float p = scratch[((long long)q * 2 + 0) * nk + j], i = scratch[((long long)q * 2 + 1) * nk + j];
+  ndcg[t] = (i <= 1e-6f) ? 1.0f : p / i;
+}
+}  // namespace lr2
+
+extern "C" int lr2_ndcg_presorted(const long long* pred_rel, const long long* true_rel, const int* lens, int B, int N,
+                                  const long long* ks, int nk, const float* log2_table, float* ndcg, float* scratch,
+                                  void* stream) {
+  if (B <= 0 || N <= 0 || nk <= 0 || scratch == nullptr) return LR2_ERR_BAD_SHAPE;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  lr2::ndcg_presorted_kernel<<<(2 * B + 63) / 64, 64, 0, s>>>(pred_rel, true_rel, lens, B, N, ks, nk, log2_table,
+                                                             ndcg, scratch);
+  if (cudaGetLastError() != cudaSuccess) return LR2_ERR_CUDA;
+  lr2::ndcg_ratio_kernel<<<(B * nk + 127) / 128, 128, 0, s>>>(scratch, B, nk, ndcg);
+  LR2_RETURN_LAUNCH();
+}

@@ -321,7 +321,7 @@ class FusionEngine:
             sink.put_vec(m.head.weight, dw); sink.put_vec(m.head.bias, dbias)
             dxa, dya = xit_backward(W["xitt"], ctx["c_t"], dz, sink)
             # x == y for xitt: total input gradient = dxa + dya
-            dfeat = ops.gemm_free_add(dxa, dya) if False else _add_bf16(dxa, dya)
+            dfeat = _add_bf16(dxa, dya)
             dpos = ops.add_pos_bwd(dfeat, bs, T)
             gp = torch.zeros_like(m.pos_emb.weight)
             gp[:T] = dpos

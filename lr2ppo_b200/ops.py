@@ -371,3 +371,17 @@ def ndcg_at_k(scores, labels, ks, lens=None, want_order=False):
     check(L.lr2_ndcg_at_k(ptr(scores), ptr(labels), ptr(lens), B, N, N, ptr(ks_t), len(ks), ptr(log2_table(N, dev)),
                           ptr(out), ptr(order), _lib.stream()), "lr2_ndcg_at_k")
     return (out, order) if want_order else out
+
+
+def ndcg_presorted(pred_rel, true_rel, ks, lens=None):
+    """pred_rel, true_rel i64 [B,N] already in rank order -> ndcg f32 [B, len(ks)] (ndcg.py:54-65)."""
+    L = _L()
+    _cuda(pred_rel, i64); _cuda(true_rel, i64)
+    B, N = pred_rel.shape
+    dev = pred_rel.device
+    ks_t = torch.tensor(list(ks), dtype=i64, device=dev)
+    out = torch.empty((B, len(ks)), dtype=f32, device=dev)
+    scratch = torch.empty(2 * B * len(ks), dtype=f32, device=dev)
+    check(L.lr2_ndcg_presorted(ptr(pred_rel), ptr(true_rel), ptr(lens), B, N, ptr(ks_t), len(ks),
+                               ptr(log2_table(N, dev)), ptr(out), ptr(scratch), _lib.stream()), "lr2_ndcg_presorted")
+    return out
