@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — LR2PPO stage-3 train step throughput (queries/s) on N B200s.
+
+  python bench.py --gpus 1 --steps 20 --warmup 5            (N>1: launched under torch.distributed.run)
+  python bench.py --impl reference --steps K --warmup W     (reference arm: CPU oracle port on the host cores)
+
+One "step" = one stage-3 LR2PPO batch of 24 (clip, tag-pair) queries per GPU (ppo.sh:21) taken through the
+whole hot path: rollout (actor + critic + sort/compose + reward model, finetune/ppo.py:845-883) AND update
+(actor/critic forward+backward, fused PPO losses, two AdamW steps over 519 M + 526 M parameters,
+finetune/ppo.py:518-587) — the amortised form of the reference's 200-rollout / 200-update cycle.
+Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BS, TAGS, SEQ, IMGS, FEAT = 24, 2, 196, 16, 768       # ppo.sh:21-24
+LR, CRITIC_LR = 1e-3, 1e-3                             # ppo.sh:27-28
+TRAIN_STEPS = 341301                                   # 273040 * 30 / 24 + 1 (finetune/ppo.py:796)
+FLOP_PER_QUERY = 107.5e9
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-steps", type=int, default=2)
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([c.strip() for c in line.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------ reference arm (CPU oracle port) ------
+def cpu_stage3(steps, warmup, budget_s, threads=None):
+    """Times oracle/stage3_ref.step on the host cores. Returns dict(value q/s, cores, sample, ms_per_step)."""
+    import torch
+    from oracle import stage3_ref
+    from tests import golden_util
+    cores = threads or os.cpu_count()
+    torch.set_num_threads(cores)
+    t0 = time.perf_counter()
+    actor = stage3_ref.RefModel(golden_util.make_state_dict("actor"))
+    critic = stage3_ref.RefModel(golden_util.make_state_dict("critic"))
+    reward = stage3_ref.RefModel(golden_util.make_state_dict("reward"), trainable=False)
+    build_s = time.perf_counter() - t0
+    g = torch.Generator().manual_seed(7)
+
+    def batch(bs):
+        text = torch.randn(bs, TAGS, SEQ, FEAT, generator=g)
+        img = torch.randn(bs, 1, IMGS, FEAT, generator=g).repeat(1, TAGS, 1, 1)
+        return text, img
+
+    lr = LR * (1.0 / (TRAIN_STEPS * 0.1))
+    # probe with the full batch; shrink the per-step sample if the run would exceed the budget
+    bs = BS
+    text, img = batch(bs)
+    t0 = time.perf_counter()
+    stage3_ref.step(actor, critic, reward, text, img, lr, lr)
+    probe = time.perf_counter() - t0
+    total = steps + max(0, warmup - 1)
+    while bs > 3 and probe * total * (0.35 + 0.65 * bs / BS) > budget_s:
+        bs //= 2
+    text, img = batch(bs)
+    for _ in range(max(0, warmup - 1)):
+        stage3_ref.step(actor, critic, reward, text, img, lr, lr)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        stage3_ref.step(actor, critic, reward, text, img, lr, lr)
+    dt = time.perf_counter() - t0
+    return {"value": bs * steps / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} stage-3 steps (rollout+update, full-size 519M/526M/526M-param fp32 models) of "
+                      f"{bs} queries each through oracle/stage3_ref.py (torch CPU fp32, {cores} threads); "
+                      f"model build {build_s:.0f}s not timed", "ms_per_step": dt / steps * 1e3, "bs": bs}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    r = cpu_stage3(args.steps, args.warmup, budget_s=240.0)
+    line = {"metric": "LR2PPO stage-3 train queries/sec", "value": r["value"], "unit": "queries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": "stage-3 LR2PPO step (rollout + update), LRMovieNet-shaped synthetic batch "
+                                   f"[{r['bs']},2,196,768]+[{r['bs']},2,16,768], CPU oracle port of the reference path",
+                       "queries_per_step": r["bs"]},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------- B200 arm -----------
+def build_models(torch, device):
+    import argparse as ap
+    from lr2ppo_b200 import ppo
+    margs = ap.Namespace(mode="reg", labels_num=3, seq_length=SEQ, max_imgs=IMGS, visual_feat_dim=FEAT)
+    with torch.device(device):
+        model = ppo.ActorCritic(margs, margs)
+        reward = ppo.Reward(margs, margs)
+    with torch.no_grad():
+        for m in (model, reward):
+            for n, p in m.named_parameters():          # finetune/ppo.py:363-365
+                if "gamma" not in n and "beta" not in n:
+                    p.normal_(0, 0.02)
+            # keep the pre-LN statistics sane for a throughput run: LayerNorm scales back to 1
+            for mod in m.modules():
+                if isinstance(mod, torch.nn.LayerNorm):
+                    mod.weight.fill_(1.0)
+    model.eval(); reward.eval()
+    return model, reward
+
+
+def summarize_profile(torch, prof, steps):
+    """Aggregate per-call CUDA-event durations by kernel family; pick the dominant one for the roofline."""
+    groups = {}
+    for name, a, e0, e1 in prof:
+        ms = e0.elapsed_time(e1)
+        key, work = name, 0.0
+        if name == "lr2_gemm_bf16":
+            M, N, K = a[10], a[11], a[12]
+            amn, bmn, tr = a[2], a[5], a[9]
+            kind = "wgrad" if (amn and bmn) else ("dgrad" if (bmn or (amn and tr)) else "fwd")
+            big = max(M, N, K) >= 100000
+            key = f"gemm_{'fc1_' if big else ''}{kind}"
+            work = 2.0 * M * N * K
+        g = groups.setdefault(key, {"ms": 0.0, "calls": 0, "work": 0.0})
+        g["ms"] += ms; g["calls"] += 1; g["work"] += work
+    for g in groups.values():
+        g["ms_per_step"] = g["ms"] / steps
+    return groups
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    from lr2ppo_b200 import _lib, ppo
+    from lr2ppo_b200.dist import GradSync
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.load().lr2_check_device(), "device")
+    torch.manual_seed(7 + rank)                                    # finetune/ppo.py:754 (seed + rank)
+    model, reward = build_models(torch, dev)
+    hp = argparse.Namespace(learning_rate=LR, critic_learning_rate=CRITIC_LR, optimizer="adamw", scheduler="linear",
+                            train_steps=TRAIN_STEPS, warmup=0.1, kl_div_loss_weight=0.001, entropy_weight=0.001,
+                            value_clip=0.5, mode="reg")
+    opt, copt, sch, csch = ppo.build_optimizer(hp, model)
+    sync = GradSync(world) if world > 1 else None
+    if sync is not None:
+        sync.broadcast_params(model)
+        sync.broadcast_params(reward)
+
+    # synthetic LRMovieNet-shaped batches in PINNED host memory (text 28.9 MB, img 2.4 MB, tgts 384 B each)
+    g = torch.Generator().manual_seed(100 + rank)
+    pool = []
+    for _ in range(4):
+        text = torch.randn(BS, TAGS, SEQ, FEAT, generator=g).pin_memory()
+        img = torch.randn(BS, 1, IMGS, FEAT, generator=g).repeat(1, TAGS, 1, 1).contiguous().pin_memory()
+        tgts = torch.randint(0, 3, (BS, TAGS), generator=g).pin_memory()
+        pool.append((text, img, tgts))
+    resident = [tuple(t.to(dev) for t in b) for b in pool]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in pool[0])
+    stats_host = torch.empty(10, dtype=torch.float32).pin_memory()
+
+    def step(batch):
+        text, img, tgts = batch
+        mem = ppo.rollout(model, reward, text, img, tgts)
+        model.train()                                              # update runs in train mode (dropout 0.1 live)
+        stats = ppo.update_batch(hp, model, opt, copt, mem, sync)
+        model.eval()
+        sch.step(); csch.step()
+        return stats
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0 = _lib.launch_count()
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms, _lib.launch_count() - c0
+
+    # ---- warm-up, then (1) device-resident timed region with clock sampling --------------------------------
+    for i in range(max(3, args.warmup)):
+        step(resident[i % len(resident)])
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(lambda i: step(resident[i % len(resident)]), args.steps)
+    if rank == 0:
+        sampler.stop_flag = True
+    value = world * BS * args.steps / (ms / 1e3)
+
+    # ---- (2) end-to-end: pinned host -> device every step, stats read back every step ---------------------
+    def e2e_step(i):
+        text, img, tgts = pool[i % len(pool)]
+        b = (text.to(dev, non_blocking=True), img.to(dev, non_blocking=True), tgts.to(dev, non_blocking=True))
+        stats = step(b)
+        stats_host.copy_(stats, non_blocking=False)                # D2H + host sync, as a training loop would log
+
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e, _ = timed(e2e_step, args.steps)
+    e2e = world * BS * args.steps / (ms_e2e / 1e3)
+
+    # ---- (3) per-kernel CUDA-event pass for the roofline of the dominant kernel ----------------------------
+    roofline, breakdown = None, None
+    if rank == 0 and args.profile_steps > 0:
+        torch.cuda.synchronize()
+        _lib.PROFILE = []
+        for i in range(args.profile_steps):
+            step(resident[i % len(resident)])
+        torch.cuda.synchronize()
+        prof, _lib.PROFILE = _lib.PROFILE, None
+        groups = summarize_profile(torch, prof, args.profile_steps)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
+        tf_peak, tf_src = (peaks["bf16_tflops_sustained"], "measured sustained") if "bf16_tflops_sustained" in peaks \
+            else (1400.0, "fallback sustained")
+        total_ms = sum(gp["ms_per_step"] for gp in groups.values())
+        top = max(groups, key=lambda k: groups[k]["ms"])
+        gp = groups[top]
+        n_params = sum(p.numel() for p in model.parameters())
+        if top == "lr2_adamw_multi":
+            # 28 B/param (p,g,m,v read; p,m,v write, fp32) + 2 B/param bf16 shadow for matrices
+            per_launch = 30.0 * n_params / gp["calls"] * args.profile_steps
+            ach = per_launch / (gp["ms"] / gp["calls"] * 1e-3) / 1e9
+            roofline = {"kernel": "adamw_multi_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+                        "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                        "share_of_step": gp["ms_per_step"] / total_ms,
+                        "algorithmic_bytes_per_launch": per_launch}
+        elif top.startswith("gemm"):
+            ach = gp["work"] / (gp["ms"] * 1e-3) / 1e12
+            roofline = {"kernel": f"gemm_kernel<{top}>", "bound": "tensor", "achieved": ach, "peak": tf_peak,
+                        "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None, "peak_source": tf_src,
+                        "share_of_step": gp["ms_per_step"] / total_ms}
+        else:
+            roofline = {"kernel": top, "bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": None, "traffic": None, "share_of_step": gp["ms_per_step"] / total_ms}
+        gemm_flops = sum(v["work"] for k, v in groups.items() if k.startswith("gemm"))
+        gemm_ms = sum(v["ms"] for k, v in groups.items() if k.startswith("gemm"))
+        breakdown = {k: {"ms_per_step": round(v["ms_per_step"], 4), "calls_per_step": v["calls"] / args.profile_steps,
+                         **({"tflops": round(v["work"] / (v["ms"] * 1e-3) / 1e12, 1)} if v["work"] else {})}
+                     for k, v in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])}
+        breakdown["_gemm_all"] = {"tflops": round(gemm_flops / (gemm_ms * 1e-3) / 1e12, 1) if gemm_ms else None,
+                                  "tensor_frac_of_" + tf_src.replace(" ", "_"): round(
+                                      gemm_flops / (gemm_ms * 1e-3) / 1e12 / tf_peak, 3) if gemm_ms else None}
+
+    # ---- (4) CPU baseline (oracle port) on rank 0, N=1 only -------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        del resident
+        torch.cuda.empty_cache()
+        r = cpu_stage3(steps=2, warmup=1, budget_s=60.0)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {"metric": "LR2PPO stage-3 train queries/sec", "value": value, "unit": "queries/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": "configs[3]: stage-3 full LR2PPO step (label-ranking rollout, reward scoring, "
+                                       "advantage, fused policy/value losses, 2x AdamW) on synthetic LRMovieNet-shaped "
+                                       "data; per-GPU batch 24 queries x 2 tags, text [24,2,196,768], img [24,2,16,768], "
+                                       "fusion models 519M (actor) + 526M (critic) + 526M (reward) params, bf16 compute "
+                                       "/ fp32 master weights + fp32 Adam state",
+                           "queries_per_step_per_gpu": BS, "parallelism": f"dp{world}",
+                           "l2": "per-step working set (3 GB bf16 weights + 29 GB optimizer traffic) >> 126 MB L2; "
+                                 "no explicit flush",
+                           "tflop_per_step_per_gpu": FLOP_PER_QUERY * BS / 1e12},
+                "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d_bytes * world,
+                        "d2h_bytes_per_step": 40 * world, "ms_per_step": ms_e2e / args.steps},
+                "gpu_launches": int(launches), "clocks": sampler.summary(),
+                "model_tflops_per_gpu": FLOP_PER_QUERY * BS * args.steps / (ms / 1e3) / 1e12}
+        if roofline is not None:
+            line["roofline"] = roofline
+            line["breakdown"] = breakdown
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

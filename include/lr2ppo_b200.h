@@ -46,6 +46,9 @@ int lr2_abi_version(void);
 const char* lr2_last_error_string(int code);
 /* 0 when the current device is compute capability 10.x, LR2_ERR_WRONG_ARCH otherwise. */
 int lr2_check_device(void);
+/* number of CUDA kernels this library has launched in the current process */
+long long lr2_launch_count(void);
+void lr2_note_launches(int n);
 
 /* ---------------------------------------------------------------- dense --
  * D[M,N] = A[M,K] * B[N,K]^T, bf16 x bf16 -> fp32 (tcgen05.mma, TMEM accumulators, TMA loads).

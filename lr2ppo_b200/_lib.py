@@ -21,6 +21,8 @@ SIGNATURES = {
     "lr2_abi_version": (i32, []),
     "lr2_last_error_string": (c_char_p, [i32]),
     "lr2_check_device": (i32, []),
+    "lr2_launch_count": (i64, []),
+    "lr2_note_launches": (None, [i32]),
     "lr2_gemm_workspace_bytes": (i64, [i32, i32, i32, i32, i64]),
     "lr2_gemm_bf16": (i32, [vp, i64, i32, vp, i64, i32, vp, i64, i32, i32, i32, i32, i32, i32, vp, vp, i64, vp,
                             f32, f32, u64, u32, i32, vp, i32, vp]),
@@ -83,6 +85,31 @@ def check(code, what=""):
     if code != 0:
         msg = load().lr2_last_error_string(code).decode()
         raise Lr2Error(f"{what}: error {code} ({msg})")
+
+
+# When PROFILE is a list, every C-ABI call is bracketed by CUDA events on the launching stream and
+# (name, args, start, end) is appended (bench.py's per-kernel roofline pass). None = no overhead.
+PROFILE = None
+
+
+def run(fn, *args):
+    """Call a C-ABI entry point, raise on a non-zero return code."""
+    if PROFILE is None:
+        code = fn(*args)
+    else:
+        import torch
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        code = fn(*args)
+        e1.record()
+        PROFILE.append((fn.__name__, args, e0, e1))
+    if code != 0:
+        check(code, fn.__name__)
+
+
+def launch_count():
+    return load().lr2_launch_count()
 
 
 def ptr(t):

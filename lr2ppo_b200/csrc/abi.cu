@@ -23,3 +23,8 @@ extern "C" int lr2_check_device(void) {
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return LR2_ERR_CUDA;
   return major == 10 ? LR2_OK : LR2_ERR_WRONG_ARCH;
 }
+
+#include <atomic>
+static std::atomic<long long> g_launches{0};
+extern "C" void lr2_note_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+extern "C" long long lr2_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

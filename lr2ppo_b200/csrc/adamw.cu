@@ -89,6 +89,6 @@ extern "C" int lr2_adamw_multi(const void* const* ptrs, const long long* meta, c
   if (num_chunks <= 0 || num_chunks > 2147483647LL) return LR2_ERR_BAD_SHAPE;
   if (ptrs == nullptr || meta == nullptr || chunks == nullptr || hyper == nullptr) return LR2_ERR_BAD_SHAPE;
   adamw_multi_kernel<<<(unsigned)num_chunks, AW_THREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(ptrs, meta,
-                                                                                                       chunks, hyper);
+                                                                                                       chunks, hyper); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }

@@ -14,6 +14,10 @@
     return e__ == cudaSuccess ? LR2_OK : LR2_ERR_CUDA;        \
   } while (0)
 
+// Every kernel launch is counted (bench.py reports the number inside its timed region).
+extern "C" void lr2_note_launches(int n);
+#define LR2_LAUNCHED(n) lr2_note_launches(n)
+
 namespace lr2 {
 
 typedef __nv_bfloat16 bf16;

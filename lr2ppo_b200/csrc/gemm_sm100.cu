@@ -520,7 +520,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
   const int total = m_tiles * n_tiles * p.splits;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, p);
+  gemm_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, p); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 
@@ -600,7 +600,7 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     int blocks = (int)((total + 255) / 256);
     const int cap = num_sms() * 8;
     if (blocks > cap) blocks = cap;
-    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p, out_rows, out_cols);
+    splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p, out_rows, out_cols); LR2_LAUNCHED(1);
     LR2_RETURN_LAUNCH();
   }
   return LR2_OK;

@@ -221,7 +221,7 @@ extern "C" int lr2_cast_gather_bf16(const float* src, const long long* index, vo
   if (index == nullptr && T_src != T_dst) return LR2_ERR_BAD_SHAPE;
   const long long total = (long long)bs * T_dst * (row_elems / 8);
   cast_gather_kernel<<<grid_for(total, 256), 256, 0, S_(stream)>>>(src, index, reinterpret_cast<bf16*>(dst), bs,
-                                                                    T_src, T_dst, row_elems);
+                                                                    T_src, T_dst, row_elems); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 
@@ -232,7 +232,7 @@ extern "C" int lr2_rows_copy_bf16(const void* src, long long src_gstride, long l
   const long long total = groups * rows_per_group * (D / 8);
   rows_copy_kernel<<<grid_for(total, 256), 256, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(src), src_gstride,
                                                                   src_off, reinterpret_cast<bf16*>(dst), dst_gstride,
-                                                                  dst_off, groups, rows_per_group, D, accumulate);
+                                                                  dst_off, groups, rows_per_group, D, accumulate); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 
@@ -246,9 +246,9 @@ extern "C" int lr2_colsum_bf16(const void* x, long long ldx, long long rows, int
   if (slabs > CS_SLABS) slabs = CS_SLABS;
   if (slabs < 1) slabs = 1;
   dim3 grid((cols + 255) / 256, slabs);
-  colsum_partial_kernel<<<grid, 256, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(x), ldx, rows, cols, partials);
+  colsum_partial_kernel<<<grid, 256, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(x), ldx, rows, cols, partials); LR2_LAUNCHED(1);
   if (cudaGetLastError() != cudaSuccess) return LR2_ERR_CUDA;
-  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, S_(stream)>>>(partials, slabs, cols, out, accumulate);
+  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, S_(stream)>>>(partials, slabs, cols, out, accumulate); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 
@@ -257,7 +257,7 @@ extern "C" int lr2_rowdot_fwd(const void* x, long long row_stride, long long row
   if (rows <= 0 || D <= 0 || D % 8 || row_stride <= 0 || row_off < 0 || row_off >= row_stride)
     return LR2_ERR_BAD_SHAPE;
   rowdot_fwd_kernel<<<(rows + 7) / 8, 256, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(x), row_stride, row_off, w,
-                                                             b, out, rows, D);
+                                                             b, out, rows, D); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 
@@ -268,12 +268,12 @@ extern "C" int lr2_rowdot_bwd(const void* x, long long row_stride, long long row
   if (dx != nullptr) {
     const long long total = (long long)rows * row_stride * (D / 8);
     rowdot_bwd_dx_kernel<<<grid_for(total, 256), 256, 0, S_(stream)>>>(w, dout, reinterpret_cast<bf16*>(dx),
-                                                                        row_stride, row_off, rows, D);
+                                                                        row_stride, row_off, rows, D); LR2_LAUNCHED(1);
     if (cudaGetLastError() != cudaSuccess) return LR2_ERR_CUDA;
   }
   if (dw != nullptr) {
     rowdot_bwd_dw_kernel<<<(D + 127) / 128, 128, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(x), row_stride,
-                                                                   row_off, dout, dw, db, rows, D);
+                                                                   row_off, dout, dw, db, rows, D); LR2_LAUNCHED(1);
   }
   LR2_RETURN_LAUNCH();
 }
@@ -281,22 +281,22 @@ extern "C" int lr2_rowdot_bwd(const void* x, long long row_stride, long long row
 extern "C" int lr2_add_pos_fwd(void* x, const float* pos, int bs, int T, int D, void* stream) {
   if (bs <= 0 || T <= 0 || D <= 0 || D % 8) return LR2_ERR_BAD_SHAPE;
   const long long total = (long long)bs * T * (D / 8);
-  add_pos_fwd_kernel<<<grid_for(total, 256), 256, 0, S_(stream)>>>(reinterpret_cast<bf16*>(x), pos, bs, T, D);
+  add_pos_fwd_kernel<<<grid_for(total, 256), 256, 0, S_(stream)>>>(reinterpret_cast<bf16*>(x), pos, bs, T, D); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 extern "C" int lr2_add_pos_bwd(const void* dx, float* dpos, int bs, int T, int D, void* stream) {
   if (bs <= 0 || T <= 0 || D <= 0) return LR2_ERR_BAD_SHAPE;
-  add_pos_bwd_kernel<<<(T * D + 255) / 256, 256, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(dx), dpos, bs, T, D);
+  add_pos_bwd_kernel<<<(T * D + 255) / 256, 256, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(dx), dpos, bs, T, D); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 extern "C" int lr2_cast_f32_to_bf16(const float* src, void* dst, long long n, void* stream) {
   if (n <= 0) return LR2_ERR_BAD_SHAPE;
   if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) return LR2_ERR_MISALIGNED;
-  cast_f32_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, S_(stream)>>>(src, reinterpret_cast<bf16*>(dst), n);
+  cast_f32_bf16_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, S_(stream)>>>(src, reinterpret_cast<bf16*>(dst), n); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 extern "C" int lr2_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream) {
   if (n <= 0) return LR2_ERR_BAD_SHAPE;
-  cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(src), dst, n);
+  cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(src), dst, n); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }

@@ -222,7 +222,7 @@ extern "C" int lr2_layernorm_fwd(const void* x, const float* gamma, const float*
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) return LR2_ERR_MISALIGNED;
   ln_fwd_kernel<<<ln_blocks(rows, 148 * 16), LN_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(x), gamma, beta, reinterpret_cast<bf16*>(y), stats, rows, D, eps, mode, g_in,
-      g_out, g_off);
+      g_out, g_off); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 
@@ -248,8 +248,8 @@ extern "C" int lr2_layernorm_bwd(const void* dy, const void* x, const float* gam
   ln_bwd_kernel<<<nb, LN_WARPS * 32, smem, s>>>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x),
                                                 gamma, stats, reinterpret_cast<const bf16*>(add),
                                                 reinterpret_cast<bf16*>(dx), reinterpret_cast<bf16*>(dxm), partials,
-                                                rows, D, eps, mode, g_in, g_out, g_off, drop_p, seed, site);
+                                                rows, D, eps, mode, g_in, g_out, g_off, drop_p, seed, site); LR2_LAUNCHED(1);
   if (cudaGetLastError() != cudaSuccess) return LR2_ERR_CUDA;
-  ln_bwd_reduce_kernel<<<(2 * D + 255) / 256, 256, 0, s>>>(partials, nb, D, dgamma, dbeta);
+  ln_bwd_reduce_kernel<<<(2 * D + 255) / 256, 256, 0, s>>>(partials, nb, D, dgamma, dbeta); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }

@@ -119,7 +119,7 @@ extern "C" int lr2_ndcg_at_k(const float* scores, const long long* labels, const
   if (threads > 512) threads = 512;
   if (threads < 64) threads = 64;
   ndcg_kernel<<<B, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(scores, labels, lens, N, ld, ks, nk,
-                                                                            log2_table, ndcg, order, npad);
+                                                                            log2_table, ndcg, order, npad); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 
@@ -164,8 +164,8 @@ extern "C" int lr2_ndcg_presorted(const long long* pred_rel, const long long* tr
   if (B <= 0 || N <= 0 || nk <= 0 || scratch == nullptr) return LR2_ERR_BAD_SHAPE;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   lr2::ndcg_presorted_kernel<<<(2 * B + 63) / 64, 64, 0, s>>>(pred_rel, true_rel, lens, B, N, ks, nk, log2_table,
-                                                             ndcg, scratch);
+                                                             ndcg, scratch); LR2_LAUNCHED(1);
   if (cudaGetLastError() != cudaSuccess) return LR2_ERR_CUDA;
-  lr2::ndcg_ratio_kernel<<<(B * nk + 127) / 128, 128, 0, s>>>(scratch, B, nk, ndcg);
+  lr2::ndcg_ratio_kernel<<<(B * nk + 127) / 128, 128, 0, s>>>(scratch, B, nk, ndcg); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }

@@ -307,43 +307,43 @@ extern "C" int lr2_ppo_policy_loss(const float* s, const float* s_old, const flo
                                    float* adv, float* ds, void* stream) {
   if (B <= 0 || n <= 0) return LR2_ERR_BAD_SHAPE;
   ppo_policy_loss_kernel<<<1, PL_THREADS, 0, S_(stream)>>>(s, s_old, reward, v_old, pi, B, n, w_kl, w_ent, margin,
-                                                           adv_eps, out_scalars, kl, ent, reward_adj, adv, ds);
+                                                           adv_eps, out_scalars, kl, ent, reward_adj, adv, ds); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 extern "C" int lr2_clipped_value_loss(const float* v, const float* ret, const float* v_old, int B, float clip,
                                       float* out_loss, float* dv, void* stream) {
   if (B <= 0) return LR2_ERR_BAD_SHAPE;
-  clipped_value_loss_kernel<<<1, PL_THREADS, 0, S_(stream)>>>(v, ret, v_old, B, clip, out_loss, dv);
+  clipped_value_loss_kernel<<<1, PL_THREADS, 0, S_(stream)>>>(v, ret, v_old, B, clip, out_loss, dv); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 extern "C" int lr2_pair_hinge_loss(const float* chosen, const float* reject, int B, float margin, float* out,
                                    float* dchosen, float* dreject, void* stream) {
   if (B <= 0) return LR2_ERR_BAD_SHAPE;
-  pair_hinge_kernel<<<1, PL_THREADS, 0, S_(stream)>>>(chosen, reject, B, margin, out, dchosen, dreject);
+  pair_hinge_kernel<<<1, PL_THREADS, 0, S_(stream)>>>(chosen, reject, B, margin, out, dchosen, dreject); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 extern "C" int lr2_smooth_l1_loss(const float* logits, const long long* tgt, long long n, float beta, float* out_loss,
                                   float* dlogits, void* stream) {
   if (n <= 0 || beta <= 0.f) return LR2_ERR_BAD_SHAPE;
-  smooth_l1_kernel<<<1, PL_THREADS, 0, S_(stream)>>>(logits, tgt, n, beta, out_loss, dlogits);
+  smooth_l1_kernel<<<1, PL_THREADS, 0, S_(stream)>>>(logits, tgt, n, beta, out_loss, dlogits); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 extern "C" int lr2_ppo_rollout(const float* scores, const long long* state, int B, int n, int n_prefix,
                                long long* next_state, long long* order, void* stream) {
   if (B <= 0 || n <= 0 || n_prefix < 0) return LR2_ERR_BAD_SHAPE;
-  ppo_rollout_kernel<<<(B + 127) / 128, 128, 0, S_(stream)>>>(scores, state, B, n, n_prefix, next_state, order);
+  ppo_rollout_kernel<<<(B + 127) / 128, 128, 0, S_(stream)>>>(scores, state, B, n, n_prefix, next_state, order); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 extern "C" int lr2_rank_sample(const float* scores, const float* u, int B, int n, int greedy, long long* perm,
                                float* logprob, void* stream) {
   if (B <= 0 || n <= 0) return LR2_ERR_BAD_SHAPE;
   if (!greedy && u == nullptr) return LR2_ERR_BAD_SHAPE;
-  rank_sample_kernel<<<(B + 127) / 128, 128, 0, S_(stream)>>>(scores, u, B, n, greedy, perm, logprob);
+  rank_sample_kernel<<<(B + 127) / 128, 128, 0, S_(stream)>>>(scores, u, B, n, greedy, perm, logprob); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 extern "C" int lr2_gae_scan(const float* rewards, const float* values, const float* notdone, int B, int T,
                             float gamma, float lam, float* adv, float* ret, void* stream) {
   if (B <= 0 || T <= 0) return LR2_ERR_BAD_SHAPE;
-  gae_scan_kernel<<<(B + 3) / 4, 128, 0, S_(stream)>>>(rewards, values, notdone, B, T, gamma, lam, adv, ret);
+  gae_scan_kernel<<<(B + 3) / 4, 128, 0, S_(stream)>>>(rewards, values, notdone, B, T, gamma, lam, adv, ret); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }

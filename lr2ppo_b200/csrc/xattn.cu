@@ -219,7 +219,7 @@ extern "C" int lr2_xattn_fwd(const void* q, long long ldq, const void* k, const 
   if (threads > 256) threads = 256;
   xattn_fwd_kernel<<<items * H, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(q), ldq, reinterpret_cast<const bf16*>(k), reinterpret_cast<const bf16*>(v),
-      ldkv, reinterpret_cast<bf16*>(o), ldo, Sq, Skv, H, dh, pre_scale, post_scale);
+      ldkv, reinterpret_cast<bf16*>(o), ldo, Sq, Skv, H, dh, pre_scale, post_scale); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 
@@ -244,6 +244,6 @@ extern "C" int lr2_xattn_bwd(const void* q, long long ldq, const void* k, const 
   xattn_bwd_kernel<<<items * H, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(
       reinterpret_cast<const bf16*>(q), ldq, reinterpret_cast<const bf16*>(k), reinterpret_cast<const bf16*>(v),
       ldkv, reinterpret_cast<const bf16*>(d_o), ldo, reinterpret_cast<bf16*>(dq), lddq, reinterpret_cast<bf16*>(dk),
-      reinterpret_cast<bf16*>(dv), lddkv, Sq, Skv, H, dh, pre_scale, post_scale);
+      reinterpret_cast<bf16*>(dv), lddkv, Sq, Skv, H, dh, pre_scale, post_scale); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }

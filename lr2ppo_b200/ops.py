@@ -82,10 +82,10 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=bf16, transposed_o
         raise _lib.Lr2Error("aux must be bf16 with unit inner stride")
     if c2 is not None and (c2.dtype != bf16 or c2.stride(-2) != ldc):
         raise _lib.Lr2Error("c2 must be bf16 with the same pitch as the output")
-    check(L.lr2_gemm_bf16(ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), ptr(out), ldc,
+    _lib.run(L.lr2_gemm_bf16, ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), ptr(out), ldc,
                           int(out.dtype == f32), int(transposed_out), M, N, K, epilogue, ptr(bias), ptr(aux),
                           aux.stride(-2) if aux is not None else 0, ptr(c2), float(beta), float(drop_p), int(seed),
-                          int(site), int(splits), ptr(ws), int(block_n), _lib.stream()), "lr2_gemm_bf16")
+                          int(site), int(splits), ptr(ws), int(block_n), _lib.stream())
     return out
 
 
@@ -99,8 +99,8 @@ def layernorm_fwd(x, gamma, beta, eps, mode=0, out=None, regroup=None, want_stat
     if out is None:
         out = torch.empty_like(x)
     stats = torch.empty((rows, 2), dtype=f32, device=x.device) if want_stats else None
-    check(L.lr2_layernorm_fwd(ptr(x), ptr(gamma), ptr(beta), ptr(out), ptr(stats), rows, D, float(eps), mode, g_in,
-                              g_out, g_off, _lib.stream()), "lr2_layernorm_fwd")
+    _lib.run(L.lr2_layernorm_fwd, ptr(x), ptr(gamma), ptr(beta), ptr(out), ptr(stats), rows, D, float(eps), mode, g_in,
+                              g_out, g_off, _lib.stream())
     return out, stats
 
 
@@ -117,9 +117,9 @@ def layernorm_bwd(dy, x, gamma, stats, eps, mode=0, add=None, regroup=None, drop
     dgamma = torch.empty(D, dtype=f32, device=x.device)
     dbeta = torch.empty(D, dtype=f32, device=x.device)
     part = _workspace(L.lr2_layernorm_bwd_partials_floats(D) * 4, x.device)
-    check(L.lr2_layernorm_bwd(ptr(dy), ptr(x), ptr(gamma), ptr(stats), ptr(add), ptr(dx), ptr(dxm), ptr(dgamma),
+    _lib.run(L.lr2_layernorm_bwd, ptr(dy), ptr(x), ptr(gamma), ptr(stats), ptr(add), ptr(dx), ptr(dxm), ptr(dgamma),
                               ptr(dbeta), ptr(part), rows, D, float(eps), mode, g_in, g_out, g_off, float(drop_p),
-                              int(seed), int(site), _lib.stream()), "lr2_layernorm_bwd")
+                              int(seed), int(site), _lib.stream())
     return dx, dxm, dgamma, dbeta
 
 
@@ -136,8 +136,8 @@ def xattn_fwd(q, k, v, H, pre_scale, post_scale):
     if k.stride(1) != v.stride(1):
         raise _lib.Lr2Error("k and v must share a pitch")
     o = torch.empty((items, Sq, E), dtype=bf16, device=q.device)
-    check(L.lr2_xattn_fwd(ptr(q), q.stride(1), ptr(k), ptr(v), k.stride(1), ptr(o), E, items, Sq, Skv, H, dh,
-                          float(pre_scale), float(post_scale), _lib.stream()), "lr2_xattn_fwd")
+    _lib.run(L.lr2_xattn_fwd, ptr(q), q.stride(1), ptr(k), ptr(v), k.stride(1), ptr(o), E, items, Sq, Skv, H, dh,
+                          float(pre_scale), float(post_scale), _lib.stream())
     return o
 
 
@@ -155,9 +155,9 @@ def xattn_bwd(q, k, v, d_o, H, pre_scale, post_scale, dkv_out=None):
         dk, dv = dkv_out
     if dk.stride(1) != dv.stride(1):
         raise _lib.Lr2Error("dk and dv must share a pitch")
-    check(L.lr2_xattn_bwd(ptr(q), q.stride(1), ptr(k), ptr(v), k.stride(1), ptr(d_o), E, ptr(dq), E, ptr(dk),
+    _lib.run(L.lr2_xattn_bwd, ptr(q), q.stride(1), ptr(k), ptr(v), k.stride(1), ptr(d_o), E, ptr(dq), E, ptr(dk),
                           ptr(dv), dk.stride(1), items, Sq, Skv, H, dh, float(pre_scale), float(post_scale),
-                          _lib.stream()), "lr2_xattn_bwd")
+                          _lib.stream())
     return dq, dk, dv
 
 
@@ -171,16 +171,15 @@ def cast_gather(src, index=None, out=None):
     T_dst = index.shape[1] if index is not None else T_src
     if out is None:
         out = torch.empty((bs, T_dst) + tuple(src.shape[2:]), dtype=bf16, device=src.device)
-    check(L.lr2_cast_gather_bf16(ptr(src), ptr(index), ptr(out), bs, T_src, T_dst, row, _lib.stream()),
-          "lr2_cast_gather_bf16")
+    _lib.run(L.lr2_cast_gather_bf16, ptr(src), ptr(index), ptr(out), bs, T_src, T_dst, row, _lib.stream())
     return out
 
 
 def rows_copy(src, src_gstride, src_off, dst, dst_gstride, dst_off, groups, rows_per_group, D, accumulate=False):
     L = _L()
     _cuda(src, bf16, "src"); _cuda(dst, bf16, "dst")
-    check(L.lr2_rows_copy_bf16(ptr(src), src_gstride, src_off, ptr(dst), dst_gstride, dst_off, groups,
-                               rows_per_group, D, int(accumulate), _lib.stream()), "lr2_rows_copy_bf16")
+    _lib.run(L.lr2_rows_copy_bf16, ptr(src), src_gstride, src_off, ptr(dst), dst_gstride, dst_off, groups,
+                               rows_per_group, D, int(accumulate), _lib.stream())
     return dst
 
 
@@ -192,8 +191,7 @@ def colsum(x, out=None, accumulate=False):
     if out is None:
         out = torch.empty(cols, dtype=f32, device=x.device)
     part = _workspace(L.lr2_colsum_partials_floats(cols) * 4, x.device)
-    check(L.lr2_colsum_bf16(ptr(x), x.stride(0), rows, cols, ptr(out), ptr(part), int(accumulate), _lib.stream()),
-          "lr2_colsum_bf16")
+    _lib.run(L.lr2_colsum_bf16, ptr(x), x.stride(0), rows, cols, ptr(out), ptr(part), int(accumulate), _lib.stream())
     return out
 
 
@@ -202,8 +200,7 @@ def rowdot_fwd(x, w, b, rows, row_stride=1, row_off=0):
     _cuda(x, bf16, "x"); _cuda(w, f32, "w"); _cuda(b, f32, "b")
     D = x.shape[-1]
     out = torch.empty(rows, dtype=f32, device=x.device)
-    check(L.lr2_rowdot_fwd(ptr(x), row_stride, row_off, ptr(w), ptr(b), ptr(out), rows, D, _lib.stream()),
-          "lr2_rowdot_fwd")
+    _lib.run(L.lr2_rowdot_fwd, ptr(x), row_stride, row_off, ptr(w), ptr(b), ptr(out), rows, D, _lib.stream())
     return out
 
 
@@ -214,15 +211,15 @@ def rowdot_bwd(x, w, dout, rows, row_stride=1, row_off=0):
     dx = torch.empty((rows * row_stride, D), dtype=bf16, device=x.device)
     dw = torch.empty(D, dtype=f32, device=x.device)
     db = torch.empty(1, dtype=f32, device=x.device)
-    check(L.lr2_rowdot_bwd(ptr(x), row_stride, row_off, ptr(w), ptr(dout), ptr(dx), ptr(dw), ptr(db), rows, D,
-                           _lib.stream()), "lr2_rowdot_bwd")
+    _lib.run(L.lr2_rowdot_bwd, ptr(x), row_stride, row_off, ptr(w), ptr(dout), ptr(dx), ptr(dw), ptr(db), rows, D,
+                           _lib.stream())
     return dx, dw, db
 
 
 def add_pos_fwd(x, pos, bs, T):
     L = _L()
     _cuda(x, bf16, "x"); _cuda(pos, f32, "pos")
-    check(L.lr2_add_pos_fwd(ptr(x), ptr(pos), bs, T, x.shape[-1], _lib.stream()), "lr2_add_pos_fwd")
+    _lib.run(L.lr2_add_pos_fwd, ptr(x), ptr(pos), bs, T, x.shape[-1], _lib.stream())
     return x
 
 
@@ -231,7 +228,7 @@ def add_pos_bwd(dx, bs, T):
     _cuda(dx, bf16, "dx")
     D = dx.shape[-1]
     dpos = torch.empty((T, D), dtype=f32, device=dx.device)
-    check(L.lr2_add_pos_bwd(ptr(dx), ptr(dpos), bs, T, D, _lib.stream()), "lr2_add_pos_bwd")
+    _lib.run(L.lr2_add_pos_bwd, ptr(dx), ptr(dpos), bs, T, D, _lib.stream())
     return dpos
 
 
@@ -240,7 +237,7 @@ def to_bf16(src, out=None):
     _cuda(src, f32, "src")
     if out is None:
         out = torch.empty(src.shape, dtype=bf16, device=src.device)
-    check(L.lr2_cast_f32_to_bf16(ptr(src), ptr(out), src.numel(), _lib.stream()), "lr2_cast_f32_to_bf16")
+    _lib.run(L.lr2_cast_f32_to_bf16, ptr(src), ptr(out), src.numel(), _lib.stream())
     return out
 
 
@@ -249,7 +246,7 @@ def to_f32(src, out=None):
     _cuda(src, bf16, "src")
     if out is None:
         out = torch.empty(src.shape, dtype=f32, device=src.device)
-    check(L.lr2_cast_bf16_to_f32(ptr(src), ptr(out), src.numel(), _lib.stream()), "lr2_cast_bf16_to_f32")
+    _lib.run(L.lr2_cast_bf16_to_f32, ptr(src), ptr(out), src.numel(), _lib.stream())
     return out
 
 
@@ -267,9 +264,9 @@ def ppo_policy_loss(s, s_old, reward, v_old, pi, w_kl, w_ent, margin=0.01, adv_e
     radj = torch.empty(B, dtype=f32, device=dev)
     adv = torch.empty(B, dtype=f32, device=dev)
     ds = torch.empty((B, n), dtype=f32, device=dev) if want_grad else None
-    check(L.lr2_ppo_policy_loss(ptr(s), ptr(s_old), ptr(reward), ptr(v_old), ptr(pi), B, n, float(w_kl),
+    _lib.run(L.lr2_ppo_policy_loss, ptr(s), ptr(s_old), ptr(reward), ptr(v_old), ptr(pi), B, n, float(w_kl),
                                 float(w_ent), float(margin), float(adv_eps), ptr(scal), ptr(kl), ptr(ent),
-                                ptr(radj), ptr(adv), ptr(ds), _lib.stream()), "lr2_ppo_policy_loss")
+                                ptr(radj), ptr(adv), ptr(ds), _lib.stream())
     return dict(loss=scal[0], rank_loss=scal[1], hinge_cnt=scal[2], sum_abs_adv=scal[3], kl=kl, entropy=ent,
                 reward_adj=radj, adv=adv, ds=ds)
 
@@ -281,8 +278,7 @@ def clipped_value_loss(v, ret, v_old, clip, want_grad=True):
     B = v.numel()
     loss = torch.empty(1, dtype=f32, device=v.device)
     dv = torch.empty(B, dtype=f32, device=v.device) if want_grad else None
-    check(L.lr2_clipped_value_loss(ptr(v), ptr(ret), ptr(v_old), B, float(clip), ptr(loss), ptr(dv), _lib.stream()),
-          "lr2_clipped_value_loss")
+    _lib.run(L.lr2_clipped_value_loss, ptr(v), ptr(ret), ptr(v_old), B, float(clip), ptr(loss), ptr(dv), _lib.stream())
     return loss[0], dv
 
 
@@ -293,8 +289,8 @@ def pair_hinge_loss(chosen, reject, margin=1.0, want_grad=True):
     out = torch.empty(2, dtype=f32, device=chosen.device)
     dc = torch.empty(B, dtype=f32, device=chosen.device) if want_grad else None
     dr = torch.empty(B, dtype=f32, device=chosen.device) if want_grad else None
-    check(L.lr2_pair_hinge_loss(ptr(chosen), ptr(reject), B, float(margin), ptr(out), ptr(dc), ptr(dr),
-                                _lib.stream()), "lr2_pair_hinge_loss")
+    _lib.run(L.lr2_pair_hinge_loss, ptr(chosen), ptr(reject), B, float(margin), ptr(out), ptr(dc), ptr(dr),
+                                _lib.stream())
     return out[0], out[1], dc, dr
 
 
@@ -304,8 +300,7 @@ def smooth_l1_loss(logits, tgt, beta=0.3, want_grad=True):
     n = logits.numel()
     loss = torch.empty(1, dtype=f32, device=logits.device)
     dl = torch.empty(n, dtype=f32, device=logits.device) if want_grad else None
-    check(L.lr2_smooth_l1_loss(ptr(logits), ptr(tgt), n, float(beta), ptr(loss), ptr(dl), _lib.stream()),
-          "lr2_smooth_l1_loss")
+    _lib.run(L.lr2_smooth_l1_loss, ptr(logits), ptr(tgt), n, float(beta), ptr(loss), ptr(dl), _lib.stream())
     return loss[0], dl
 
 
@@ -315,8 +310,7 @@ def ppo_rollout(scores, state=None, n_prefix=2, want_order=False):
     B, n = scores.shape
     ns = torch.empty((B, n_prefix + n), dtype=i64, device=scores.device)
     order = torch.empty((B, n), dtype=i64, device=scores.device) if want_order else None
-    check(L.lr2_ppo_rollout(ptr(scores), ptr(state), B, n, n_prefix, ptr(ns), ptr(order), _lib.stream()),
-          "lr2_ppo_rollout")
+    _lib.run(L.lr2_ppo_rollout, ptr(scores), ptr(state), B, n, n_prefix, ptr(ns), ptr(order), _lib.stream())
     return (ns, order) if want_order else ns
 
 
@@ -326,8 +320,7 @@ def rank_sample(scores, u=None, greedy=False):
     B, n = scores.shape
     perm = torch.empty((B, n), dtype=i64, device=scores.device)
     lp = torch.empty(B, dtype=f32, device=scores.device)
-    check(L.lr2_rank_sample(ptr(scores), ptr(u), B, n, int(greedy), ptr(perm), ptr(lp), _lib.stream()),
-          "lr2_rank_sample")
+    _lib.run(L.lr2_rank_sample, ptr(scores), ptr(u), B, n, int(greedy), ptr(perm), ptr(lp), _lib.stream())
     return perm, lp
 
 
@@ -339,8 +332,8 @@ def gae_scan(rewards, values, gamma, lam, notdone=None):
         raise _lib.Lr2Error("values must be [B, T+1]")
     adv = torch.empty((B, T), dtype=f32, device=rewards.device)
     ret = torch.empty((B, T), dtype=f32, device=rewards.device)
-    check(L.lr2_gae_scan(ptr(rewards), ptr(values), ptr(notdone), B, T, float(gamma), float(lam), ptr(adv), ptr(ret),
-                         _lib.stream()), "lr2_gae_scan")
+    _lib.run(L.lr2_gae_scan, ptr(rewards), ptr(values), ptr(notdone), B, T, float(gamma), float(lam), ptr(adv), ptr(ret),
+                         _lib.stream())
     return adv, ret
 
 
@@ -368,8 +361,8 @@ def ndcg_at_k(scores, labels, ks, lens=None, want_order=False):
     ks_t = torch.tensor(list(ks), dtype=i64, device=dev)
     out = torch.empty((B, len(ks)), dtype=f32, device=dev)
     order = torch.full((B, N), -1, dtype=i64, device=dev) if want_order else None
-    check(L.lr2_ndcg_at_k(ptr(scores), ptr(labels), ptr(lens), B, N, N, ptr(ks_t), len(ks), ptr(log2_table(N, dev)),
-                          ptr(out), ptr(order), _lib.stream()), "lr2_ndcg_at_k")
+    _lib.run(L.lr2_ndcg_at_k, ptr(scores), ptr(labels), ptr(lens), B, N, N, ptr(ks_t), len(ks), ptr(log2_table(N, dev)),
+                          ptr(out), ptr(order), _lib.stream())
     return (out, order) if want_order else out
 
 
@@ -382,6 +375,6 @@ def ndcg_presorted(pred_rel, true_rel, ks, lens=None):
     ks_t = torch.tensor(list(ks), dtype=i64, device=dev)
     out = torch.empty((B, len(ks)), dtype=f32, device=dev)
     scratch = torch.empty(2 * B * len(ks), dtype=f32, device=dev)
-    check(L.lr2_ndcg_presorted(ptr(pred_rel), ptr(true_rel), ptr(lens), B, N, ptr(ks_t), len(ks),
-                               ptr(log2_table(N, dev)), ptr(out), ptr(scratch), _lib.stream()), "lr2_ndcg_presorted")
+    _lib.run(L.lr2_ndcg_presorted, ptr(pred_rel), ptr(true_rel), ptr(lens), B, N, ptr(ks_t), len(ks),
+                               ptr(log2_table(N, dev)), ptr(out), ptr(scratch), _lib.stream())
     return out

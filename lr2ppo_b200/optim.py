@@ -129,8 +129,8 @@ class FusedAdamW(Optimizer):
             if tab["hyper_host"] != hv:
                 tab["hyper"].copy_(torch.tensor(hv, dtype=torch.float32))
                 tab["hyper_host"] = hv
-            check(L.lr2_adamw_multi(tab["ptrs"].data_ptr(), tab["meta"].data_ptr(), tab["chunks"].data_ptr(),
-                                    tab["n_chunks"], tab["hyper"].data_ptr(), _lib.stream()), "lr2_adamw_multi")
+            _lib.run(L.lr2_adamw_multi, tab["ptrs"].data_ptr(), tab["meta"].data_ptr(), tab["chunks"].data_ptr(),
+                     tab["n_chunks"], tab["hyper"].data_ptr(), _lib.stream())
         return loss
 
 

@@ -1,0 +1,182 @@
+"""Stage-3 (LR2PPO) rollout, update and evaluation with the reference's function signatures
+(finetune/ppo.py: build_optimizer:378, clipped_value_loss:494, train_model:501, evaluate:620, rollout
+loop :845-883), re-built on the fused engine:
+
+  * rollout: actor + critic + stable descending sort + permutation compose + reward model, no host sync
+    (the reference loops over the batch in Python, finetune/ppo.py:869-871);
+  * update: one fused kernel for KL / entropy / advantage / pair order / RankLoss / policy loss and its
+    backward (the reference synchronises the host once per row at :563-568 and again at :52, :576);
+  * the ten per-batch statistic all-reduces (:589-598) are packed into one.
+"""
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .losses import RankLoss, clipped_value_loss, ppo_policy_loss  # noqa: F401  (re-exported, reference names)
+from .models import Actor, ActorCritic, Critic, Mlp, Reward  # noqa: F401
+from .ndcg import AverageNDCGMeter
+from .optim import str2optimizer, str2scheduler
+
+
+def log(t, eps=1e-20):
+    """ref: finetune/ppo.py:431-432."""
+    return torch.log(t.clamp(min=eps))
+
+
+def build_optimizer(args, model):
+    """ref: finetune/ppo.py:378-419 — two AdamW optimizers (actor, critic), no decay for bias/gamma/beta,
+    linear warm-up schedules.  Returns (optimizer, critic_optimizer, scheduler, critic_scheduler)."""
+    no_decay = ["bias", "gamma", "beta"]
+
+    def groups(named):
+        named = list(named)
+        return [{"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
+                {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
+
+    opt_name = getattr(args, "optimizer", "adamw")
+    if opt_name not in str2optimizer:
+        raise ValueError(f"optimizer {opt_name!r} is outside the LR2PPO hot path (only adamw is used by the scripts)")
+    optimizer = str2optimizer[opt_name](groups(model.actor.named_parameters()), lr=args.learning_rate,
+                                        correct_bias=False)
+    critic_optimizer = str2optimizer[opt_name](groups(model.critic.named_parameters()),
+                                               lr=args.critic_learning_rate, correct_bias=False)
+    for eng, opt in ((model.actor._engine, optimizer), (model.critic._engine, critic_optimizer)):
+        attach_shadows(eng, opt)
+    sched = getattr(args, "scheduler", "linear")
+    if sched == "constant":
+        scheduler = str2scheduler[sched](optimizer)
+        critic_scheduler = str2scheduler[sched](critic_optimizer)
+    elif sched == "constant_with_warmup":
+        scheduler = str2scheduler[sched](optimizer, args.train_steps * args.warmup)
+        critic_scheduler = str2scheduler[sched](critic_optimizer, args.train_steps * args.warmup)
+    else:
+        scheduler = str2scheduler[sched](optimizer, args.train_steps * args.warmup, args.train_steps)
+        critic_scheduler = str2scheduler[sched](critic_optimizer, args.train_steps * args.warmup, args.train_steps)
+    return optimizer, critic_optimizer, scheduler, critic_scheduler
+
+
+def attach_shadows(engine, optimizer):
+    """Let the optimizer refresh the engine's bf16 weight copies in its own pass (no separate cast kernels)."""
+    for group in optimizer.param_groups:
+        for p in group["params"]:
+            if p.dim() >= 2 and p.is_cuda:
+                optimizer.register_shadow(p, engine.bank.get(p))
+
+
+@torch.no_grad()
+def rollout(model, reward_model, text_emb_batch, img_emb_batch, tgts_batch, state=None):
+    """One rollout timestep (finetune/ppo.py:845-883).  Returns the memory entry
+    [state, next_state, action_scores, rewards, value, text, img, tgts] (no clones needed: nothing aliases)."""
+    bs, tags_num = text_emb_batch.shape[:2]
+    if state is None:
+        state = torch.arange(tags_num, device=text_emb_batch.device).unsqueeze(0).repeat(bs, 1)
+    was_training = model.training
+    model.eval()
+    reward_model.eval()
+    action_logits = model.actor.scores(text_emb_batch, img_emb_batch)
+    value = model.critic(text_emb_batch, img_emb_batch, tgts_batch, state)
+    if model.actor.mode == "cls":
+        pr = action_logits.view(bs, tags_num, 3).softmax(dim=-1)
+        action_scores = pr[:, :, 1] + 2 * pr[:, :, 2]
+    else:
+        action_scores = action_logits.view(bs, tags_num)
+    next_state = ops.ppo_rollout(action_scores.contiguous(), state.contiguous(), 2)
+    rewards = reward_model(text_emb_batch, img_emb_batch, tgts_batch, next_state)
+    if was_training:
+        model.train()
+    return [state, next_state, action_scores, rewards, value, text_emb_batch, img_emb_batch, tgts_batch]
+
+
+_STAT_NAMES = ["policy_loss", "value_loss", "kl_penalty", "old_value", "value", "rewards_ori", "rewards",
+               "advantages", "rank_loss", "entropy"]
+
+
+def update_batch(args, model, optimizer, critic_optim, memory, grad_sync=None):
+    """One stored batch of the update loop (finetune/ppo.py:518-587).  Returns a [10] tensor of the
+    statistics the reference logs (means over the batch), still on the device."""
+    state, next_state, old_action_prob, rewards, old_value, text, img, tgts = memory
+    model.zero_grad(set_to_none=False) if getattr(args, "keep_grad_buffers", True) else model.zero_grad()
+    bs, tags_num = old_action_prob.shape[:2]
+    action_logits = model.actor.scores(text, img)
+    value = model.critic(text, img, tgts, state)
+    if model.actor.mode == "cls":
+        pr = action_logits.view(bs, tags_num, 3).softmax(dim=-1)
+        action_scores = pr[:, :, 1] + 2 * pr[:, :, 2]
+    else:
+        action_scores = action_logits.view(bs, tags_num)
+    pair = next_state[:, -2:].contiguous()
+    loss, rank_loss, kl, ent, rewards_adj, adv = ppo_policy_loss(
+        action_scores, old_action_prob, rewards, old_value, pair, args.kl_div_loss_weight, args.entropy_weight,
+        0.01, -0.1)
+    loss.backward()
+    if grad_sync is not None:
+        grad_sync(model.actor)
+    optimizer.step()
+    value_loss = clipped_value_loss(value, rewards_adj.detach(), old_value, args.value_clip)
+    value_loss.backward()
+    if grad_sync is not None:
+        grad_sync(model.critic)
+    critic_optim.step()
+    return torch.stack([loss.detach(), value_loss.detach(), kl.mean(), old_value.mean(), value.detach().mean(),
+                        rewards.mean(), rewards_adj.mean(), adv.mean(), rank_loss, ent.mean()])
+
+
+def train_model(args, model, optimizer, critic_optim, scheduler, critic_scheduler, memories, epoch, grad_sync=None):
+    """ref: finetune/ppo.py:501-617 — same arguments, same ten returned averages
+    [policy_loss, value_loss, kl_penalty, old_value, value, rewards_ori, rewards, advantages, rank_loss, entropy]."""
+    total = None
+    for memory in memories:
+        stats = update_batch(args, model, optimizer, critic_optim, memory, grad_sync)
+        total = stats if total is None else total + stats
+    total = total / len(memories)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        total = total / dist.get_world_size()
+        dist.all_reduce(total)          # one packed all-reduce instead of ten per batch
+    scheduler.step()
+    critic_scheduler.step()
+    return list(total.unbind(0))
+
+
+@torch.no_grad()
+def evaluate_scores(model, text_emb, img_emb):
+    """Actor scores of every tag of one clip (finetune/ppo.py:640-649)."""
+    logits = model.actor.scores(text_emb, img_emb)
+    if model.actor.mode == "cls":
+        logits = logits.view(-1, 3)
+        return logits[:, 1] + 2 * logits[:, 2]
+    return logits.view(-1)
+
+
+@torch.no_grad()
+def evaluate(args, val_loader, step, split="test", num_tasks=None):
+    """ref: finetune/ppo.py:620-681.  Scores every clip of this rank's shard, then ONE segmented NDCG launch
+    and ONE all_gather for the whole pass (the reference gathers once per clip)."""
+    args.model.eval()
+    scores_l, gold_l = [], []
+    for text_emb, img_emb, tgts in val_loader:
+        text = text_emb.to(args.device)
+        img = img_emb.unsqueeze(1).repeat(1, text.shape[1], 1, 1).to(args.device)
+        scores_l.append(evaluate_scores(args.model, text, img))
+        gold_l.append(tgts.to(args.device).view(-1))
+    meter = AverageNDCGMeter()
+    n = len(scores_l)
+    nmax = max(s.numel() for s in scores_l)
+    scores = torch.full((n, nmax), float("-inf"), device=args.device)
+    labels = torch.zeros((n, nmax), dtype=torch.int64, device=args.device)
+    lens = torch.tensor([s.numel() for s in scores_l], dtype=torch.int32, device=args.device)
+    for i, (s, g) in enumerate(zip(scores_l, gold_l)):
+        scores[i, :s.numel()] = s
+        labels[i, :g.numel()] = g
+    vals = meter.batch_ndcg(scores, labels, lens=lens)
+    if num_tasks and num_tasks > 1:
+        gathered = [torch.zeros_like(vals) for _ in range(num_tasks)]
+        dist.all_gather(gathered, vals)
+        vals = torch.cat(gathered, dim=0)
+    if getattr(args, "is_master", True):
+        meter.add_batch(vals)
+        ndcg_value = meter.value()
+        if hasattr(args, "logger"):
+            args.logger.info("NDCG:")
+            args.logger.info("".join("\nNDCG@{}={:.4f}".format(k, ndcg_value[k]) for k in sorted(ndcg_value.keys())))
+        return ndcg_value[100000000]
+    return None
