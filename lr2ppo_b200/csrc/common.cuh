@@ -43,6 +43,36 @@ __device__ __forceinline__ float gelu_erf_grad(float x) {
   return cdf + x * pdf;
 }
 
+// Fast GELU for bf16 epilogues: erf by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7, three orders of
+// magnitude below bf16 resolution) with one MUFU.RCP and one MUFU.EX2; cdf and pdf share the exponential.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+  const float e = ex2_approx(-z * z * 1.4426950408889634f);
+  const float erf_abs = 1.0f - poly * e;            // erf(|x|/sqrt2)
+  const float cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  return x * cdf;
+}
+__device__ __forceinline__ float gelu_fast_grad(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+  const float e = ex2_approx(-z * z * 1.4426950408889634f);   // = exp(-x^2/2)
+  const float cdf = 0.5f * (1.0f + copysignf(1.0f - poly * e, x));
+  return cdf + x * 0.39894228040143267794f * e;
+}
+
 // ---- Philox4x32-10 counter RNG (dropout masks are a pure function of
 // (seed, site, element index), so backward regenerates them) -------------
 struct Philox4 {

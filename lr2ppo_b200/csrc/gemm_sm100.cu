@@ -22,6 +22,7 @@
 #include <unordered_map>
 #include <string>
 #include <cstring>
+#include <cstdlib>
 #include "common.cuh"
 #include "../../include/lr2ppo_b200.h"
 
@@ -30,7 +31,9 @@ namespace lr2 {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 16;                      // four per TMEM lane quadrant
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;   // warp0 TMA, warp1 MMA, warps2-17 epilogue
+constexpr int STG_PITCH = 36;                      // floats per staged row (32 + 4 pad)
 
 struct GemmParams {
   int M, N, K;
@@ -47,10 +50,13 @@ struct GemmParams {
   long long ldaux;
   float beta;          // fp32 out only: out += beta * C_old
   float drop_p;        // 0 = no dropout
+  unsigned int drop_thresh;  // drop_p * 2^32 (host-computed)
+  float drop_scale;    // 1/(1-p)
   unsigned long long seed;
   unsigned int site;
   float* ws;           // split-K workspace [splits][out_rows*ldc]
   long long ws_slab;   // elements per slab
+  int debug;           // experiment switch (LR2_GEMM_DEBUG)
 };
 
 // ------------------------------------------------------------------ PTX --
@@ -119,8 +125,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // UMMA shared-memory descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor layout:
 // start>>4 @0, LBO>>4 @16, SBO>>4 @32, version=1 @46, layout_type=2 (SWIZZLE_128B) @61).
@@ -141,7 +147,9 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
 
 // -------------------------------------------------------------- epilogue --
 // One output row r, 8 consecutive output columns c..c+7 (c % 8 == 0, c + 8 <= ncols).
-__device__ __forceinline__ void epi_store8(const GemmParams& p, float (&v)[8], long long r, int c) {
+// epi_math8 loads bias / aux / old C and transforms v in registers (pre = bf16 pre-activation for C2);
+// epi_write8 issues the stores.  Split so that the caller can interleave two independent groups.
+__device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], uint4& pre, long long r, int c) {
   const long long off = r * p.ldc + c;
   if (p.epi == LR2_EPI_NONE) {
     if (p.c_f32 && p.beta != 0.f) {
@@ -150,55 +158,59 @@ __device__ __forceinline__ void epi_store8(const GemmParams& p, float (&v)[8], l
       v[0] += p.beta * a.x; v[1] += p.beta * a.y; v[2] += p.beta * a.z; v[3] += p.beta * a.w;
       v[4] += p.beta * b.x; v[5] += p.beta * b.y; v[6] += p.beta * b.z; v[7] += p.beta * b.w;
     }
-  } else {
-    if (p.bias != nullptr && (p.epi == LR2_EPI_BIAS || p.epi == LR2_EPI_BIAS_GELU || p.epi == LR2_EPI_BIAS_DROP_RES)) {
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
-      v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-      v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-    }
-    float a[8];
-    if (p.epi == LR2_EPI_BIAS_DROP_RES || p.epi == LR2_EPI_DGELU || p.epi == LR2_EPI_ADD) {
-      const uint4 u = *reinterpret_cast<const uint4*>(p.aux + r * p.ldaux + c);
-      float2 t;
-      t = unpack_bf16x2(u.x); a[0] = t.x; a[1] = t.y;
-      t = unpack_bf16x2(u.y); a[2] = t.x; a[3] = t.y;
-      t = unpack_bf16x2(u.z); a[4] = t.x; a[5] = t.y;
-      t = unpack_bf16x2(u.w); a[6] = t.x; a[7] = t.y;
-    }
-    uint32_t keep = 0xFFu;
-    float dscale = 1.f;
-    if (p.drop_p > 0.f) {
-      const uint32_t th = dropout_thresh(p.drop_p);
-      const uint64_t lin = (uint64_t)off;  // ldc-strided linear index; multiple of 8
-      keep = dropout_keep4(p.seed, p.site, lin >> 2, th) | (dropout_keep4(p.seed, p.site, (lin >> 2) + 1, th) << 4);
-      dscale = 1.f / (1.f - p.drop_p);
-    }
-    if (p.epi == LR2_EPI_BIAS_GELU) {
-      if (p.C2 != nullptr) {
-        uint4 u;
-        u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
-        u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-        *reinterpret_cast<uint4*>(p.C2 + off) = u;
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        // GELU is evaluated on the bf16-rounded pre-activation so that backward
-        // (which only has the stored bf16 copy) differentiates the same function.
-        const float x = __bfloat162float(__float2bfloat16(v[i]));
-        v[i] = ((keep >> i) & 1u) ? gelu_erf(x) * dscale : 0.f;
-      }
-    } else if (p.epi == LR2_EPI_BIAS_DROP_RES) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = (((keep >> i) & 1u) ? v[i] * dscale : 0.f) + a[i];
-    } else if (p.epi == LR2_EPI_DGELU) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * gelu_erf_grad(a[i]) * dscale : 0.f;
-    } else if (p.epi == LR2_EPI_ADD) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] += a[i];
-    }
+    return;
   }
+  if (p.bias != nullptr && (p.epi == LR2_EPI_BIAS || p.epi == LR2_EPI_BIAS_GELU || p.epi == LR2_EPI_BIAS_DROP_RES)) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
+    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  }
+  float a[8];
+  if (p.epi == LR2_EPI_BIAS_DROP_RES || p.epi == LR2_EPI_DGELU || p.epi == LR2_EPI_ADD) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p.aux + r * p.ldaux + c);
+    float2 t;
+    t = unpack_bf16x2(u.x); a[0] = t.x; a[1] = t.y;
+    t = unpack_bf16x2(u.y); a[2] = t.x; a[3] = t.y;
+    t = unpack_bf16x2(u.z); a[4] = t.x; a[5] = t.y;
+    t = unpack_bf16x2(u.w); a[6] = t.x; a[7] = t.y;
+  }
+  uint32_t keep = 0xFFu;
+  float dscale = 1.f;
+  if (p.drop_p > 0.f) {
+    const uint32_t th = p.drop_thresh;
+    const uint64_t lin = (uint64_t)off;  // ldc-strided linear index; multiple of 8
+    keep = dropout_keep4(p.seed, p.site, lin >> 2, th) | (dropout_keep4(p.seed, p.site, (lin >> 2) + 1, th) << 4);
+    dscale = p.drop_scale;
+  }
+  if (p.epi == LR2_EPI_BIAS_GELU) {
+    pre.x = pack_bf16x2(v[0], v[1]); pre.y = pack_bf16x2(v[2], v[3]);
+    pre.z = pack_bf16x2(v[4], v[5]); pre.w = pack_bf16x2(v[6], v[7]);
+    // GELU is evaluated on the bf16-rounded pre-activation so that backward (which only has the
+    // stored bf16 copy) differentiates the same function.
+    float2 t;
+    float x[8];
+    t = unpack_bf16x2(pre.x); x[0] = t.x; x[1] = t.y;
+    t = unpack_bf16x2(pre.y); x[2] = t.x; x[3] = t.y;
+    t = unpack_bf16x2(pre.z); x[4] = t.x; x[5] = t.y;
+    t = unpack_bf16x2(pre.w); x[6] = t.x; x[7] = t.y;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? gelu_fast(x[i]) * dscale : 0.f;
+  } else if (p.epi == LR2_EPI_BIAS_DROP_RES) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = (((keep >> i) & 1u) ? v[i] * dscale : 0.f) + a[i];
+  } else if (p.epi == LR2_EPI_DGELU) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * gelu_fast_grad(a[i]) * dscale : 0.f;
+  } else if (p.epi == LR2_EPI_ADD) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += a[i];
+  }
+}
+__device__ __forceinline__ void epi_write8(const GemmParams& p, const float (&v)[8], const uint4& pre, long long r,
+                                           int c) {
+  const long long off = r * p.ldc + c;
+  if (p.epi == LR2_EPI_BIAS_GELU && p.C2 != nullptr) *reinterpret_cast<uint4*>(p.C2 + off) = pre;
   if (p.c_f32) {
     float4* o = reinterpret_cast<float4*>((float*)p.C + off);
     o[0] = make_float4(v[0], v[1], v[2], v[3]);
@@ -209,6 +221,11 @@ __device__ __forceinline__ void epi_store8(const GemmParams& p, float (&v)[8], l
     u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
     *reinterpret_cast<uint4*>((bf16*)p.C + off) = u;
   }
+}
+__device__ __forceinline__ void epi_store8(const GemmParams& p, float (&v)[8], long long r, int c) {
+  uint4 pre = make_uint4(0, 0, 0, 0);
+  epi_math8(p, v, pre, r, c);
+  epi_write8(p, v, pre, r, c);
 }
 
 // Scalar epilogue (transposed tiles and ragged edges). No dropout on this path.
@@ -224,11 +241,11 @@ __device__ __forceinline__ void epi_store1(const GemmParams& p, float v, long lo
       a = __bfloat162float(p.aux[r * p.ldaux + c]);
     if (p.epi == LR2_EPI_BIAS_GELU) {
       if (p.C2 != nullptr) p.C2[off] = __float2bfloat16(v);
-      v = gelu_erf(__bfloat162float(__float2bfloat16(v)));
+      v = gelu_fast(__bfloat162float(__float2bfloat16(v)));
     } else if (p.epi == LR2_EPI_BIAS_DROP_RES || p.epi == LR2_EPI_ADD) {
       v += a;
     } else if (p.epi == LR2_EPI_DGELU) {
-      v *= gelu_erf_grad(a);
+      v *= gelu_fast_grad(a);
     }
   }
   if (p.c_f32) ((float*)p.C)[off] = v;
@@ -241,9 +258,10 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
   static constexpr int BAR_BYTES = 256;
-  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 for manual alignment
+  static constexpr int STG_BYTES = EPI_WARPS * 32 * STG_PITCH * 4;      // epilogue staging (fp32), per warp 32 rows
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024;  // +1024 for manual alignment
 };
 
 template <int BN, bool A_MN, bool B_MN>
@@ -262,6 +280,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* stg_all = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -278,7 +297,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 4); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_WARPS); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -363,7 +382,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     }
   } else {
     // ======================= epilogue warps =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // warp -> (TMEM lane quadrant, column half). Per 64-column chunk: TMEM -> registers -> per-warp smem
+    // staging (row per lane), then re-read with 8 lanes per row so that bias / aux / C / C2 accesses are
+    // 128-byte coalesced and every lane has 8 independent elements in flight for the GELU / Philox math.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;                             // column part 0..3
+    float* stg = stg_all + (size_t)(warp - 2) * 32 * STG_PITCH;
+    constexpr int COLS_PER_WARP = (BN / 4 < 32) ? 32 : BN / 4;    // BN=64: only parts 0,1 have columns
+    constexpr int CW = 32;                                        // chunk width
+    constexpr int TPR = CW / 8;                                   // lanes per row in the coalesced phase
+    constexpr int RPI = 32 / TPR;                                 // rows per iteration
     int it = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
       const int split = w % p.splits;
@@ -373,7 +401,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(&tfull_bar[buf], acc_phase);
       tc_fence_after();
-      const int m = mt * BM + quad * 32 + lane;
+      const int m_base = mt * BM + quad * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
       GemmParams q = p;
       if (p.splits > 1) {  // raw fp32 partial into this split's slab
@@ -381,32 +409,75 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         q.C = p.ws + (long long)split * p.ws_slab;
       }
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)c0, r);
-        const int n0 = nt * BN + c0;
-        if (n0 >= p.N) continue;
+      for (int c0 = half * COLS_PER_WARP; c0 < (half + 1) * COLS_PER_WARP && c0 < BN; c0 += CW) {
+        const int n_base = nt * BN + c0;
+        if (n_base >= p.N) break;  // warp-uniform
         if (!p.transposed_out) {
-          if (m < p.M) {
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const int n = n0 + g * 8;
-              if (n + 8 <= p.N) {
-                float v[8];
+          for (int cc = 0; cc < CW; cc += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + (uint32_t)(c0 + cc), r);
+            tmem_ld_wait();
+            float4* dst = reinterpret_cast<float4*>(stg + lane * STG_PITCH + cc);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-                epi_store8(q, v, m, n);
-              } else {
-                for (int i = 0; i < 8; ++i)
-                  if (n + i < p.N) epi_store1(q, __uint_as_float(r[g * 8 + i]), m, n + i);
+            for (int i = 0; i < 8; ++i)
+              dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+          }
+          __syncwarp();
+          const int cg = (lane % TPR) * 8;
+#pragma unroll 1
+          for (int rr = 0; rr < 32; rr += 2 * RPI) {
+            const int rl0 = rr + lane / TPR, rl1 = rl0 + RPI;
+            const int m0 = m_base + rl0, m1 = m_base + rl1;
+            const int n = n_base + cg;
+            const bool full = (n + 8 <= p.N);
+            if (full && m1 < p.M) {
+              // two independent 8-wide groups in flight (rows rl0 and rl1)
+              const float4* s0 = reinterpret_cast<const float4*>(stg + rl0 * STG_PITCH + cg);
+              const float4* s1 = reinterpret_cast<const float4*>(stg + rl1 * STG_PITCH + cg);
+              const float4 x0 = s0[0], x1 = s0[1], y0 = s1[0], y1 = s1[1];
+              float v0[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+              float v1[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+              uint4 p0 = make_uint4(0, 0, 0, 0), p1 = make_uint4(0, 0, 0, 0);
+              epi_math8(q, v0, p0, m0, n);
+              epi_math8(q, v1, p1, m1, n);
+              epi_write8(q, v0, p0, m0, n);
+              epi_write8(q, v1, p1, m1, n);
+            } else {
+#pragma unroll 1
+              for (int h2 = 0; h2 < 2; ++h2) {
+                const int row_l = h2 ? rl1 : rl0;
+                const int m = m_base + row_l;
+                if (m < p.M && n < p.N) {
+                  const float4* src = reinterpret_cast<const float4*>(stg + row_l * STG_PITCH + cg);
+                  const float4 x0 = src[0], x1 = src[1];
+                  float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                  if (full) {
+                    epi_store8(q, v, m, n);
+                  } else {
+                    for (int i = 0; i < 8; ++i)
+                      if (n + i < p.N) epi_store1(q, v[i], m, n + i);
+                  }
+                }
               }
             }
           }
+          __syncwarp();
         } else {
-          if (m < p.M) {
+          // transposed tile (skinny GEMMs): lane = output column m, registers = output rows; a warp store
+          // writes 32 consecutive columns of one output row.
+          const int m = m_base + lane;
+#pragma unroll 1
+          for (int cc = 0; cc < CW; cc += 32) {
+            uint32_t r[32];
+            tmem_ld32(taddr + (uint32_t)(c0 + cc), r);
+            tmem_ld_wait();
+            if (m < p.M) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (n0 + i < p.N) epi_store1(q, __uint_as_float(r[i]), n0 + i, m);
+              for (int i = 0; i < 32; ++i)
+                if (n_base + cc + i < p.N) epi_store1(q, __uint_as_float(r[i]), n_base + cc + i, m);
+            }
           }
         }
       }
@@ -586,7 +657,9 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   p.C = C; p.ldc = ldc; p.C2 = reinterpret_cast<bf16*>(C2);
   p.bias = bias; p.aux = reinterpret_cast<const bf16*>(aux); p.ldaux = ldaux;
   p.beta = beta; p.drop_p = drop_p; p.seed = seed; p.site = site;
+  p.drop_thresh = dropout_thresh(drop_p); p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.ws = reinterpret_cast<float*>(workspace);
+  { const char* d = getenv("LR2_GEMM_DEBUG"); p.debug = d ? atoi(d) : 0; }
   const long long out_rows = transposed_out ? N : M;
   p.ws_slab = out_rows * ldc;
 
