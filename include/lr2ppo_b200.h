@@ -41,6 +41,7 @@ extern "C" {
 #define LR2_EPI_BIAS_DROP_RES 3 /* out = dropout(acc + bias[c]) + aux[r,c]                    */
 #define LR2_EPI_DGELU 4         /* out = acc * gelu_erf'(aux[r,c]) * dropout_mask             */
 #define LR2_EPI_ADD 5           /* out = acc + aux[r,c]                                       */
+#define LR2_EPI_ADAMW 6         /* internal: fused wgrad + AdamW (lr2_gemm_wgrad_adamw)       */
 
 int lr2_abi_version(void);
 const char* lr2_last_error_string(int code);
@@ -68,6 +69,16 @@ int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, l
                   const float* bias, const void* aux, long long ldaux, void* C2, float beta, float drop_p,
                   unsigned long long seed, unsigned int site, int splits, void* workspace, int block_n,
                   void* stream);
+
+/* Fused weight-gradient + AdamW for one Linear weight [out_f, in_f] (used for out_layer.fc1, 500 M params):
+ * grad = dY[rows, out_f]^T @ X[rows, in_f] stays in TMEM and is consumed by the AdamW update of
+ * param / exp_avg / exp_avg_sq (fp32, in place) and the bf16 shadow; no gradient tensor exists.
+ * hyper = the 8-float device buffer of lr2_adamw_multi.
+ * ref: finetune/ppo.py:579-580 (loss.backward(); optimizer.step()) restricted to out_layer.fc1.weight;
+ *      tencentpretrain/utils/optimizers.py:374-402. */
+int lr2_gemm_wgrad_adamw(const void* dY, long long lddy, const void* X, long long ldx, int rows, int out_f, int in_f,
+                         float* param, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, const float* hyper,
+                         float weight_decay, void* stream);
 
 /* ------------------------------------------------------------ layernorm --
  * mode 0: torch nn.LayerNorm (biased variance, eps inside sqrt)   ref: finetune/xit.py:31-41,71-74,96-100

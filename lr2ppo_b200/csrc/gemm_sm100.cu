@@ -56,7 +56,9 @@ struct GemmParams {
   unsigned int site;
   float* ws;           // split-K workspace [splits][out_rows*ldc]
   long long ws_slab;   // elements per slab
-  int debug;           // experiment switch (LR2_GEMM_DEBUG)
+  int raster;          // 0: tiles strided over CTAs, m fastest; 1: contiguous chunk per CTA, n fastest
+  // LR2_EPI_ADAMW (fused wgrad + AdamW): C = fp32 parameter (in/out)
+  float* adam_m; float* adam_v; bf16* adam_shadow; const float* adam_hyper; float adam_wd;
 };
 
 // ------------------------------------------------------------------ PTX --
@@ -159,6 +161,39 @@ __device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], ui
       v[4] += p.beta * b.x; v[5] += p.beta * b.y; v[6] += p.beta * b.z; v[7] += p.beta * b.w;
     }
     return;
+  }
+  if (p.epi == LR2_EPI_ADAMW) {
+    // ref: tencentpretrain/utils/optimizers.py:374-402; acc = this tile of the weight gradient
+    const float lr = p.adam_hyper[0], b1 = p.adam_hyper[1], b2 = p.adam_hyper[2], eps = p.adam_hyper[3],
+                omb1 = p.adam_hyper[4], omb2 = p.adam_hyper[5], gs = p.adam_hyper[6], lrd = p.adam_hyper[7];
+    float* P = (float*)p.C + off; float* Mm = p.adam_m + off; float* Vv = p.adam_v + off;
+    const float4 p0 = *reinterpret_cast<const float4*>(P), p1 = *reinterpret_cast<const float4*>(P + 4);
+    const float4 m0 = *reinterpret_cast<const float4*>(Mm), m1 = *reinterpret_cast<const float4*>(Mm + 4);
+    const float4 v0 = *reinterpret_cast<const float4*>(Vv), v1 = *reinterpret_cast<const float4*>(Vv + 4);
+    float pp[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    float mm[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+    float vv[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float g = v[i] * gs;
+      mm[i] = mm[i] * b1 + g * omb1;
+      vv[i] = vv[i] * b2 + (g * g) * omb2;
+      const float denom = sqrtf(vv[i]) + eps;
+      float pn = pp[i] - lr * (mm[i] / denom);
+      if (p.adam_wd > 0.f) pn = pn - (lrd * p.adam_wd) * pn;
+      v[i] = pn;
+    }
+    *reinterpret_cast<float4*>(Mm) = make_float4(mm[0], mm[1], mm[2], mm[3]);
+    *reinterpret_cast<float4*>(Mm + 4) = make_float4(mm[4], mm[5], mm[6], mm[7]);
+    *reinterpret_cast<float4*>(Vv) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    *reinterpret_cast<float4*>(Vv + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
+    if (p.adam_shadow != nullptr) {
+      uint4 u;
+      u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+      u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(p.adam_shadow + off) = u;
+    }
+    return;  // epi_write8 stores v (the new parameter) as fp32 into C
   }
   if (p.bias != nullptr && (p.epi == LR2_EPI_BIAS || p.epi == LR2_EPI_BIAS_GELU || p.epi == LR2_EPI_BIAS_DROP_RES)) {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
@@ -289,6 +324,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_kb = (p.K + BK - 1) / BK;
   const int total_work = m_tiles * n_tiles * p.splits;
+  // work range of this CTA (identical in all three roles)
+  int w_begin, w_end, w_step;
+  if (p.raster == 0) { w_begin = blockIdx.x; w_end = total_work; w_step = gridDim.x; }
+  else {
+    const int per = (total_work + gridDim.x - 1) / gridDim.x;
+    w_begin = blockIdx.x * per; w_end = min(total_work, w_begin + per); w_step = 1;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -316,10 +358,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = w_begin; w < w_end; w += w_step) {
         const int split = w % p.splits;
         const int t = w / p.splits;
-        const int mt = t % m_tiles, nt = t / m_tiles;
+        const int mt = p.raster ? t / n_tiles : t % m_tiles, nt = p.raster ? t % n_tiles : t / m_tiles;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(num_kb, kb0 + p.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -352,7 +394,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      for (int w = w_begin; w < w_end; w += w_step, ++it) {
         const int split = w % p.splits;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(num_kb, kb0 + p.kb_per_split);
@@ -393,10 +435,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     constexpr int TPR = CW / 8;                                   // lanes per row in the coalesced phase
     constexpr int RPI = 32 / TPR;                                 // rows per iteration
     int it = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+    for (int w = w_begin; w < w_end; w += w_step, ++it) {
       const int split = w % p.splits;
       const int t = w / p.splits;
-      const int mt = t % m_tiles, nt = t / m_tiles;
+      const int mt = p.raster ? t / n_tiles : t % m_tiles, nt = p.raster ? t % n_tiles : t / m_tiles;
       const int buf = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(&tfull_bar[buf], acc_phase);
@@ -659,7 +701,6 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   p.beta = beta; p.drop_p = drop_p; p.seed = seed; p.site = site;
   p.drop_thresh = dropout_thresh(drop_p); p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.ws = reinterpret_cast<float*>(workspace);
-  { const char* d = getenv("LR2_GEMM_DEBUG"); p.debug = d ? atoi(d) : 0; }
   const long long out_rows = transposed_out ? N : M;
   p.ws_slab = out_rows * ldc;
 
@@ -677,4 +718,38 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     LR2_RETURN_LAUNCH();
   }
   return LR2_OK;
+}
+
+// Fused out_layer.fc1 weight gradient + AdamW: the [out, in] fp32 parameter is updated tile by tile from the
+// TMEM accumulator of dY^T X, so the 500 M-element gradient is never written to or read from HBM.
+// HBM bytes per parameter: read p, m, v (12) + write p, m, v (12) + bf16 shadow (2) = 26 (28+2 unfused, plus
+// the 4+4 of writing and re-reading the gradient).
+extern "C" int lr2_gemm_wgrad_adamw(const void* dY, long long lddy, const void* X, long long ldx, int rows, int out_f,
+                                    int in_f, float* param, float* exp_avg, float* exp_avg_sq, void* shadow_bf16,
+                                    const float* hyper, float weight_decay, void* stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  if (rows <= 0 || out_f <= 0 || in_f <= 0) return LR2_ERR_BAD_SHAPE;
+  if ((lddy % 8) || (ldx % 8) || (in_f % 8)) return LR2_ERR_MISALIGNED;
+  if ((reinterpret_cast<uintptr_t>(dY) | reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(param) |
+       reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq) |
+       reinterpret_cast<uintptr_t>(shadow_bf16)) & 15)
+    return LR2_ERR_MISALIGNED;
+  if (hyper == nullptr) return LR2_ERR_BAD_SHAPE;
+  constexpr int BN = 128;
+  CUtensorMap ta, tb;
+  int rc = get_tmap(dY, out_f, rows, lddy, 64, BK, &ta);   // A: MN-major [K=rows, M=out_f]
+  if (rc != LR2_OK) return rc;
+  rc = get_tmap(X, in_f, rows, ldx, 64, BK, &tb);           // B: MN-major [K=rows, N=in_f]
+  if (rc != LR2_OK) return rc;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.M = out_f; p.N = in_f; p.K = rows;
+  p.splits = 1; p.kb_per_split = (rows + BK - 1) / BK;
+  p.epi = LR2_EPI_ADAMW; p.transposed_out = 0; p.c_f32 = 1;
+  p.C = param; p.ldc = in_f;
+  p.drop_scale = 1.f;
+  p.raster = 1;   // each CTA walks along a row panel: long contiguous p/m/v streams per row
+  p.adam_m = exp_avg; p.adam_v = exp_avg_sq; p.adam_shadow = reinterpret_cast<bf16*>(shadow_bf16);
+  p.adam_hyper = hyper; p.adam_wd = weight_decay;
+  return launch_major<BN>(true, true, ta, tb, p, stream);
 }

@@ -235,6 +235,22 @@ class FusionEngine:
         self.kind = kind
         self.bank = ShadowBank()
         self._calls = 0
+        self.fc1_stash = None      # list of (dY, X) when out_layer.fc1 is updated by the fused wgrad+AdamW kernel
+        self.dp_gather = None      # optional callable(t) -> all-gathered rows (data-parallel fused mode)
+
+    def enable_fused_fc1(self, optimizer):
+        """Route out_layer.fc1.weight through lr2_gemm_wgrad_adamw (gradient never materialised)."""
+        self.fc1_stash = []
+        w = self.m.out_layer.fc1.weight
+
+        def provider():
+            pairs, self.fc1_stash = self.fc1_stash, []
+            if self.dp_gather is not None:
+                pairs = [(self.dp_gather(a), self.dp_gather(b)) for a, b in pairs]
+            return pairs
+
+        optimizer.register_shadow(w, self.bank.get(w))
+        optimizer.register_fused_wgrad(w, provider)
 
     # weights are re-wrapped per call (cheap) so that parameter updates are always seen
     def _weights(self):
@@ -329,7 +345,12 @@ class FusionEngine:
         # out_layer
         _wgrad(sink, W["o2"].mod, dfeat, ctx["y1"])
         dy1p = _dgrad(dfeat, W["o2"].w, epilogue=EPI_DGELU, aux=ctx["pre3"])
-        _wgrad(sink, W["o1"].mod, dy1p, ctx["cat"])
+        if self.fc1_stash is not None:
+            # fused mode: the optimizer consumes (dY, X) in lr2_gemm_wgrad_adamw; no 2 GB gradient is written
+            self.fc1_stash.append((dy1p, ctx["cat"]))
+            sink.put_vec(W["o1"].mod.bias, ops.colsum(dy1p))
+        else:
+            _wgrad(sink, W["o1"].mod, dy1p, ctx["cat"])
         dcat = torch.empty_like(ctx["cat"])
         if items <= 256:
             bn = 64 if items <= 64 else (128 if items <= 128 else 256)

@@ -39,6 +39,8 @@ class FusedAdamW(Optimizer):
         self._tables = {}      # group index -> dict
         self._shadows = {}     # id(p) -> bf16 tensor (may be registered externally)
         self._grad_src = {}    # id(p) -> tensor used as gradient instead of p.grad (e.g. bf16 wgrad buffers)
+        self._fused = {}       # id(p) -> provider() of [(dY, X)] for the fused wgrad+AdamW kernel
+        self._hyper = {}       # group index -> device hyper-parameter buffer
 
     # -- extras -----------------------------------------------------------
     def register_shadow(self, p, shadow):
@@ -49,6 +51,13 @@ class FusedAdamW(Optimizer):
     def register_grad(self, p, grad):
         """Read the gradient of `p` from `grad` (fp32 or bf16 buffer owned by the caller)."""
         self._grad_src[id(p)] = grad
+        self._tables.clear()
+
+    def register_fused_wgrad(self, p, provider):
+        """Update the 2-D weight `p` with lr2_gemm_wgrad_adamw: `provider()` returns the list of
+        (dY [rows, out] bf16, X [rows, in] bf16) activations stashed by backward since the last step; the
+        gradient dY^T X is consumed inside the kernel and never materialised (p.grad stays None)."""
+        self._fused[id(p)] = provider
         self._tables.clear()
 
     def shadow_of(self, p):
@@ -62,12 +71,9 @@ class FusedAdamW(Optimizer):
         g = self._grad_src.get(id(p))
         return g if g is not None else p.grad
 
-    def _build(self, gi, group):
+    def _build(self, gi, group, ps):
         L = _lib.load()
         chunk = L.lr2_adamw_chunk_elems()
-        ps = [p for p in group["params"] if self._grad_of(p) is not None]
-        if not ps:
-            return None
         dev = ps[0].device
         ptrs, meta, chunks, gptrs = [], [], [], []
         for t, p in enumerate(ps):
@@ -91,12 +97,29 @@ class FusedAdamW(Optimizer):
             gptrs.append(g.data_ptr())
             for off in range(0, p.numel(), chunk):
                 chunks += [t, off]
-        tab = dict(params=ps, gptrs=gptrs, n_chunks=len(chunks) // 2,
+        tab = dict(params=ps, ids=[id(p) for p in ps], gptrs=gptrs, n_chunks=len(chunks) // 2,
                    ptrs=torch.tensor(ptrs, dtype=torch.int64, device=dev),
                    meta=torch.tensor(meta, dtype=torch.int64, device=dev),
-                   chunks=torch.tensor(chunks, dtype=torch.int64, device=dev),
-                   hyper=torch.zeros(8, dtype=torch.float32, device=dev), hyper_host=None)
+                   chunks=torch.tensor(chunks, dtype=torch.int64, device=dev))
         return tab
+
+    def _hyper_buf(self, gi, group, dev):
+        """Device-side hyper-parameters of group gi: {step_size, b1, b2, eps, 1-b1, 1-b2, grad_scale, lr}."""
+        ent = self._hyper.get(gi)
+        if ent is None:
+            ent = {"dev": torch.zeros(8, dtype=torch.float32, device=dev), "host": None, "t": 0}
+            self._hyper[gi] = ent
+        beta1, beta2 = group["betas"]
+        lr = group["lr"]
+        ent["t"] += 1
+        step_size = lr
+        if group["correct_bias"]:
+            step_size = lr * math.sqrt(1.0 - beta2 ** ent["t"]) / (1.0 - beta1 ** ent["t"])
+        hv = (step_size, beta1, beta2, group["eps"], 1.0 - beta1, 1.0 - beta2, self.grad_scale, lr)
+        if ent["host"] != hv:
+            ent["dev"].copy_(torch.tensor(hv, dtype=torch.float32))
+            ent["host"] = hv
+        return ent["dev"]
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -106,31 +129,41 @@ class FusedAdamW(Optimizer):
                 loss = closure()
         L = _lib.load()
         for gi, group in enumerate(self.param_groups):
-            tab = self._tables.get(gi)
-            if tab is not None:
-                cur = [self._grad_of(p) for p in tab["params"]]
-                if any(g is None for g in cur) or [g.data_ptr() for g in cur] != tab["gptrs"] or \
-                        len(tab["params"]) != sum(1 for p in group["params"] if self._grad_of(p) is not None):
-                    tab = None
-            if tab is None:
-                tab = self._build(gi, group)
-                self._tables[gi] = tab
-            if tab is None:
+            live = [p for p in group["params"] if id(p) not in self._fused and self._grad_of(p) is not None]
+            fused = [p for p in group["params"] if id(p) in self._fused]
+            if not live and not fused:
                 continue
-            beta1, beta2 = group["betas"]
-            lr = group["lr"]
-            step_size = lr
-            for p in tab["params"]:
-                self.state[p]["step"] += 1
-            if group["correct_bias"]:
-                t = self.state[tab["params"][0]]["step"]
-                step_size = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
-            hv = (step_size, beta1, beta2, group["eps"], 1.0 - beta1, 1.0 - beta2, self.grad_scale, lr)
-            if tab["hyper_host"] != hv:
-                tab["hyper"].copy_(torch.tensor(hv, dtype=torch.float32))
-                tab["hyper_host"] = hv
-            _lib.run(L.lr2_adamw_multi, tab["ptrs"].data_ptr(), tab["meta"].data_ptr(), tab["chunks"].data_ptr(),
-                     tab["n_chunks"], tab["hyper"].data_ptr(), _lib.stream())
+            hyper = self._hyper_buf(gi, group, (live or fused)[0].device)
+            tab = self._tables.get(gi)
+            if tab is not None and ([id(p) for p in live] != tab["ids"] or
+                                    [self._grad_of(p).data_ptr() for p in live] != tab["gptrs"]):
+                tab = None
+            if tab is None and live:
+                tab = self._build(gi, group, live)
+                self._tables[gi] = tab
+            if live:
+                for p in live:
+                    self.state[p]["step"] += 1
+                _lib.run(L.lr2_adamw_multi, tab["ptrs"].data_ptr(), tab["meta"].data_ptr(),
+                         tab["chunks"].data_ptr(), tab["n_chunks"], hyper.data_ptr(), _lib.stream())
+            for p in fused:
+                pairs = self._fused[id(p)]()
+                if not pairs:
+                    continue
+                dy = pairs[0][0] if len(pairs) == 1 else torch.cat([a for a, _ in pairs], dim=0)
+                x = pairs[0][1] if len(pairs) == 1 else torch.cat([b for _, b in pairs], dim=0)
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = 0
+                    st["exp_avg"] = torch.zeros_like(p.data)
+                    st["exp_avg_sq"] = torch.zeros_like(p.data)
+                st["step"] += 1
+                sh = self._shadows.get(id(p))
+                out_f, in_f = p.shape
+                _lib.run(L.lr2_gemm_wgrad_adamw, dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), dy.shape[0],
+                         out_f, in_f, p.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
+                         sh.data_ptr() if sh is not None else None, hyper.data_ptr(), float(group["weight_decay"]),
+                         _lib.stream())
         return loss
 
 

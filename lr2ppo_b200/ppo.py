@@ -42,6 +42,8 @@ def build_optimizer(args, model):
                                                lr=args.critic_learning_rate, correct_bias=False)
     for eng, opt in ((model.actor._engine, optimizer), (model.critic._engine, critic_optimizer)):
         attach_shadows(eng, opt)
+        if getattr(args, "fused_fc1", True):
+            eng.enable_fused_fc1(opt)
     sched = getattr(args, "scheduler", "linear")
     if sched == "constant":
         scheduler = str2scheduler[sched](optimizer)

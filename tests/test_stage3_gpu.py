@@ -1,0 +1,119 @@
+"""Stage-3 LR2PPO step (rollout + update) on the CUDA engine vs the CPU oracle restatement
+(oracle/stage3_ref.py, pinned to the reference by tests/golden/*).  The reference update runs with dropout 0.1
+live; parity is defined with dropout off (model.eval()), as SURVEY.md §7 prescribes.
+bf16 compute: 2e-2 relative to each tensor's scale; permutations / indices bit-exact."""
+import argparse
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from tests import golden_util
+from oracle import stage3_ref
+
+TOL = 2e-2
+
+
+def _margs():
+    c = golden_util.FUSION_CFG
+    return argparse.Namespace(mode="reg", labels_num=3, seq_length=c["seq_length"], max_imgs=c["max_imgs"],
+                              visual_feat_dim=c["feat"])
+
+
+def _hp(fused):
+    return argparse.Namespace(learning_rate=1e-5, critic_learning_rate=2e-5, optimizer="adamw", scheduler="constant",
+                              train_steps=1000, warmup=0.1, kl_div_loss_weight=0.001, entropy_weight=0.001,
+                              value_clip=0.5, mode="reg", fused_fc1=fused)
+
+
+def _rel(d, ref):
+    d, ref = d.detach().float().cpu(), ref.detach().float().cpu()
+    return ((d - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
+
+
+def _build_gpu(sds):
+    from lr2ppo_b200 import ppo
+    model = ppo.ActorCritic(_margs(), _margs())
+    reward = ppo.Reward(_margs(), _margs())
+    model.actor.load_state_dict(sds["actor"]); model.critic.load_state_dict(sds["critic"])
+    reward.load_state_dict(sds["reward"])
+    return model.cuda().eval(), reward.cuda().eval()
+
+
+@pytest.fixture(scope="module")
+def sds():
+    return {k: golden_util.make_state_dict(k) for k in ("actor", "critic", "reward")}
+
+
+def test_stage3_step_vs_cpu_oracle(sds):
+    from lr2ppo_b200 import ppo
+    g = torch.Generator().manual_seed(5)
+    bs = 6
+    text = torch.randn(bs, 2, 196, 768, generator=g)
+    img = torch.randn(bs, 1, 16, 768, generator=g).repeat(1, 2, 1, 1)
+    tgts = torch.randint(0, 3, (bs, 2), generator=g)
+    # ---- CPU oracle
+    ra = stage3_ref.RefModel(sds["actor"]); rc = stage3_ref.RefModel(sds["critic"])
+    rr = stage3_ref.RefModel(sds["reward"], trainable=False)
+    mem_ref, out_ref = stage3_ref.step(ra, rc, rr, text, img, 1e-5, 2e-5)
+    # ---- CUDA engine (fused out_layer.fc1 wgrad+AdamW on)
+    model, reward = _build_gpu(sds)
+    hp = _hp(True)
+    opt, copt, sch, csch = ppo.build_optimizer(hp, model)
+    mem = ppo.rollout(model, reward, text.cuda(), img.cuda(), tgts.cuda())
+    state, next_state, scores, rewards, value = mem[:5]
+    assert torch.equal(next_state.cpu(), mem_ref[1])                      # bit-exact permutations
+    assert _rel(scores, mem_ref[2]) < TOL and _rel(rewards, mem_ref[3]) < TOL and _rel(value, mem_ref[4]) < TOL
+    # update on the ORACLE's memory so both sides optimise the same objective
+    mem_g = [mem_ref[0].cuda(), mem_ref[1].cuda(), mem_ref[2].cuda(), mem_ref[3].cuda(), mem_ref[4].cuda(),
+             text.cuda(), img.cuda(), tgts.cuda()]
+    stats = ppo.update_batch(hp, model, opt, copt, mem_g)
+    names = ["policy_loss", "value_loss"]
+    for i, n in enumerate(names):
+        assert abs(stats[i].item() - out_ref[n].item()) <= TOL * max(1e-3, abs(out_ref[n].item())), (n, stats[i], out_ref[n])
+    # first Adam moment = 0.1 * gradient: linear in the gradient, compared on every parameter
+    for net, ref, o in ((model.actor, ra, opt), (model.critic, rc, copt)):
+        rms = {n: (ref.m[n].double().norm() / max(1, ref.m[n].numel()) ** 0.5).item() for n in ref.m}
+        top = max(rms.values())
+        for n, p in net.named_parameters():
+            got = o.state[p]["exp_avg"]
+            if rms[n] < 1e-4 * top:
+                assert (got.double().norm() / max(1, got.numel()) ** 0.5).item() < 1e-2 * top, n
+                continue
+            gs, rs = golden_util.grad_sample(got, 65536), golden_util.grad_sample(ref.m[n], 65536)
+            scale = max(rs.abs().max().item(), rms[n])
+            err = (gs.float().cpu() - rs).abs().max().item() / scale
+            assert err < 5 * TOL, (n, err)
+            nerr = abs(got.double().norm().item() - ref.m[n].double().norm().item()) / ref.m[n].double().norm().item()
+            assert nerr < TOL, (n, nerr)
+
+
+def test_fused_fc1_update_equals_unfused(sds):
+    from lr2ppo_b200 import ppo
+    g = torch.Generator().manual_seed(6)
+    bs = 4
+    text = torch.randn(bs, 2, 196, 768, generator=g).cuda()
+    img = torch.randn(bs, 1, 16, 768, generator=g).repeat(1, 2, 1, 1).cuda()
+    tgts = torch.randint(0, 3, (bs, 2), generator=g).cuda()
+    results = []
+    for fused in (True, False):
+        model, reward = _build_gpu(sds)
+        hp = _hp(fused)
+        opt, copt, _, _ = ppo.build_optimizer(hp, model)
+        mem = ppo.rollout(model, reward, text, img, tgts)
+        for _ in range(2):
+            ppo.update_batch(hp, model, opt, copt, mem)
+        w = model.actor.out_layer.fc1.weight
+        assert (w.grad is None) == fused                                  # fused: no gradient tensor exists
+        results.append((golden_util.grad_sample(w.detach(), 1 << 18).cpu(),
+                        golden_util.grad_sample(opt.state[w]["exp_avg"], 1 << 18).cpu(),
+                        golden_util.grad_sample(model.actor._engine.bank.get(w), 1 << 18).float().cpu(),
+                        model.critic.out_layer.fc1.bias.detach().cpu().clone()))
+        del model, reward, opt, copt
+        torch.cuda.empty_cache()
+    (wf, mf, sf, bf_), (wu, mu, su, bu) = results
+    assert _rel(mf, mu) < 1e-3                  # same fp32 accumulation, different tile order only
+    assert (wf - wu).abs().max().item() < 1e-6
+    assert torch.equal(sf, wf.to(torch.bfloat16).float())                # bf16 shadow refreshed by the fused kernel
+    assert _rel(bf_, bu) < 1e-5
