@@ -202,6 +202,8 @@ def main():
     if sync is not None:
         sync.broadcast_params(model)
         sync.broadcast_params(reward)
+        sync.attach(model.actor, opt)
+        sync.attach(model.critic, copt)
 
     # synthetic LRMovieNet-shaped batches in PINNED host memory (text 28.9 MB, img 2.4 MB, tgts 384 B each)
     g = torch.Generator().manual_seed(100 + rank)

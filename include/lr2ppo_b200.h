@@ -118,6 +118,10 @@ int lr2_xattn_bwd(const void* q, long long ldq, const void* k, const void* v, lo
  * ref: finetune/ppo.py:268-271 (text_emb[batch_index, index]) fused with the fp32 -> bf16 cast. */
 int lr2_cast_gather_bf16(const float* src, const long long* index, void* dst_bf16, int bs, int T_src, int T_dst,
                          long long row_elems, void* stream);
+/* dst[b, j, :] = src[b, index[b, j], :] on bf16 rows (feature reuse when index repeats items: the reward
+ * model's 4-slot input [0, 1, pi(0), pi(1)] holds only 2 distinct items, ref: finetune/ppo.py:318-322). */
+int lr2_gather_rows_bf16(const void* src, const long long* index, void* dst, int bs, int T_src, int T_dst,
+                         long long row_elems, void* stream);
 /* grouped row copy: dst[(g*dst_gstride + dst_off + r), :] (+)= src[(g*src_gstride + src_off + r), :]
  * ref: finetune/ppo.py:224 (cat of x and img_feature) and its backward split. */
 int lr2_rows_copy_bf16(const void* src, long long src_gstride, long long src_off, void* dst, long long dst_gstride,

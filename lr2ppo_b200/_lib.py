@@ -35,6 +35,7 @@ SIGNATURES = {
     "lr2_xattn_bwd": (i32, [vp, i64, vp, vp, i64, vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, f32, f32,
                             vp]),
     "lr2_cast_gather_bf16": (i32, [vp, vp, vp, i32, i32, i32, i64, vp]),
+    "lr2_gather_rows_bf16": (i32, [vp, vp, vp, i32, i32, i32, i64, vp]),
     "lr2_rows_copy_bf16": (i32, [vp, i64, i64, vp, i64, i64, i64, i64, i32, i32, vp]),
     "lr2_colsum_partials_floats": (i64, [i32]),
     "lr2_colsum_bf16": (i32, [vp, i64, i64, i32, vp, vp, i32, vp]),

@@ -151,9 +151,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
 // One output row r, 8 consecutive output columns c..c+7 (c % 8 == 0, c + 8 <= ncols).
 // epi_math8 loads bias / aux / old C and transforms v in registers (pre = bf16 pre-activation for C2);
 // epi_write8 issues the stores.  Split so that the caller can interleave two independent groups.
+template <bool ADAMW>
 __device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], uint4& pre, long long r, int c) {
   const long long off = r * p.ldc + c;
-  if (p.epi == LR2_EPI_NONE) {
+  if (!ADAMW && p.epi == LR2_EPI_NONE) {
     if (p.c_f32 && p.beta != 0.f) {
       const float4* o = reinterpret_cast<const float4*>((const float*)p.C + off);
       float4 a = o[0], b = o[1];
@@ -162,7 +163,7 @@ __device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], ui
     }
     return;
   }
-  if (p.epi == LR2_EPI_ADAMW) {
+  if constexpr (ADAMW) {
     // ref: tencentpretrain/utils/optimizers.py:374-402; acc = this tile of the weight gradient
     const float lr = p.adam_hyper[0], b1 = p.adam_hyper[1], b2 = p.adam_hyper[2], eps = p.adam_hyper[3],
                 omb1 = p.adam_hyper[4], omb2 = p.adam_hyper[5], gs = p.adam_hyper[6], lrd = p.adam_hyper[7];
@@ -194,7 +195,7 @@ __device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], ui
       *reinterpret_cast<uint4*>(p.adam_shadow + off) = u;
     }
     return;  // epi_write8 stores v (the new parameter) as fp32 into C
-  }
+  } else {
   if (p.bias != nullptr && (p.epi == LR2_EPI_BIAS || p.epi == LR2_EPI_BIAS_GELU || p.epi == LR2_EPI_BIAS_DROP_RES)) {
     const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
     const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
@@ -241,6 +242,7 @@ __device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], ui
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += a[i];
   }
+  }
 }
 __device__ __forceinline__ void epi_write8(const GemmParams& p, const float (&v)[8], const uint4& pre, long long r,
                                            int c) {
@@ -259,7 +261,7 @@ __device__ __forceinline__ void epi_write8(const GemmParams& p, const float (&v)
 }
 __device__ __forceinline__ void epi_store8(const GemmParams& p, float (&v)[8], long long r, int c) {
   uint4 pre = make_uint4(0, 0, 0, 0);
-  epi_math8(p, v, pre, r, c);
+  epi_math8<false>(p, v, pre, r, c);
   epi_write8(p, v, pre, r, c);
 }
 
@@ -299,7 +301,7 @@ struct SmemLayout {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024;  // +1024 for manual alignment
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool ADAMW>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
             const GemmParams p) {
@@ -482,10 +484,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
               float v0[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
               float v1[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
               uint4 p0 = make_uint4(0, 0, 0, 0), p1 = make_uint4(0, 0, 0, 0);
-              epi_math8(q, v0, p0, m0, n);
-              epi_math8(q, v1, p1, m1, n);
-              epi_write8(q, v0, p0, m0, n);
-              epi_write8(q, v1, p1, m1, n);
+              if constexpr (ADAMW) {   // HBM-bound: one group at a time keeps the register budget
+                epi_math8<true>(q, v0, p0, m0, n);
+                epi_write8(q, v0, p0, m0, n);
+                epi_math8<true>(q, v1, p1, m1, n);
+                epi_write8(q, v1, p1, m1, n);
+              } else {
+                epi_math8<false>(q, v0, p0, m0, n);
+                epi_math8<false>(q, v1, p1, m1, n);
+                epi_write8(q, v0, p0, m0, n);
+                epi_write8(q, v1, p1, m1, n);
+              }
             } else {
 #pragma unroll 1
               for (int h2 = 0; h2 < 2; ++h2) {
@@ -621,19 +630,19 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool ADAMW = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout<BN>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel<BN, A_MN, B_MN, ADAMW>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return LR2_ERR_CUDA;
     configured = true;
   }
   const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
   const int total = m_tiles * n_tiles * p.splits;
   const int grid = total < num_sms() ? total : num_sms();
-  gemm_kernel<BN, A_MN, B_MN><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, p); LR2_LAUNCHED(1);
+  gemm_kernel<BN, A_MN, B_MN, ADAMW><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, p); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 
@@ -701,6 +710,7 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   p.beta = beta; p.drop_p = drop_p; p.seed = seed; p.site = site;
   p.drop_thresh = dropout_thresh(drop_p); p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.ws = reinterpret_cast<float*>(workspace);
+  { static int r = -1; if (r < 0) { const char* e = getenv("LR2_GEMM_RASTER"); r = e ? atoi(e) : 0; } p.raster = r; }
   const long long out_rows = transposed_out ? N : M;
   p.ws_slab = out_rows * ldc;
 
@@ -735,7 +745,8 @@ extern "C" int lr2_gemm_wgrad_adamw(const void* dY, long long lddy, const void* 
        reinterpret_cast<uintptr_t>(shadow_bf16)) & 15)
     return LR2_ERR_MISALIGNED;
   if (hyper == nullptr) return LR2_ERR_BAD_SHAPE;
-  constexpr int BN = 128;
+  static int BN_sel = 0;
+  if (BN_sel == 0) { const char* e = getenv("LR2_ADAMW_BN"); BN_sel = e ? atoi(e) : 128; }
   CUtensorMap ta, tb;
   int rc = get_tmap(dY, out_f, rows, lddy, 64, BK, &ta);   // A: MN-major [K=rows, M=out_f]
   if (rc != LR2_OK) return rc;
@@ -751,5 +762,6 @@ extern "C" int lr2_gemm_wgrad_adamw(const void* dY, long long lddy, const void* 
   p.raster = 1;   // each CTA walks along a row panel: long contiguous p/m/v streams per row
   p.adam_m = exp_avg; p.adam_v = exp_avg_sq; p.adam_shadow = reinterpret_cast<bf16*>(shadow_bf16);
   p.adam_hyper = hyper; p.adam_wd = weight_decay;
-  return launch_major<BN>(true, true, ta, tb, p, stream);
+  if (BN_sel == 256) return launch<256, true, true, true>(ta, tb, p, stream);
+  return launch<128, true, true, true>(ta, tb, p, stream);
 }

@@ -300,3 +300,31 @@ extern "C" int lr2_cast_bf16_to_f32(const void* src, float* dst, long long n, vo
   cast_bf16_f32_kernel<<<grid_for(n, 256), 256, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(src), dst, n); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
+
+// bf16 -> bf16 indexed row gather: dst[b, j, :] = src[b, index[b, j], :]  (pooled-feature reuse for the
+// reward model's duplicated items, ref: finetune/ppo.py:318-322 with index = [0, 1, pi(0), pi(1)])
+namespace lr2 {
+__global__ void gather_bf16_kernel(const bf16* __restrict__ src, const long long* __restrict__ index,
+                                   bf16* __restrict__ dst, int bs, int T_src, int T_dst, long long row_elems) {
+  const long long vec_per_row = row_elems / 8;
+  const long long total = (long long)bs * T_dst * vec_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long slot = i / vec_per_row, c = (i % vec_per_row) * 8;
+    const long long b = slot / T_dst, j = slot % T_dst;
+    const long long sj = index[b * T_dst + j];
+    *reinterpret_cast<uint4*>(dst + slot * row_elems + c) =
+        *reinterpret_cast<const uint4*>(src + (b * T_src + sj) * row_elems + c);
+  }
+}
+}  // namespace lr2
+extern "C" int lr2_gather_rows_bf16(const void* src, const long long* index, void* dst, int bs, int T_src, int T_dst,
+                                    long long row_elems, void* stream) {
+  if (bs <= 0 || T_src <= 0 || T_dst <= 0 || row_elems <= 0 || row_elems % 8 || index == nullptr)
+    return LR2_ERR_BAD_SHAPE;
+  const long long total = (long long)bs * T_dst * (row_elems / 8);
+  lr2::gather_bf16_kernel<<<lr2::grid_for(total, 256), 256, 0, S_(stream)>>>(
+      reinterpret_cast<const lr2::bf16*>(src), index, reinterpret_cast<lr2::bf16*>(dst), bs, T_src, T_dst, row_elems);
+  LR2_LAUNCHED(1);
+  LR2_RETURN_LAUNCH();
+}

@@ -1,14 +1,18 @@
 """Data-parallel gradient synchronisation over NCCL (one process per GPU, NVLink 5 / NVSwitch).
 
-The reference trains independent replicas in stage 2/3 (no DDP wrap: SURVEY.md §0 fact 5); the
-north_star adds a gradient all-reduce.  Gradients are SUM-reduced and the 1/world factor is folded
-into the fused AdamW (`grad_scale`), so no extra pass touches the 2 GB out_layer.fc1 gradient.
-Small gradients travel in one flat bucket; tensors >= 64 MB are reduced in place.
+The reference trains independent replicas in stage 2/3 (no DDP wrap: SURVEY.md §0 fact 5); the north_star adds
+gradient averaging.  Design for the LR2PPO fusion model, where one matrix (out_layer.fc1, 500 M params) holds
+97 % of the parameters but only sees `items` (48) activation rows per rank:
+
+  * out_layer.fc1.weight: instead of all-reducing its 2 GB fp32 gradient, every rank ALL-GATHERS the two
+    activation operands of the weight gradient (dY [items,3072] and X [items,162816], bf16: 15.9 MB per rank)
+    and computes the global-batch gradient locally with a K = world*items GEMM.  NVLink traffic drops from
+    2 x 2 GB to world x 16 MB per model per step.
+  * everything else (19 M params): one flat fp32 bucket, SUM all-reduce.
+  * the 1/world factor is folded into the fused AdamW (`grad_scale`), so no extra pass touches the gradients.
 """
 import torch
 import torch.distributed as dist
-
-BIG = 1 << 24  # elements
 
 
 class GradSync:
@@ -16,29 +20,44 @@ class GradSync:
         self.world = world
         self.group = group
         self._flat = {}
+        self._skip = set()
 
     def broadcast_params(self, module):
         """Replicas must start identical once gradients are averaged (rank 0's initialisation wins)."""
         for p in module.parameters():
             dist.broadcast(p.data, 0, group=self.group)
-        eng = getattr(module, "_engine", None)
-        engines = [eng] if eng is not None else [m._engine for m in module.children() if hasattr(m, "_engine")]
-        for e in engines:
+        for e in self._engines(module):
             e.bank = type(e.bank)()      # bf16 shadows are re-cast from the broadcast weights
 
+    @staticmethod
+    def _engines(module):
+        eng = getattr(module, "_engine", None)
+        return [eng] if eng is not None else [m._engine for m in module.children() if hasattr(m, "_engine")]
+
+    def gather_rows(self, t):
+        """[rows, D] -> [world*rows, D] (all ranks' rows, rank-major)."""
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+    def attach(self, module, optimizer):
+        """Enable the activation-gather path for the module's out_layer.fc1 and fold 1/world into AdamW."""
+        for e in self._engines(module):
+            e.dp_gather = self.gather_rows
+            self._skip.add(id(e.m.out_layer.fc1.weight))
+        optimizer.grad_scale = 1.0 / self.world
+        optimizer._hyper.clear()
+
     def __call__(self, module):
-        small = [p.grad for p in module.parameters() if p.grad is not None and p.grad.numel() < BIG]
-        big = [p.grad for p in module.parameters() if p.grad is not None and p.grad.numel() >= BIG]
-        works = [dist.all_reduce(g, group=self.group, async_op=True) for g in big]
-        if small:
-            n = sum(g.numel() for g in small)
-            flat = self._flat.get(id(module))
-            if flat is None or flat.numel() != n:
-                flat = torch.empty(n, dtype=torch.float32, device=small[0].device)
-                self._flat[id(module)] = flat
-            views = list(flat.split([g.numel() for g in small]))
-            torch._foreach_copy_(views, [g.view(-1) for g in small])
-            dist.all_reduce(flat, group=self.group)
-            torch._foreach_copy_([g.view(-1) for g in small], views)
-        for w in works:
-            w.wait()
+        grads = [p.grad for p in module.parameters() if p.grad is not None and id(p) not in self._skip]
+        if not grads:
+            return
+        n = sum(g.numel() for g in grads)
+        flat = self._flat.get(id(module))
+        if flat is None or flat.numel() != n:
+            flat = torch.empty(n, dtype=torch.float32, device=grads[0].device)
+            self._flat[id(module)] = flat
+        views = list(flat.split([g.numel() for g in grads]))
+        torch._foreach_copy_(views, [g.view(-1) for g in grads])
+        dist.all_reduce(flat, group=self.group)
+        torch._foreach_copy_([g.view(-1) for g in grads], views)

@@ -91,7 +91,7 @@ class _GradSink:
             p.grad.add_(val.reshape(p.shape))
 
 
-def _wgrad(sink, lin, dy, x):
+def _wgrad(sink, lin, dy, x, bias_from=None):
     """dW[out,in] (+)= dy[M,out]^T @ x[M,in]; db (+)= colsum(dy).  Both operands MN-major -> no transposes."""
     gw, beta = sink.buf(lin.weight)
     m_out, k_in = lin.weight.shape
@@ -102,7 +102,7 @@ def _wgrad(sink, lin, dy, x):
     if beta == 0.0 and tiles < 120 and rows >= 1024:
         splits = max(1, min(16, 148 // tiles, rows // 512))
     ops.gemm(dy, x, a_mn=True, b_mn=True, out=gw, beta=beta, splits=splits)
-    sink.put_vec(lin.bias, ops.colsum(dy))
+    sink.put_vec(lin.bias, ops.colsum(dy if bias_from is None else bias_from))
 
 
 def _dgrad(dy, lin_w, **kw):
@@ -270,12 +270,17 @@ class FusionEngine:
         bs, Tsrc, S, E = text.shape
         I = img.shape[2]
         T = index.shape[1] if index is not None else Tsrc
-        items = bs * T
+        # Inference-only reuse: when `index` repeats items (reward model: [0, 1, pi(0), pi(1)] holds 2 distinct
+        # items) the pooled feature of each (clip, tag) item is computed once and gathered afterwards. Exact in
+        # eval mode; not used when training (independent dropout masks per occurrence).
+        reuse = index is not None and T > Tsrc and not train and not save
+        body_index = None if reuse else index
+        items = bs * (Tsrc if reuse else T)
         if seed is None:
             self._calls += 1
             seed = (torch.initial_seed() * 1000003 + self._calls) & 0x7FFFFFFFFFFFFFFF
-        xt = ops.cast_gather(text.reshape(bs, Tsrc, S * E), index).view(items * S, E)
-        xi = ops.cast_gather(img.reshape(bs, Tsrc, I * E), index).view(items * I, E)
+        xt = ops.cast_gather(text.reshape(bs, Tsrc, S * E), body_index).view(items * S, E)
+        xi = ops.cast_gather(img.reshape(bs, Tsrc, I * E), body_index).view(items * I, E)
         tf, c_tp = mlp_forward(W["tp1"], W["tp2"], xt, save)
         imf, c_ip = mlp_forward(W["ip1"], W["ip2"], xi, save)
         cat = torch.empty((items, (S + I) * E), dtype=bf16, device=text.device)
@@ -298,6 +303,9 @@ class FusionEngine:
         else:
             y1 = ops.gemm(cat, o1.w, epilogue=EPI_BIAS_GELU, bias=o1.b, c2=pre3, splits=4)
         feat = ops.gemm(y1, W["o2"].w, epilogue=EPI_BIAS, bias=W["o2"].b)
+        if reuse:
+            feat = ops.gather_rows(feat.view(bs, Tsrc, E), index).view(bs * T, E)
+            items = bs * T
         ctx = None
         if self.kind == "actor":
             n_out = m.head.weight.shape[0]
@@ -349,6 +357,9 @@ class FusionEngine:
             # fused mode: the optimizer consumes (dY, X) in lr2_gemm_wgrad_adamw; no 2 GB gradient is written
             self.fc1_stash.append((dy1p, ctx["cat"]))
             sink.put_vec(W["o1"].mod.bias, ops.colsum(dy1p))
+        elif self.dp_gather is not None:
+            # data parallel: gather the two (small) wgrad operands instead of all-reducing the 2 GB gradient
+            _wgrad(sink, W["o1"].mod, self.dp_gather(dy1p), self.dp_gather(ctx["cat"]), bias_from=dy1p)
         else:
             _wgrad(sink, W["o1"].mod, dy1p, ctx["cat"])
         dcat = torch.empty_like(ctx["cat"])

@@ -378,3 +378,14 @@ def ndcg_presorted(pred_rel, true_rel, ks, lens=None):
     _lib.run(L.lr2_ndcg_presorted, ptr(pred_rel), ptr(true_rel), ptr(lens), B, N, ptr(ks_t), len(ks),
                                ptr(log2_table(N, dev)), ptr(out), ptr(scratch), _lib.stream())
     return out
+
+
+def gather_rows(src, index):
+    """src bf16 [bs, T_src, R], index i64 [bs, T_dst] -> bf16 [bs, T_dst, R]."""
+    L = _L()
+    _cuda(src, bf16, "src"); _cuda(index, i64, "index")
+    bs, T_src, R = src.shape
+    T_dst = index.shape[1]
+    out = torch.empty((bs, T_dst, R), dtype=bf16, device=src.device)
+    _lib.run(L.lr2_gather_rows_bf16, ptr(src), ptr(index), ptr(out), bs, T_src, T_dst, R, _lib.stream())
+    return out

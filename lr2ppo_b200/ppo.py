@@ -42,7 +42,8 @@ def build_optimizer(args, model):
                                                lr=args.critic_learning_rate, correct_bias=False)
     for eng, opt in ((model.actor._engine, optimizer), (model.critic._engine, critic_optimizer)):
         attach_shadows(eng, opt)
-        if getattr(args, "fused_fc1", True):
+        # opt-in: correct but DRAM-page-locality bound today, so slower than wgrad + AdamW
+        if getattr(args, "fused_fc1", False):
             eng.enable_fused_fc1(opt)
     sched = getattr(args, "scheduler", "linear")
     if sched == "constant":

@@ -63,6 +63,20 @@ def main():
         ("fc1 wgrad 3072x162816 K=48 f32", 2 * items * H * K1, H * K1 * 4 + items * K1 * 2,
          lambda: ops.gemm(dy1, cat, a_mn=True, b_mn=True, out=gW)),
     ]
+    bn = int(os.environ.get("BENCH_BN", "0"))
+    if bn:
+        cases += [
+            (f"fwd 9408x3072x768 gelu+pre BN={bn}", 2 * Mt * H * E, (Mt * E + H * E + 2 * Mt * H) * 2,
+             lambda: ops.gemm(x, w1, out=out1, epilogue=ops.EPI_BIAS_GELU, bias=b1, c2=pre, block_n=bn)),
+            (f"fwd 9408x768x3072 bias BN={bn}", 2 * Mt * H * E, (Mt * H + H * E + Mt * E) * 2,
+             lambda: ops.gemm(h, w2, out=out2, epilogue=ops.EPI_BIAS, bias=b2, block_n=bn)),
+            (f"dgrad 9408x768x3072 (b_mn) BN={bn}", 2 * Mt * H * E, (Mt * H + H * E + Mt * E) * 2,
+             lambda: ops.gemm(dh, w1, b_mn=True, out=out2, block_n=bn)),
+            (f"wgrad 3072x768 K=9408 f32 BN={bn}", 2 * Mt * H * E, (Mt * H + Mt * E) * 2 + H * E * 4,
+             lambda: ops.gemm(dh, x, a_mn=True, b_mn=True, out=gw1, block_n=bn)),
+            (f"fc1 wgrad 3072x162816 K=48 f32 BN={bn}", 2 * items * H * K1, H * K1 * 4 + items * K1 * 2,
+             lambda: ops.gemm(dy1, cat, a_mn=True, b_mn=True, out=gW, block_n=bn)),
+        ]
     only = sys.argv[1] if len(sys.argv) > 1 else None
     for name, flops, byts, fn in cases:
         if only and only not in name:
@@ -77,6 +91,16 @@ def main():
     us = timeit(lambda: opt.step(), 5)
     n = p.numel()
     print(f"{'adamw 500M fp32 grad + bf16 shadow':42s} {us:9.1f} us  {'':8s}           {30 * n / us / 1e3:8.1f} GB/s")
+    from lr2ppo_b200 import _lib
+    L = _lib.load()
+    st = opt.state[p]
+    sh = opt.shadow_of(p)
+    hyper = torch.tensor([1e-4, 0.9, 0.999, 1e-6, 0.1, 0.001, 1.0, 1e-4], device=dev)
+    fn = lambda: _lib.run(L.lr2_gemm_wgrad_adamw, dy1.data_ptr(), dy1.stride(0), cat.data_ptr(), cat.stride(0), items,
+                          H, K1, p.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), sh.data_ptr(),
+                          hyper.data_ptr(), 0.01, _lib.stream())
+    us = timeit(fn, 5)
+    print(f"{'fused fc1 wgrad+adamw (26 B/param)':42s} {us:9.1f} us  {'':8s}           {26 * n / us / 1e3:8.1f} GB/s")
 
 
 if __name__ == "__main__":
