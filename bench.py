@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
 
@@ -217,7 +218,7 @@ def main():
     h2d_bytes = sum(t.numel() * t.element_size() for t in pool[0])
     stats_host = torch.empty(10, dtype=torch.float32).pin_memory()
 
-    def step(batch):
+    def eager_step(batch):
         text, img, tgts = batch
         mem = ppo.rollout(model, reward, text, img, tgts)
         model.train()                                              # update runs in train mode (dropout 0.1 live)
@@ -225,6 +226,22 @@ def main():
         model.eval()
         sch.step(); csch.step()
         return stats
+
+    # single GPU: the whole step (rollout + update, ~300 launches) is captured once and replayed as a CUDA graph
+    use_graph = world == 1 and not args.no_graph
+    launches_per_step = None
+    if use_graph:
+        for i in range(2):
+            eager_step(resident[i])
+        c0 = _lib.launch_count()
+        gstep = ppo.GraphedStage3Step(hp, model, reward, opt, copt, *resident[0], warmup=2)
+        launches_per_step = (_lib.launch_count() - c0) // 3      # 2 warm-up passes + 1 captured pass
+
+        def step(batch):
+            sch.step(); csch.step()
+            return gstep(*batch)
+    else:
+        step = eager_step
 
     def barrier():
         if world > 1:
@@ -261,8 +278,9 @@ def main():
     # ---- (2) end-to-end: pinned host -> device every step, stats read back every step ---------------------
     def e2e_step(i):
         text, img, tgts = pool[i % len(pool)]
-        b = (text.to(dev, non_blocking=True), img.to(dev, non_blocking=True), tgts.to(dev, non_blocking=True))
-        stats = step(b)
+        b = None if use_graph else (text.to(dev, non_blocking=True), img.to(dev, non_blocking=True),
+                                    tgts.to(dev, non_blocking=True))
+        stats = step(pool[i % len(pool)]) if use_graph else step(b)   # graph: H2D straight into its static buffers
         stats_host.copy_(stats, non_blocking=False)                # D2H + host sync, as a training loop would log
 
     for i in range(2):
@@ -276,7 +294,7 @@ def main():
         torch.cuda.synchronize()
         _lib.PROFILE = []
         for i in range(args.profile_steps):
-            step(resident[i % len(resident)])
+            eager_step(resident[i % len(resident)])
         torch.cuda.synchronize()
         prof, _lib.PROFILE = _lib.PROFILE, None
         groups = summarize_profile(torch, prof, args.profile_steps)
@@ -341,7 +359,8 @@ def main():
                            "tflop_per_step_per_gpu": FLOP_PER_QUERY * BS / 1e12},
                 "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d_bytes * world,
                         "d2h_bytes_per_step": 40 * world, "ms_per_step": ms_e2e / args.steps},
-                "gpu_launches": int(launches), "clocks": sampler.summary(),
+                "gpu_launches": int(launches_per_step * args.steps if use_graph else launches),
+                "launch_mode": "cuda_graph_replay" if use_graph else "eager", "clocks": sampler.summary(),
                 "model_tflops_per_gpu": FLOP_PER_QUERY * BS * args.steps / (ms / 1e3) / 1e12}
         if roofline is not None:
             line["roofline"] = roofline

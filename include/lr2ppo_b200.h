@@ -67,7 +67,8 @@ long long lr2_gemm_workspace_bytes(int M, int N, int splits, int transposed_out,
 int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb, int b_mn_major,
                   void* C, long long ldc, int c_is_f32, int transposed_out, int M, int N, int K, int epilogue,
                   const float* bias, const void* aux, long long ldaux, void* C2, float beta, float drop_p,
-                  unsigned long long seed, unsigned int site, int splits, void* workspace, int block_n,
+                  unsigned long long seed, unsigned int site, const void* seed_dev, int splits, void* workspace,
+                  int block_n,
                   void* stream);
 
 /* Fused weight-gradient + AdamW for one Linear weight [out_f, in_f] (used for out_layer.fc1, 500 M params):
@@ -98,7 +99,7 @@ long long lr2_layernorm_bwd_partials_floats(int D);
 int lr2_layernorm_bwd(const void* dy_bf16, const void* x_bf16, const float* gamma, const float* stats,
                       const void* add_bf16, void* dx_bf16, void* dxm_bf16, float* dgamma, float* dbeta,
                       float* partials, long long rows, int D, float eps, int mode, int g_in, int g_out, int g_off,
-                      float drop_p, unsigned long long seed, unsigned int site, void* stream);
+                      float drop_p, unsigned long long seed, unsigned int site, const void* seed_dev, void* stream);
 
 /* -------------------------------------------------- XiT attention core --
  * Per (item, head): P = softmax(pre_scale * Q K^T); O = (post_scale * P) V, Skv <= 16.
@@ -114,6 +115,9 @@ int lr2_xattn_bwd(const void* q, long long ldq, const void* k, const void* v, lo
                   int Skv, int H, int dh, float pre_scale, float post_scale, void* stream);
 
 /* ------------------------------------------------------ glue kernels --- */
+/* counter[0] += inc (u64, device): the dropout seed offset read through `seed_dev` above; bumping it inside a
+ * captured CUDA graph gives every replay fresh masks (the reference draws new nn.Dropout masks per call). */
+int lr2_bump_counter(void* counter, unsigned long long inc, void* stream);
 /* dst[b, j, :] = bf16(src[b, index[b, j], :]); index == NULL -> identity (T_dst == T_src).
  * ref: finetune/ppo.py:268-271 (text_emb[batch_index, index]) fused with the fp32 -> bf16 cast. */
 int lr2_cast_gather_bf16(const float* src, const long long* index, void* dst_bf16, int bs, int T_src, int T_dst,

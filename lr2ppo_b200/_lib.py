@@ -25,12 +25,13 @@ SIGNATURES = {
     "lr2_note_launches": (None, [i32]),
     "lr2_gemm_workspace_bytes": (i64, [i32, i32, i32, i32, i64]),
     "lr2_gemm_bf16": (i32, [vp, i64, i32, vp, i64, i32, vp, i64, i32, i32, i32, i32, i32, i32, vp, vp, i64, vp,
-                            f32, f32, u64, u32, i32, vp, i32, vp]),
+                            f32, f32, u64, u32, vp, i32, vp, i32, vp]),
     "lr2_gemm_wgrad_adamw": (i32, [vp, i64, vp, i64, i32, i32, i32, vp, vp, vp, vp, vp, f32, vp]),
     "lr2_layernorm_fwd": (i32, [vp, vp, vp, vp, vp, i64, i32, f32, i32, i32, i32, i32, vp]),
     "lr2_layernorm_bwd_partials_floats": (i64, [i32]),
     "lr2_layernorm_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, i32, f32, i32, i32, i32, i32, f32, u64,
-                                u32, vp]),
+                                u32, vp, vp]),
+    "lr2_bump_counter": (i32, [vp, u64, vp]),
     "lr2_xattn_fwd": (i32, [vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, f32, f32, vp]),
     "lr2_xattn_bwd": (i32, [vp, i64, vp, vp, i64, vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, f32, f32,
                             vp]),

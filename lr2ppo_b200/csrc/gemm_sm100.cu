@@ -53,6 +53,7 @@ struct GemmParams {
   unsigned int drop_thresh;  // drop_p * 2^32 (host-computed)
   float drop_scale;    // 1/(1-p)
   unsigned long long seed;
+  const unsigned long long* seed_dev;  // optional device-resident seed offset (CUDA-graph replay safe)
   unsigned int site;
   float* ws;           // split-K workspace [splits][out_rows*ldc]
   long long ws_slab;   // elements per slab
@@ -216,7 +217,8 @@ __device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], ui
   if (p.drop_p > 0.f) {
     const uint32_t th = p.drop_thresh;
     const uint64_t lin = (uint64_t)off;  // ldc-strided linear index; multiple of 8
-    keep = dropout_keep4(p.seed, p.site, lin >> 2, th) | (dropout_keep4(p.seed, p.site, (lin >> 2) + 1, th) << 4);
+    const unsigned long long sd = p.seed + (p.seed_dev ? *p.seed_dev : 0ull);
+    keep = dropout_keep4(sd, p.site, lin >> 2, th) | (dropout_keep4(sd, p.site, (lin >> 2) + 1, th) << 4);
     dscale = p.drop_scale;
   }
   if (p.epi == LR2_EPI_BIAS_GELU) {
@@ -668,7 +670,8 @@ extern "C" long long lr2_gemm_workspace_bytes(int M, int N, int splits, int tran
 extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const void* B, long long ldb,
                              int b_mn_major, void* C, long long ldc, int c_is_f32, int transposed_out, int M, int N,
                              int K, int epilogue, const float* bias, const void* aux, long long ldaux, void* C2,
-                             float beta, float drop_p, unsigned long long seed, unsigned int site, int splits,
+                             float beta, float drop_p, unsigned long long seed, unsigned int site,
+                             const void* seed_dev, int splits,
                              void* workspace, int block_n, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (M <= 0 || N <= 0 || K <= 0) return LR2_ERR_BAD_SHAPE;
@@ -708,6 +711,7 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   p.C = C; p.ldc = ldc; p.C2 = reinterpret_cast<bf16*>(C2);
   p.bias = bias; p.aux = reinterpret_cast<const bf16*>(aux); p.ldaux = ldaux;
   p.beta = beta; p.drop_p = drop_p; p.seed = seed; p.site = site;
+  p.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
   p.drop_thresh = dropout_thresh(drop_p); p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   p.ws = reinterpret_cast<float*>(workspace);
   { static int r = -1; if (r < 0) { const char* e = getenv("LR2_GEMM_RASTER"); r = e ? atoi(e) : 0; } p.raster = r; }

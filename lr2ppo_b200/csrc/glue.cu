@@ -328,3 +328,15 @@ extern "C" int lr2_gather_rows_bf16(const void* src, const long long* index, voi
   LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
+
+// counter[0] += inc : advances the device-resident dropout seed once per training forward, so that a
+// captured CUDA graph draws fresh masks on every replay.
+namespace lr2 {
+__global__ void bump_counter_kernel(unsigned long long* c, unsigned long long inc) { c[0] += inc; }
+}  // namespace lr2
+extern "C" int lr2_bump_counter(void* counter, unsigned long long inc, void* stream) {
+  if (counter == nullptr) return LR2_ERR_BAD_SHAPE;
+  lr2::bump_counter_kernel<<<1, 1, 0, S_(stream)>>>(reinterpret_cast<unsigned long long*>(counter), inc);
+  LR2_LAUNCHED(1);
+  LR2_RETURN_LAUNCH();
+}

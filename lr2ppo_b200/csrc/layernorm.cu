@@ -96,7 +96,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ stats, const bf16* __restrict__ add, bf16* __restrict__ dx,
               bf16* __restrict__ dxm, float* __restrict__ partials, long long rows, int D, float eps, int mode,
-              int g_in, int g_out, int g_off, float drop_p, unsigned long long seed, unsigned int site) {
+              int g_in, int g_out, int g_off, float drop_p, unsigned long long seed_in, unsigned int site,
+              const unsigned long long* __restrict__ seed_dev) {
+  const unsigned long long seed = seed_in + (seed_dev ? *seed_dev : 0ull);
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nch = D / 256 + ((D % 256) ? 1 : 0);
@@ -231,7 +233,8 @@ extern "C" long long lr2_layernorm_bwd_partials_floats(int D) { return (long lon
 extern "C" int lr2_layernorm_bwd(const void* dy, const void* x, const float* gamma, const float* stats,
                                  const void* add, void* dx, void* dxm, float* dgamma, float* dbeta, float* partials,
                                  long long rows, int D, float eps, int mode, int g_in, int g_out, int g_off,
-                                 float drop_p, unsigned long long seed, unsigned int site, void* stream) {
+                                 float drop_p, unsigned long long seed, unsigned int site, const void* seed_dev,
+                                 void* stream) {
   if (rows <= 0 || D <= 0 || D % 8 || D > 256 * LN_MAX_CHUNKS) return LR2_ERR_BAD_SHAPE;
   if (mode != 0 && mode != 1) return LR2_ERR_UNSUPPORTED;
   if (partials == nullptr || stats == nullptr) return LR2_ERR_BAD_SHAPE;
@@ -248,7 +251,8 @@ extern "C" int lr2_layernorm_bwd(const void* dy, const void* x, const float* gam
   ln_bwd_kernel<<<nb, LN_WARPS * 32, smem, s>>>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x),
                                                 gamma, stats, reinterpret_cast<const bf16*>(add),
                                                 reinterpret_cast<bf16*>(dx), reinterpret_cast<bf16*>(dxm), partials,
-                                                rows, D, eps, mode, g_in, g_out, g_off, drop_p, seed, site); LR2_LAUNCHED(1);
+                                                rows, D, eps, mode, g_in, g_out, g_off, drop_p, seed, site,
+                                                reinterpret_cast<const unsigned long long*>(seed_dev)); LR2_LAUNCHED(1);
   if (cudaGetLastError() != cudaSuccess) return LR2_ERR_CUDA;
   ln_bwd_reduce_kernel<<<(2 * D + 255) / 256, 256, 0, s>>>(partials, nb, D, dgamma, dbeta); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();

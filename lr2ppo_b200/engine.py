@@ -60,33 +60,39 @@ class _Lin:
         self.b = lin.bias.detach()
 
 
-def _grad_buf(p):
-    """fp32 gradient buffer of parameter p, and beta (1 = accumulate into an existing .grad)."""
-    if p.grad is None:
-        p.grad = torch.empty_like(p, memory_format=torch.contiguous_format)
-        return p.grad, 0.0
-    return p.grad, 1.0
-
-
 class _GradSink:
-    """Tracks which parameters already received a gradient during one backward call."""
+    """Where backward puts parameter gradients.
 
-    def __init__(self):
-        self.fresh = set()
+    written=None: torch semantics — allocate when `.grad` is None, otherwise accumulate.
+    written=set : persistent-buffer mode (CUDA-graph friendly): `.grad` tensors are kept across steps; the first
+                  write to a parameter since `FusionEngine.begin_step()` overwrites the stale value, later writes
+                  in the same step (second forward/backward pair of stage 2) accumulate."""
+
+    def __init__(self, written=None):
+        self.written = written
+
+    def _stale(self, p):
+        if self.written is None or id(p) in self.written:
+            return False
+        self.written.add(id(p))
+        return True
 
     def buf(self, p):
         if p.grad is None:
             p.grad = torch.empty_like(p, memory_format=torch.contiguous_format)
-            self.fresh.add(id(p))
+            if self.written is not None:
+                self.written.add(id(p))
             return p.grad, 0.0
-        if id(p) in self.fresh:  # allocated in this call but already written -> accumulate
-            return p.grad, 1.0
-        return p.grad, 1.0
+        return p.grad, (0.0 if self._stale(p) else 1.0)
 
     def put_vec(self, p, val):
         """val: fp32 tensor shaped like p (small vectors: biases, LayerNorm params, head)."""
         if p.grad is None:
             p.grad = val.reshape(p.shape).clone()
+            if self.written is not None:
+                self.written.add(id(p))
+        elif self._stale(p):
+            p.grad.copy_(val.reshape(p.shape))
         else:
             p.grad.add_(val.reshape(p.shape))
 
@@ -128,7 +134,7 @@ class XitWeights:
         self.p_ffn_out = ffn_seq[2].p
 
 
-def xit_forward(W, x, y, items, Sq, Skv, train, seed, site_base, save, out=None, regroup=None):
+def xit_forward(W, x, y, items, Sq, Skv, train, seed, site_base, save, out=None, regroup=None, seed_dev=None):
     """XiT block on x [items*Sq, E] (queries) and y [items*Skv, E] (keys/values).
     ref: finetune/xit.py:9-148.  Returns (output or `out`, ctx)."""
     E = W.emb
@@ -145,18 +151,20 @@ def xit_forward(W, x, y, items, Sq, Skv, train, seed, site_base, save, out=None,
     post = 1.0 / math.sqrt(E)     # softmax first, then / sqrt(emb): finetune/xit.py:142-143
     a = ops.xattn_fwd(q.view(items, Sq, E), k.view(items, Skv, E), v.view(items, Skv, E), W.heads, 1.0, post)
     a = a.view(items * Sq, E)
-    x1 = ops.gemm(a, W.o.w, epilogue=EPI_BIAS_DROP_RES, bias=W.o.b, aux=x, drop_p=p1, seed=seed, site=site_base + 1)
+    x1 = ops.gemm(a, W.o.w, epilogue=EPI_BIAS_DROP_RES, bias=W.o.b, aux=x, drop_p=p1, seed=seed, site=site_base + 1,
+                  seed_dev=seed_dev)
     l2, st2 = ops.layernorm_fwd(x1, W.ln2.weight.detach(), W.ln2.bias.detach(), W.ln2.eps, 0, want_stats=save)
     pre2 = torch.empty((items * Sq, W.f1.w.shape[0]), dtype=bf16, device=x.device) if save else None
-    h2 = ops.gemm(l2, W.f1.w, epilogue=EPI_BIAS_GELU, bias=W.f1.b, c2=pre2, drop_p=p2, seed=seed, site=site_base + 2)
+    h2 = ops.gemm(l2, W.f1.w, epilogue=EPI_BIAS_GELU, bias=W.f1.b, c2=pre2, drop_p=p2, seed=seed, site=site_base + 2,
+                  seed_dev=seed_dev)
     x2 = ops.gemm(h2, W.f2.w, epilogue=EPI_BIAS_DROP_RES, bias=W.f2.b, aux=x1, drop_p=p3, seed=seed,
-                  site=site_base + 3)
+                  site=site_base + 3, seed_dev=seed_dev)
     xo, st3 = ops.layernorm_fwd(x2, W.ln3.weight.detach(), W.ln3.bias.detach(), W.ln3.eps, 0, out=out,
                                 regroup=regroup, want_stats=save)
     ctx = None
     if save:
         ctx = dict(x=x, y=y, lx=lx, ly=ly, st_x=st_x, st_y=st_y, q=q, k=k, v=v, a=a, x1=x1, st2=st2, l2=l2,
-                   pre2=pre2, h2=h2, x2=x2, st3=st3, p=(p1, p2, p3), seed=seed, site_base=site_base,
+                   pre2=pre2, h2=h2, x2=x2, st3=st3, p=(p1, p2, p3), seed=seed, seed_dev=seed_dev, site_base=site_base,
                    dims=(items, Sq, Skv), regroup=regroup)
     return xo, ctx
 
@@ -167,20 +175,22 @@ def xit_backward(W, ctx, dout, sink, need_dx=True, need_dy=True, dy_extra=None):
     items, Sq, Skv = ctx["dims"]
     E = W.emb
     p1, p2, p3 = ctx["p"]
-    seed, sb = ctx["seed"], ctx["site_base"]
+    seed, sb, sdev = ctx["seed"], ctx["site_base"], ctx["seed_dev"]
     post = 1.0 / math.sqrt(E)
     # final LayerNorm; dx2m = gradient into the (dropout-ed) FFN output
     dx2, dx2m, dg, db = ops.layernorm_bwd(dout, ctx["x2"], W.ln3.weight.detach(), ctx["st3"], W.ln3.eps, 0,
                                           regroup=ctx["regroup"], drop_p=p3, seed=seed, site=sb + 3,
-                                          want_masked=True)
+                                          want_masked=True, seed_dev=sdev)
     sink.put_vec(W.ln3.weight, dg); sink.put_vec(W.ln3.bias, db)
     # FFN
     _wgrad(sink, W.f2.mod, dx2m, ctx["h2"])
-    dh2p = _dgrad(dx2m, W.f2.w, epilogue=EPI_DGELU, aux=ctx["pre2"], drop_p=p2, seed=seed, site=sb + 2)
+    dh2p = _dgrad(dx2m, W.f2.w, epilogue=EPI_DGELU, aux=ctx["pre2"], drop_p=p2, seed=seed, site=sb + 2,
+                  seed_dev=sdev)
     _wgrad(sink, W.f1.mod, dh2p, ctx["l2"])
     dl2 = _dgrad(dh2p, W.f1.w)
     dx1, dx1m, dg, db = ops.layernorm_bwd(dl2, ctx["x1"], W.ln2.weight.detach(), ctx["st2"], W.ln2.eps, 0, add=dx2,
-                                          drop_p=p1, seed=seed, site=sb + 1, want_masked=True)
+                                          drop_p=p1, seed=seed, site=sb + 1, want_masked=True,
+                                          seed_dev=sdev)
     sink.put_vec(W.ln2.weight, dg); sink.put_vec(W.ln2.bias, db)
     # attention
     _wgrad(sink, W.o.mod, dx1m, ctx["a"])
@@ -235,8 +245,15 @@ class FusionEngine:
         self.kind = kind
         self.bank = ShadowBank()
         self._calls = 0
+        self.seed_counter = None   # int64[1] device tensor: dropout seed offset
+        self.persistent_grads = False  # keep .grad buffers across steps (see _GradSink); call begin_step() per step
+        self._written = set()
         self.fc1_stash = None      # list of (dY, X) when out_layer.fc1 is updated by the fused wgrad+AdamW kernel
         self.dp_gather = None      # optional callable(t) -> all-gathered rows (data-parallel fused mode)
+
+    def begin_step(self):
+        """Persistent-gradient mode: start of a new optimizer step (replaces model.zero_grad())."""
+        self._written.clear()
 
     def enable_fused_fc1(self, optimizer):
         """Route out_layer.fc1.weight through lr2_gemm_wgrad_adamw (gradient never materialised)."""
@@ -276,9 +293,17 @@ class FusionEngine:
         reuse = index is not None and T > Tsrc and not train and not save
         body_index = None if reuse else index
         items = bs * (Tsrc if reuse else T)
+        seed_dev = None
         if seed is None:
-            self._calls += 1
-            seed = (torch.initial_seed() * 1000003 + self._calls) & 0x7FFFFFFFFFFFFFFF
+            # dropout seed = host base (torch.initial_seed) + a device-resident counter bumped per training
+            # forward, so a CUDA-graph replay of this call sequence still draws fresh masks; backward reads the
+            # snapshot taken here.
+            seed = (torch.initial_seed() * 1000003 + id(self) % 9973) & 0x7FFFFFFFFFFFFFFF
+            if train:
+                if self.seed_counter is None or self.seed_counter.device != text.device:
+                    self.seed_counter = torch.zeros(1, dtype=torch.int64, device=text.device)
+                ops.bump_counter(self.seed_counter, 1)
+                seed_dev = self.seed_counter.clone() if save else self.seed_counter
         xt = ops.cast_gather(text.reshape(bs, Tsrc, S * E), body_index).view(items * S, E)
         xi = ops.cast_gather(img.reshape(bs, Tsrc, I * E), body_index).view(items * I, E)
         tf, c_tp = mlp_forward(W["tp1"], W["tp2"], xt, save)
@@ -286,7 +311,7 @@ class FusionEngine:
         cat = torch.empty((items, (S + I) * E), dtype=bf16, device=text.device)
         cat_rows = cat.view(items * (S + I), E)
         _, c_x = xit_forward(W["xit"], tf, imf, items, S, I, train, seed, 0, save, out=cat_rows,
-                             regroup=(S, S + I, 0))
+                             regroup=(S, S + I, 0), seed_dev=seed_dev)
         ops.rows_copy(imf, I, 0, cat_rows, S + I, S, items, I, E)
         # out_layer.fc1: weight is the 128-row MMA operand, items are N; split-K streams the weight once
         o1 = W["o1"]
@@ -319,7 +344,7 @@ class FusionEngine:
             return logits, ctx
         # critic / reward: + pos_emb, self-attention over the T items, head on the LAST token
         ops.add_pos_fwd(feat, m.pos_emb.weight.detach()[:T].contiguous(), bs, T)
-        z, c_t = xit_forward(W["xitt"], feat, feat, bs, T, T, train, seed, 3, save)
+        z, c_t = xit_forward(W["xitt"], feat, feat, bs, T, T, train, seed, 3, save, seed_dev=seed_dev)
         logits = ops.rowdot_fwd(z, m.head.weight.detach().view(-1), m.head.bias.detach(), bs, T, T - 1)
         if save:
             ctx = dict(W=W, dims=(bs, T, S, I, E, items), c_tp=c_tp, c_ip=c_ip, c_x=c_x, cat=cat, pre3=pre3, y1=y1,
@@ -331,7 +356,7 @@ class FusionEngine:
         m = self.m
         W = ctx["W"]
         bs, T, S, I, E, items = ctx["dims"]
-        sink = _GradSink()
+        sink = _GradSink(self._written if self.persistent_grads else None)
         dlogits = dlogits.contiguous().to(f32)
         if self.kind == "actor":
             if m.head.weight.shape[0] == 1:

@@ -47,8 +47,8 @@ def _workspace(nbytes, device):
 
 # ------------------------------------------------------------------ GEMM --
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=bf16, transposed_out=False, epilogue=EPI_NONE,
-         bias=None, aux=None, c2=None, beta=0.0, drop_p=0.0, seed=0, site=0, splits=1, block_n=0, M=None, N=None,
-         K=None):
+         bias=None, aux=None, c2=None, beta=0.0, drop_p=0.0, seed=0, site=0, seed_dev=None, splits=1, block_n=0,
+         M=None, N=None, K=None):
     """D[M,N] = A[M,K] @ B[N,K]^T  (bf16 in, fp32 accumulate).
 
     a: [M,K] (a_mn=False) or [K,M] (a_mn=True); b likewise with N.  Row pitch = stride(0).
@@ -85,7 +85,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=bf16, transposed_o
     _lib.run(L.lr2_gemm_bf16, ptr(a), a.stride(0), int(a_mn), ptr(b), b.stride(0), int(b_mn), ptr(out), ldc,
                           int(out.dtype == f32), int(transposed_out), M, N, K, epilogue, ptr(bias), ptr(aux),
                           aux.stride(-2) if aux is not None else 0, ptr(c2), float(beta), float(drop_p), int(seed),
-                          int(site), int(splits), ptr(ws), int(block_n), _lib.stream())
+                          int(site), ptr(seed_dev), int(splits), ptr(ws), int(block_n), _lib.stream())
     return out
 
 
@@ -105,7 +105,7 @@ def layernorm_fwd(x, gamma, beta, eps, mode=0, out=None, regroup=None, want_stat
 
 
 def layernorm_bwd(dy, x, gamma, stats, eps, mode=0, add=None, regroup=None, drop_p=0.0, seed=0, site=0,
-                  want_masked=False):
+                  want_masked=False, seed_dev=None):
     L = _L()
     _cuda(dy, bf16, "dy"); _cuda(x, bf16, "x"); _cuda(gamma, f32, "gamma"); _cuda(stats, f32, "stats")
     _cuda(add, bf16, "add")
@@ -119,7 +119,7 @@ def layernorm_bwd(dy, x, gamma, stats, eps, mode=0, add=None, regroup=None, drop
     part = _workspace(L.lr2_layernorm_bwd_partials_floats(D) * 4, x.device)
     _lib.run(L.lr2_layernorm_bwd, ptr(dy), ptr(x), ptr(gamma), ptr(stats), ptr(add), ptr(dx), ptr(dxm), ptr(dgamma),
                               ptr(dbeta), ptr(part), rows, D, float(eps), mode, g_in, g_out, g_off, float(drop_p),
-                              int(seed), int(site), _lib.stream())
+                              int(seed), int(site), ptr(seed_dev), _lib.stream())
     return dx, dxm, dgamma, dbeta
 
 
@@ -389,3 +389,11 @@ def gather_rows(src, index):
     out = torch.empty((bs, T_dst, R), dtype=bf16, device=src.device)
     _lib.run(L.lr2_gather_rows_bf16, ptr(src), ptr(index), ptr(out), bs, T_src, T_dst, R, _lib.stream())
     return out
+
+
+def bump_counter(counter, inc=1):
+    """counter: int64 CUDA tensor of one element (device-resident dropout seed offset)."""
+    L = _L()
+    _cuda(counter, i64, "counter")
+    _lib.run(L.lr2_bump_counter, ptr(counter), int(inc), _lib.stream())
+    return counter

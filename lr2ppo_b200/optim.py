@@ -41,6 +41,7 @@ class FusedAdamW(Optimizer):
         self._grad_src = {}    # id(p) -> tensor used as gradient instead of p.grad (e.g. bf16 wgrad buffers)
         self._fused = {}       # id(p) -> provider() of [(dY, X)] for the fused wgrad+AdamW kernel
         self._hyper = {}       # group index -> device hyper-parameter buffer
+        self.frozen_hyper = False  # True while the step is replayed from a CUDA graph
 
     # -- extras -----------------------------------------------------------
     def register_shadow(self, p, shadow):
@@ -111,6 +112,8 @@ class FusedAdamW(Optimizer):
             self._hyper[gi] = ent
         beta1, beta2 = group["betas"]
         lr = group["lr"]
+        if self.frozen_hyper and ent["host"] is not None:
+            return ent["dev"]          # inside a captured CUDA graph: the caller refreshes it with update_hyper()
         ent["t"] += 1
         step_size = lr
         if group["correct_bias"]:
@@ -120,6 +123,27 @@ class FusedAdamW(Optimizer):
             ent["dev"].copy_(torch.tensor(hv, dtype=torch.float32))
             ent["host"] = hv
         return ent["dev"]
+
+    def update_hyper(self):
+        """Recompute lr / bias-correction on the host and upload the 8 floats of every group asynchronously
+        (pinned staging).  Used with CUDA graphs, where `step()` itself must not copy from the host."""
+        for gi, group in enumerate(self.param_groups):
+            ent = self._hyper.get(gi)
+            if ent is None:
+                continue
+            beta1, beta2 = group["betas"]
+            lr = group["lr"]
+            ent["t"] += 1
+            step_size = lr
+            if group["correct_bias"]:
+                step_size = lr * math.sqrt(1.0 - beta2 ** ent["t"]) / (1.0 - beta1 ** ent["t"])
+            hv = (step_size, beta1, beta2, group["eps"], 1.0 - beta1, 1.0 - beta2, self.grad_scale, lr)
+            if ent["host"] != hv:
+                if "pin" not in ent:
+                    ent["pin"] = torch.empty(8, dtype=torch.float32).pin_memory()
+                ent["pin"].copy_(torch.tensor(hv, dtype=torch.float32))
+                ent["dev"].copy_(ent["pin"], non_blocking=True)
+                ent["host"] = hv
 
     @torch.no_grad()
     def step(self, closure=None):

@@ -98,7 +98,10 @@ def update_batch(args, model, optimizer, critic_optim, memory, grad_sync=None):
     """One stored batch of the update loop (finetune/ppo.py:518-587).  Returns a [10] tensor of the
     statistics the reference logs (means over the batch), still on the device."""
     state, next_state, old_action_prob, rewards, old_value, text, img, tgts = memory
-    model.zero_grad(set_to_none=False) if getattr(args, "keep_grad_buffers", True) else model.zero_grad()
+    if model.actor._engine.persistent_grads:
+        model.actor._engine.begin_step(); model.critic._engine.begin_step()   # .grad buffers are reused
+    else:
+        model.zero_grad()
     bs, tags_num = old_action_prob.shape[:2]
     action_logits = model.actor.scores(text, img)
     value = model.critic(text, img, tgts, state)
@@ -183,3 +186,46 @@ def evaluate(args, val_loader, step, split="test", num_tasks=None):
             args.logger.info("".join("\nNDCG@{}={:.4f}".format(k, ndcg_value[k]) for k in sorted(ndcg_value.keys())))
         return ndcg_value[100000000]
     return None
+
+
+class GraphedStage3Step:
+    """One stage-3 step (rollout + update of one batch) captured in a CUDA graph and replayed.
+
+    ~300 kernel launches + the torch glue of a step cost more host time than the small kernels take on the
+    GPU; replaying a graph removes that.  Requirements handled here: static input buffers, persistent `.grad`
+    buffers (no allocation / pointer-table rebuild inside the graph), AdamW hyper-parameters refreshed from
+    the host before each replay, dropout seeds read from a device counter bumped inside the graph.
+    Single-GPU only (no collectives inside the captured region)."""
+
+    def __init__(self, args, model, reward_model, optimizer, critic_optim, text, img, tgts, warmup=3):
+        self.args, self.model, self.reward = args, model, reward_model
+        self.opt, self.copt = optimizer, critic_optim
+        self.text, self.img, self.tgts = text.clone(), img.clone(), tgts.clone()
+        for e in (model.actor._engine, model.critic._engine):
+            e.persistent_grads = True
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.stats = self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.opt.frozen_hyper = self.copt.frozen_hyper = True
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.stats = self._eager()
+
+    def _eager(self):
+        mem = rollout(self.model, self.reward, self.text, self.img, self.tgts)
+        self.model.train()
+        stats = update_batch(self.args, self.model, self.opt, self.copt, mem)
+        self.model.eval()
+        return stats
+
+    def __call__(self, text, img, tgts):
+        self.text.copy_(text, non_blocking=True)
+        self.img.copy_(img, non_blocking=True)
+        self.tgts.copy_(tgts, non_blocking=True)
+        self.opt.update_hyper(); self.copt.update_hyper()
+        self.graph.replay()
+        return self.stats
