@@ -227,14 +227,18 @@ def main():
         sch.step(); csch.step()
         return stats
 
-    # single GPU: the whole step (rollout + update, ~300 launches) is captured once and replayed as a CUDA graph
-    use_graph = world == 1 and not args.no_graph
+    # the whole step (rollout + update, ~300 launches, plus the NCCL collectives when N > 1) is captured once and
+    # replayed as a CUDA graph; --no-graph runs it eagerly
+    use_graph = not args.no_graph
+    if world > 1:
+        for e in (model.actor._engine, model.critic._engine):
+            e.persistent_grads = True
     launches_per_step = None
     if use_graph:
         for i in range(2):
             eager_step(resident[i])
         c0 = _lib.launch_count()
-        gstep = ppo.GraphedStage3Step(hp, model, reward, opt, copt, *resident[0], warmup=2)
+        gstep = ppo.GraphedStage3Step(hp, model, reward, opt, copt, *resident[0], warmup=2, grad_sync=sync)
         launches_per_step = (_lib.launch_count() - c0) // 3      # 2 warm-up passes + 1 captured pass
 
         def step(batch):
@@ -290,13 +294,16 @@ def main():
 
     # ---- (3) per-kernel CUDA-event pass for the roofline of the dominant kernel ----------------------------
     roofline, breakdown = None, None
-    if rank == 0 and args.profile_steps > 0:
+    if args.profile_steps > 0:
+        # every rank runs these steps (they contain collectives); only rank 0 brackets its calls with events
         torch.cuda.synchronize()
-        _lib.PROFILE = []
+        if rank == 0:
+            _lib.PROFILE = []
         for i in range(args.profile_steps):
             eager_step(resident[i % len(resident)])
         torch.cuda.synchronize()
         prof, _lib.PROFILE = _lib.PROFILE, None
+    if rank == 0 and args.profile_steps > 0:
         groups = summarize_profile(torch, prof, args.profile_steps)
         peaks = {}
         try:

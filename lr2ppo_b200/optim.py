@@ -96,13 +96,25 @@ class FusedAdamW(Optimizer):
                      sh.data_ptr() if sh is not None else 0, 0]
             meta += [p.numel(), _f2i(group["weight_decay"]), int(g.dtype == torch.bfloat16), 0]
             gptrs.append(g.data_ptr())
-            for off in range(0, p.numel(), chunk):
-                chunks += [t, off]
-        tab = dict(params=ps, ids=[id(p) for p in ps], gptrs=gptrs, n_chunks=len(chunks) // 2,
+            offs = torch.arange(0, p.numel(), chunk, dtype=torch.int64)
+            chunks.append(torch.stack([torch.full_like(offs, t), offs], dim=1))
+        chunk_t = torch.cat(chunks, dim=0).contiguous()
+        tab = dict(params=ps, ids=[id(p) for p in ps], gptrs=gptrs, n_chunks=chunk_t.shape[0],
                    ptrs=torch.tensor(ptrs, dtype=torch.int64, device=dev),
                    meta=torch.tensor(meta, dtype=torch.int64, device=dev),
-                   chunks=torch.tensor(chunks, dtype=torch.int64, device=dev))
+                   chunks=chunk_t.to(dev))
         return tab
+
+    def _refresh_ptrs(self, tab):
+        """Only the gradient addresses changed (autograd / zero_grad re-allocated them): patch the pointer table."""
+        ptrs = tab["ptrs"].cpu()
+        gptrs = []
+        for t, p in enumerate(tab["params"]):
+            g = self._grad_of(p)
+            ptrs[6 * t + 1] = g.data_ptr()
+            gptrs.append(g.data_ptr())
+        tab["ptrs"].copy_(ptrs)
+        tab["gptrs"] = gptrs
 
     def _hyper_buf(self, gi, group, dev):
         """Device-side hyper-parameters of group gi: {step_size, b1, b2, eps, 1-b1, 1-b2, grad_scale, lr}."""
@@ -159,9 +171,10 @@ class FusedAdamW(Optimizer):
                 continue
             hyper = self._hyper_buf(gi, group, (live or fused)[0].device)
             tab = self._tables.get(gi)
-            if tab is not None and ([id(p) for p in live] != tab["ids"] or
-                                    [self._grad_of(p).data_ptr() for p in live] != tab["gptrs"]):
+            if tab is not None and [id(p) for p in live] != tab["ids"]:
                 tab = None
+            if tab is not None and [self._grad_of(p).data_ptr() for p in live] != tab["gptrs"]:
+                self._refresh_ptrs(tab)
             if tab is None and live:
                 tab = self._build(gi, group, live)
                 self._tables[gi] = tab

@@ -195,10 +195,10 @@ class GraphedStage3Step:
     GPU; replaying a graph removes that.  Requirements handled here: static input buffers, persistent `.grad`
     buffers (no allocation / pointer-table rebuild inside the graph), AdamW hyper-parameters refreshed from
     the host before each replay, dropout seeds read from a device counter bumped inside the graph.
-    Single-GPU only (no collectives inside the captured region)."""
+    With `grad_sync` (N > 1) the NCCL all-gather / all-reduce calls are captured in the same graph."""
 
-    def __init__(self, args, model, reward_model, optimizer, critic_optim, text, img, tgts, warmup=3):
-        self.args, self.model, self.reward = args, model, reward_model
+    def __init__(self, args, model, reward_model, optimizer, critic_optim, text, img, tgts, warmup=3, grad_sync=None):
+        self.args, self.model, self.reward, self.grad_sync = args, model, reward_model, grad_sync
         self.opt, self.copt = optimizer, critic_optim
         self.text, self.img, self.tgts = text.clone(), img.clone(), tgts.clone()
         for e in (model.actor._engine, model.critic._engine):
@@ -218,7 +218,7 @@ class GraphedStage3Step:
     def _eager(self):
         mem = rollout(self.model, self.reward, self.text, self.img, self.tgts)
         self.model.train()
-        stats = update_batch(self.args, self.model, self.opt, self.copt, mem)
+        stats = update_batch(self.args, self.model, self.opt, self.copt, mem, self.grad_sync)
         self.model.eval()
         return stats
 

@@ -117,3 +117,44 @@ def test_fused_fc1_update_equals_unfused(sds):
     assert (wf - wu).abs().max().item() < 1e-6
     assert torch.equal(sf, wf.to(torch.bfloat16).float())                # bf16 shadow refreshed by the fused kernel
     assert _rel(bf_, bu) < 1e-5
+
+
+def test_cuda_graph_step_equals_eager(sds):
+    """GraphedStage3Step (CUDA-graph replay, persistent grads, device seeds) == eager rollout + update_batch."""
+    from lr2ppo_b200 import ppo
+    g = torch.Generator().manual_seed(8)
+    bs = 4
+    batches = [(torch.randn(bs, 2, 196, 768, generator=g).cuda(),
+                torch.randn(bs, 1, 16, 768, generator=g).repeat(1, 2, 1, 1).cuda(),
+                torch.randint(0, 3, (bs, 2), generator=g).cuda()) for _ in range(2)]
+
+    def build():
+        model, reward = _build_gpu(sds)
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0                                   # train == eval, so both paths are deterministic
+        hp = _hp(False)
+        hp.learning_rate, hp.critic_learning_rate = 1e-7, 2e-7   # a few raw-Adam steps must stay in the linear regime
+        opt, copt, _, _ = ppo.build_optimizer(hp, model)
+        return model, reward, hp, opt, copt
+
+    # eager: 2 steps on batch 0 (the graph class runs 2 eager warm-ups; the capture pass itself executes nothing)
+    model, reward, hp, opt, copt = build()
+    seq = [batches[0]] * 2 + [batches[1], batches[0]]
+    for b in seq:
+        mem = ppo.rollout(model, reward, *b)
+        model.train(); st_e = ppo.update_batch(hp, model, opt, copt, mem); model.eval()
+    we = golden_util.grad_sample(model.actor.out_layer.fc1.weight.detach(), 1 << 16).cpu()
+    ce = model.critic.head.weight.detach().cpu().clone()
+    st_e = st_e.cpu()
+    del model, reward, opt, copt
+    torch.cuda.empty_cache()
+
+    model, reward, hp, opt, copt = build()
+    gstep = ppo.GraphedStage3Step(hp, model, reward, opt, copt, *batches[0], warmup=2)
+    gstep(*batches[1])
+    st_g = gstep(*batches[0]).cpu()
+    wg = golden_util.grad_sample(model.actor.out_layer.fc1.weight.detach(), 1 << 16).cpu()
+    cg = model.critic.head.weight.detach().cpu()
+    assert torch.allclose(st_g, st_e, rtol=1e-4, atol=1e-6), (st_g, st_e)
+    assert torch.allclose(wg, we, rtol=0, atol=1e-7) and torch.allclose(cg, ce, rtol=0, atol=1e-7)
