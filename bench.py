@@ -376,7 +376,12 @@ def main():
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        # NCCL work captured in the CUDA graph makes communicator teardown hang on some stacks: synchronise,
+        # flush and leave without running the destructors.
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush(); sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
