@@ -1,0 +1,80 @@
+"""Stage-1 (pointwise) and stage-2 (pairwise reward model) train / eval steps with the reference's signatures.
+
+  stage 1: finetune/pointwise.py:300-313 (train_model), :316-412 (evaluate, NDCG)
+  stage 2: finetune/reward_pair_dataloader.py:347-365 (train_model), :367-412 (evaluate, pair accuracy)
+"""
+import torch
+import torch.distributed as dist
+
+from . import losses
+from .ndcg import AverageNDCGMeter
+
+
+def pointwise_train_model(args, model, optimizer, scheduler, text_emb_batch, img_emb_batch, tgts_batch):
+    """loss = SmoothL1(beta 0.3)(logits, tgts); backward; AdamW; scheduler (per batch)."""
+    model.zero_grad()
+    loss, _ = model(text_emb_batch, img_emb_batch, tgts_batch)
+    loss.backward()
+    optimizer.step()
+    scheduler.step()
+    return loss
+
+
+def reward_train_model(args, model, optimizer, scheduler, text_emb_batch, img_emb_batch, tgts_batch,
+                       chosen_index_batch, reject_index_batch, margin=1.0):
+    """Two forwards (chosen / reject 4-slot orderings) -> hinge relu(m - (c - r)).mean() -> one backward.
+    Returns (loss, acc) like the reference."""
+    model.zero_grad()
+    chosen = model(text_emb_batch, img_emb_batch, tgts_batch, chosen_index_batch)
+    reject = model(text_emb_batch, img_emb_batch, tgts_batch, reject_index_batch)
+    loss, acc = losses.pair_hinge_loss(chosen, reject, margin)
+    loss.backward()
+    optimizer.step()
+    scheduler.step()
+    return loss, acc
+
+
+@torch.no_grad()
+def reward_evaluate(args, model, dataloader, num_tasks=None):
+    """Pair accuracy over the loader; ONE all_reduce for the whole pass (the reference issues two per batch)."""
+    model.eval()
+    counts = torch.zeros(2, device=args.device)
+    for text_emb, img_emb, tgts, chosen_index, reject_index in dataloader:
+        text = text_emb.to(args.device)
+        img = img_emb.unsqueeze(1).repeat(1, text.shape[1], 1, 1).to(args.device)
+        t = tgts.to(args.device)
+        c = model(text, img, t, chosen_index.to(args.device))
+        r = model(text, img, t, reject_index.to(args.device))
+        counts[0] += (c > r).float().sum()
+        counts[1] += c.numel()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(counts)
+    return counts[0] / counts[1].clamp_min(1)
+
+
+@torch.no_grad()
+def pointwise_evaluate(args, model, dataloader, num_tasks=None):
+    """NDCG over clips of variable length (finetune/pointwise.py:316-412, 'reg' mode): scores every clip, then
+    one segmented NDCG launch and one all_gather."""
+    model.eval()
+    scores_l, gold_l = [], []
+    for text_emb, img_emb, tgts in dataloader:
+        text = text_emb.to(args.device)
+        img = img_emb.unsqueeze(1).repeat(1, text.shape[1], 1, 1).to(args.device)
+        scores_l.append(model(text, img, None).view(-1))
+        gold_l.append(tgts.to(args.device).view(-1))
+    meter = AverageNDCGMeter()
+    n, nmax = len(scores_l), max(s.numel() for s in scores_l)
+    scores = torch.full((n, nmax), float("-inf"), device=args.device)
+    labels = torch.zeros((n, nmax), dtype=torch.int64, device=args.device)
+    lens = torch.tensor([s.numel() for s in scores_l], dtype=torch.int32, device=args.device)
+    for i, (s, g) in enumerate(zip(scores_l, gold_l)):
+        scores[i, :s.numel()] = s
+        labels[i, :g.numel()] = g
+    vals = meter.batch_ndcg(scores, labels, lens=lens)
+    if num_tasks and num_tasks > 1:
+        gathered = [torch.zeros_like(vals) for _ in range(num_tasks)]
+        dist.all_gather(gathered, vals)
+        vals = torch.cat(gathered, dim=0)
+    meter.add_batch(vals)
+    return meter.value()

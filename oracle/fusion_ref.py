@@ -79,3 +79,27 @@ def critic_forward(sd, text, img, index):
     x = xit(sd, "xitt.", x, x)
     logits = F.linear(x, sd["head.weight"], sd["head.bias"])
     return logits[:, -1].reshape(bs)
+
+
+# ---- "trad" (MSLR / MQ2008) variants: finetune/ppo_trad.py:142-283 -------------------------------------------
+def trad_body(sd, text):
+    """text [bs, T, 768] -> [bs, T, 768]: xit((x, x)) on single-token items, cat with x, out_layer."""
+    bs, T, E = text.shape
+    x = text.reshape(bs * T, 1, E)
+    f = xit(sd, "xit.", x, x)
+    f = torch.cat([f, x], dim=1)
+    return mlp(sd, "out_layer.", f.reshape(bs * T, -1)).view(bs, T, E)
+
+
+def trad_actor_forward(sd, text):
+    return F.linear(trad_body(sd, text), sd["head.weight"], sd["head.bias"]).view(-1)
+
+
+def trad_critic_forward(sd, text, index):
+    bs = text.shape[0]
+    text = text[torch.arange(bs).view(bs, 1), index]
+    x = trad_body(sd, text)
+    T = x.shape[1]
+    x = x + sd["pos_emb.weight"][:T].unsqueeze(0)
+    x = xit(sd, "xitt.", x, x)
+    return F.linear(x, sd["head.weight"], sd["head.bias"])[:, -1].reshape(bs)

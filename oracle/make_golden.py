@@ -245,12 +245,85 @@ def gen_fusion():
     print("fusion.pt written")
 
 
+def gen_trad():
+    """Reference trad Actor / Critic / Reward (finetune/ppo_trad.py:142-283) forward + backward."""
+    pt = ref_loader.load("ppo_trad")
+    import argparse
+    args = argparse.Namespace(mode="reg", labels_num=5)
+    out = {}
+    for kind in ("actor", "critic", "reward"):
+        cls = {"actor": pt.Actor, "critic": pt.Critic, "reward": pt.Reward}[kind]
+        model = cls(args, args)
+        model.load_state_dict(golden_util.make_trad_state_dict(kind), strict=True)
+        model.eval()
+        text, tgts, index = golden_util.trad_inputs(kind)
+        if kind == "actor":
+            _, logits = model(text, None, tgts)
+        else:
+            logits = model(text, None, tgts, index)
+        gw = golden_util.out_grad(kind, logits.numel())
+        (logits * gw).sum().backward()
+        rec = {"logits": logits.detach().clone()}
+        for name, p in model.named_parameters():
+            rec["gnorm/" + name] = p.grad.double().norm().float()
+            rec["grad/" + name] = (p.grad if p.grad.numel() <= 4096 else golden_util.grad_sample(p.grad)).clone()
+        out[kind] = rec
+        print("trad", kind, logits[:3].tolist())
+    torch.save(out, os.path.join(GOLD, "trad.pt"))
+
+
+def gen_stage12():
+    """ONE reference training step of stage 1 (finetune/pointwise.py:300-313) and stage 2
+    (finetune/reward_pair_dataloader.py:347-365) with the reference AdamW + constant schedule."""
+    import argparse
+    opt_mod = ref_loader.load("tencentpretrain.utils.optimizers")
+    out = {}
+    for stage in (1, 2):
+        mod = ref_loader.load("pointwise" if stage == 1 else "reward_pair_dataloader")
+        cfg = golden_util.FUSION_CFG
+        args = argparse.Namespace(mode="reg", labels_num=3, seq_length=cfg["seq_length"], max_imgs=cfg["max_imgs"],
+                                  visual_feat_dim=cfg["feat"])
+        model = mod.Classifier(args, args)
+        kind = "actor" if stage == 1 else "reward"
+        model.load_state_dict(golden_util.make_state_dict(kind), strict=True)
+        model.train()
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0                      # parity is defined without dropout noise
+        no_decay = ["bias", "gamma", "beta"]
+        named = list(model.named_parameters())
+        groups = [{"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
+                  {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
+        opt = opt_mod.AdamW(groups, lr=golden_util.STEP_LR, correct_bias=False)
+        sch = opt_mod.get_constant_schedule(opt)
+        text, img, tgts, chosen, reject = golden_util.stage_inputs(stage)
+        before = {n: p.detach().clone() for n, p in named}
+        if stage == 1:
+            loss = mod.train_model(args, model, opt, sch, text, img, tgts)
+            rec = {"loss": loss.detach().clone()}
+        else:
+            loss, acc = mod.train_model(args, model, opt, sch, text, img, tgts, chosen, reject)
+            rec = {"loss": loss.detach().clone(), "acc": acc.detach().clone()}
+        for n, p in named:
+            rec["m/" + n] = golden_util.grad_sample(opt.state[p]["exp_avg"], 4096).clone()
+            rec["mnorm/" + n] = opt.state[p]["exp_avg"].double().norm().float()
+            rec["delta/" + n] = golden_util.grad_sample(p.detach() - before[n], 4096).clone()
+        out[f"stage{stage}"] = rec
+        print("stage", stage, {k: v.tolist() for k, v in rec.items() if k in ("loss", "acc")})
+        del model, opt, before
+    torch.save(out, os.path.join(GOLD, "stage12.pt"))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ["rows", "ppo_update", "fusion"]
+    which = sys.argv[1:] or ["rows", "ppo_update", "fusion", "trad", "stage12"]
     if "rows" in which:
         gen_rows()
     if "ppo_update" in which:
         gen_ppo_update()
     if "fusion" in which:
         gen_fusion()
+    if "trad" in which:
+        gen_trad()
+    if "stage12" in which:
+        gen_stage12()

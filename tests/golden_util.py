@@ -99,3 +99,60 @@ def make_state_dict(kind, cfg=FUSION_CFG):
         else:
             sd[name] = r * 0.02
     return sd
+
+
+# ---- "trad" models (finetune/ppo_trad.py:142-283) --------------------------------------------------------
+TRAD_SEEDS = dict(actor=411, critic=422, reward=433)
+
+
+def trad_param_specs(kind, E=768):
+    specs = []
+    if kind != "actor":
+        specs += [("pos_emb.weight", (4, E))]
+    specs += _xit_specs("xit", E)
+    if kind != "actor":
+        specs += _xit_specs("xitt", E)
+    specs += _mlp_specs("out_layer", 2 * E, 4 * E, E)
+    specs += [("head.weight", (1, E)), ("head.bias", (1,))]
+    return specs
+
+
+def make_trad_state_dict(kind):
+    g = torch.Generator().manual_seed(TRAD_SEEDS[kind])
+    sd = {}
+    for name, shape in trad_param_specs(kind):
+        r = torch.randn(shape, generator=g)
+        sd[name] = r * 0.02 if len(shape) >= 2 else (1.0 + 0.1 * r if _is_ln_scale(name) else r * 0.02)
+    return sd
+
+
+def trad_inputs(kind, bs=24, docs=2):
+    g = torch.Generator().manual_seed(7000 + TRAD_SEEDS[kind])
+    text = torch.randn(bs, docs, 768, generator=g)
+    tgts = torch.randint(0, 5, (bs, docs), generator=g)
+    if kind == "actor":
+        index = None
+    elif kind == "critic":
+        index = torch.stack([torch.randperm(docs, generator=g) for _ in range(bs)])
+    else:
+        perm = torch.stack([torch.randperm(docs, generator=g) for _ in range(bs)])
+        index = torch.cat([torch.arange(docs).unsqueeze(0).repeat(bs, 1), perm], dim=1)
+    return text, tgts, index
+
+
+# ---- stage 1 / stage 2 single training step on the full-size fusion models --------------------------------
+STEP_LR = 2e-6
+
+
+def stage_inputs(stage):
+    g = torch.Generator().manual_seed(8100 + stage)
+    bs, T = (2, 3) if stage == 1 else (3, 2)
+    text = torch.randn(bs, T, 196, 768, generator=g)
+    img = torch.randn(bs, 1, 16, 768, generator=g).repeat(1, T, 1, 1)
+    tgts = torch.randint(0, 3, (bs, T), generator=g)
+    chosen = reject = None
+    if stage == 2:
+        pick = torch.randint(0, 2, (bs,), generator=g)
+        chosen = torch.tensor([[0, 1, 0, 1], [1, 0, 0, 1]])[pick]       # reward_pair_dataloader.py:128-141
+        reject = torch.tensor([[0, 1, 1, 0], [1, 0, 1, 0]])[pick]
+    return text, img, tgts, chosen, reject

@@ -196,3 +196,18 @@ def test_fusion_restatement_vs_reference_modules(kind):
             logits = fusion_ref.critic_forward(sd, text, img, index)
     ref = gold[kind]["logits"]
     assert (logits - ref).abs().max() <= 1e-5 * ref.abs().max().clamp_min(1.0), (logits, ref)
+
+
+@pytest.mark.parametrize("kind", ["actor", "critic", "reward"])
+def test_trad_restatement_vs_reference_modules(kind):
+    """oracle/fusion_ref.trad_* == reference ppo_trad Actor/Critic/Reward (finetune/ppo_trad.py:142-283)."""
+    from oracle import fusion_ref
+    from tests import golden_util
+    gold = torch.load(os.path.join(GOLD, "trad.pt"))
+    sd = golden_util.make_trad_state_dict(kind)
+    text, tgts, index = golden_util.trad_inputs(kind)
+    with torch.no_grad():
+        logits = fusion_ref.trad_actor_forward(sd, text) if kind == "actor" else \
+            fusion_ref.trad_critic_forward(sd, text, index)
+    ref = gold[kind]["logits"]
+    assert (logits - ref).abs().max() <= 1e-5 * ref.abs().max().clamp_min(1.0)
