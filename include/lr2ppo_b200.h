@@ -114,6 +114,30 @@ int lr2_xattn_bwd(const void* q, long long ldq, const void* k, const void* v, lo
                   long long ldo, void* dq, long long lddq, void* dk, void* dv, long long lddkv, int items, int Sq,
                   int Skv, int H, int dh, float pre_scale, float post_scale, void* stream);
 
+/* ------------------------------------- TencentPretrain tower kernels --
+ * Multi-headed self-attention core, flash-style (scores never leave the SM), S <= 256, dh == 64:
+ *   P = softmax(Q K^T * scale + key_bias[b, j]);  O = dropout(P) V;  lse[b,h,i] saved for backward.
+ * q/k/v: [B*S, ...] rows with pitch ld (views into a merged QKV buffer are fine), head h at column h*dh.
+ * ref: tencentpretrain/layers/multi_headed_attn.py:55-76, encoders/transformer_encoder.py:62-68 (mask). */
+int lr2_mha_fwd(const void* q, const void* k, const void* v, long long ld, const float* key_bias, void* o,
+                long long ldo, float* lse, int B, int S, int H, int dh, float scale, float drop_p,
+                unsigned long long seed, const void* seed_dev, void* stream);
+int lr2_mha_bwd(const void* q, const void* k, const void* v, long long ld, const float* key_bias, const void* o,
+                const void* d_o, long long ldo, const float* lse, void* dq, void* dk, void* dv, long long ldd, int B,
+                int S, int H, int dh, float scale, float drop_p, unsigned long long seed, const void* seed_dev,
+                void* stream);
+/* out[r,:] = word[src[r],:] + pos[r % S,:] (+ seg_table[seg[r],:])   ref: embeddings/{word,pos,seg}_embedding.py */
+int lr2_embed_sum(const long long* src, const long long* seg, const float* word, const float* pos,
+                  const float* seg_table, void* out_bf16, long long rows, int S, int D, void* stream);
+/* table[idx[r],:] += d[r,:] (fp32 atomics): gradient of an embedding lookup */
+int lr2_embed_scatter_add(const long long* idx, const void* d_bf16, float* table, long long rows, int D, void* stream);
+/* im2col for Conv2d(k = s = ps, no bias): [B,C,H,W] f32 -> [B*(H/ps)*(W/ps), C*ps*ps] bf16
+ * ref: embeddings/patch_embedding.py:18,27 */
+int lr2_patchify(const float* img, void* out_bf16, int B, int C, int Hh, int Ww, int ps, void* stream);
+/* out = x * keep(seed, site, element index) / (1-p): elementwise dropout / its backward (n % 8 == 0) */
+int lr2_dropout_bf16(const void* x, void* out, long long n, float p, unsigned long long seed, unsigned int site,
+                     const void* seed_dev, void* stream);
+
 /* ------------------------------------------------------ glue kernels --- */
 /* counter[0] += inc (u64, device): the dropout seed offset read through `seed_dev` above; bumping it inside a
  * captured CUDA graph gives every replay fresh masks (the reference draws new nn.Dropout masks per call). */

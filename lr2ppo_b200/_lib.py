@@ -35,6 +35,13 @@ SIGNATURES = {
     "lr2_xattn_fwd": (i32, [vp, i64, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, f32, f32, vp]),
     "lr2_xattn_bwd": (i32, [vp, i64, vp, vp, i64, vp, i64, vp, i64, vp, vp, i64, i32, i32, i32, i32, i32, f32, f32,
                             vp]),
+    "lr2_mha_fwd": (i32, [vp, vp, vp, i64, vp, vp, i64, vp, i32, i32, i32, i32, f32, f32, u64, vp, vp]),
+    "lr2_mha_bwd": (i32, [vp, vp, vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, i64, i32, i32, i32, i32, f32, f32, u64, vp,
+                          vp]),
+    "lr2_embed_sum": (i32, [vp, vp, vp, vp, vp, vp, i64, i32, i32, vp]),
+    "lr2_embed_scatter_add": (i32, [vp, vp, vp, i64, i32, vp]),
+    "lr2_patchify": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
+    "lr2_dropout_bf16": (i32, [vp, vp, i64, f32, u64, u32, vp, vp]),
     "lr2_cast_gather_bf16": (i32, [vp, vp, vp, i32, i32, i32, i64, vp]),
     "lr2_gather_rows_bf16": (i32, [vp, vp, vp, i32, i32, i32, i64, vp]),
     "lr2_rows_copy_bf16": (i32, [vp, i64, i64, vp, i64, i64, i64, i64, i32, i32, vp]),

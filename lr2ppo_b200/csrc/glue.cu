@@ -340,3 +340,112 @@ extern "C" int lr2_bump_counter(void* counter, unsigned long long inc, void* str
   LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
+
+// ---- TencentPretrain embedding kernels -------------------------------------------------------------------------
+namespace lr2 {
+// out[b,s,:] = word[src[b,s],:] + pos[s,:] + segE[seg[b,s],:]   (ref: embeddings/{word,pos,seg}_embedding.py,
+// embedding.py:23-30), fp32 tables -> bf16 row
+__global__ void embed_sum_kernel(const long long* __restrict__ src, const long long* __restrict__ seg,
+                                 const float* __restrict__ word, const float* __restrict__ pos,
+                                 const float* __restrict__ segE, bf16* __restrict__ out, long long rows, int S, int D) {
+  const int vec = D / 8;
+  const long long total = rows * vec;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / vec;
+    const int c = (int)(i % vec) * 8;
+    const float* w = word + src[r] * D + c;
+    const float* p = pos + (r % S) * D + c;
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = w[k] + p[k];
+    if (segE != nullptr) {
+      const float* g = segE + seg[r] * D + c;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] += g[k];
+    }
+    st8f(out + r * D + c, v);
+  }
+}
+// table[idx[r], :] += d[r, :]  (fp32 atomics; embedding-gradient scatter)
+__global__ void embed_scatter_kernel(const long long* __restrict__ idx, const bf16* __restrict__ d,
+                                     float* __restrict__ table, long long rows, int D) {
+  const long long total = rows * D;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / D;
+    const int c = (int)(i % D);
+    atomicAdd(table + idx[r] * D + c, __bfloat162float(d[i]));
+  }
+}
+// patches[b*P + py*pw + px, (c, ky, kx)] = img[b, c, py*ps+ky, px*ps+kx]  (Conv2d k=s=ps as a GEMM operand,
+// ref: embeddings/patch_embedding.py:18,27)
+__global__ void patchify_kernel(const float* __restrict__ img, bf16* __restrict__ out, int B, int C, int Hh, int Ww,
+                                int ps) {
+  const int ph = Hh / ps, pw = Ww / ps;
+  const long long K = (long long)C * ps * ps;
+  const long long total = (long long)B * ph * pw * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / K;
+    const int kk = (int)(i % K);
+    const int c = kk / (ps * ps), ky = (kk / ps) % ps, kx = kk % ps;
+    const int b = (int)(row / (ph * pw)), p = (int)(row % (ph * pw));
+    const int y = (p / pw) * ps + ky, x = (p % pw) * ps + kx;
+    out[i] = __float2bfloat16(img[(((long long)b * C + c) * Hh + y) * Ww + x]);
+  }
+}
+// out = x * keep(seed, site, idx) / (1 - p)   (elementwise dropout and its backward; same Philox stream as the
+// GEMM epilogues so masks can be regenerated anywhere)
+__global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, long long n, float p,
+                               uint32_t thresh, unsigned long long seed_in, unsigned int site,
+                               const unsigned long long* __restrict__ seed_dev) {
+  const unsigned long long seed = seed_in + (seed_dev ? *seed_dev : 0ull);
+  const float sc = 1.f / (1.f - p);
+  const long long n8 = n / 8;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    ld8f(x + i * 8, v);
+    const uint32_t keep = dropout_keep4(seed, site, (unsigned long long)i * 2, thresh) |
+                          (dropout_keep4(seed, site, (unsigned long long)i * 2 + 1, thresh) << 4);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = ((keep >> k) & 1u) ? v[k] * sc : 0.f;
+    st8f(out + i * 8, v);
+  }
+}
+}  // namespace lr2
+
+extern "C" int lr2_embed_sum(const long long* src, const long long* seg, const float* word, const float* pos,
+                             const float* seg_table, void* out_bf16, long long rows, int S, int D, void* stream) {
+  if (rows <= 0 || S <= 0 || D <= 0 || D % 8) return LR2_ERR_BAD_SHAPE;
+  lr2::embed_sum_kernel<<<lr2::grid_for(rows * (D / 8), 256), 256, 0, S_(stream)>>>(
+      src, seg, word, pos, seg_table, reinterpret_cast<lr2::bf16*>(out_bf16), rows, S, D);
+  LR2_LAUNCHED(1);
+  LR2_RETURN_LAUNCH();
+}
+extern "C" int lr2_embed_scatter_add(const long long* idx, const void* d_bf16, float* table, long long rows, int D,
+                                     void* stream) {
+  if (rows <= 0 || D <= 0) return LR2_ERR_BAD_SHAPE;
+  lr2::embed_scatter_kernel<<<lr2::grid_for(rows * D, 256), 256, 0, S_(stream)>>>(
+      idx, reinterpret_cast<const lr2::bf16*>(d_bf16), table, rows, D);
+  LR2_LAUNCHED(1);
+  LR2_RETURN_LAUNCH();
+}
+extern "C" int lr2_patchify(const float* img, void* out_bf16, int B, int C, int Hh, int Ww, int ps, void* stream) {
+  if (B <= 0 || C <= 0 || ps <= 0 || Hh % ps || Ww % ps) return LR2_ERR_BAD_SHAPE;
+  const long long total = (long long)B * C * Hh * Ww;
+  lr2::patchify_kernel<<<lr2::grid_for(total, 256), 256, 0, S_(stream)>>>(img, reinterpret_cast<lr2::bf16*>(out_bf16),
+                                                                         B, C, Hh, Ww, ps);
+  LR2_LAUNCHED(1);
+  LR2_RETURN_LAUNCH();
+}
+extern "C" int lr2_dropout_bf16(const void* x, void* out, long long n, float p, unsigned long long seed,
+                                unsigned int site, const void* seed_dev, void* stream) {
+  if (n <= 0 || n % 8 || p < 0.f || p >= 1.f) return LR2_ERR_BAD_SHAPE;
+  lr2::dropout_kernel<<<lr2::grid_for(n / 8, 256), 256, 0, S_(stream)>>>(
+      reinterpret_cast<const lr2::bf16*>(x), reinterpret_cast<lr2::bf16*>(out), n, p, lr2::dropout_thresh(p), seed, site,
+      reinterpret_cast<const unsigned long long*>(seed_dev));
+  LR2_LAUNCHED(1);
+  LR2_RETURN_LAUNCH();
+}

@@ -397,3 +397,69 @@ def bump_counter(counter, inc=1):
     _cuda(counter, i64, "counter")
     _lib.run(L.lr2_bump_counter, ptr(counter), int(inc), _lib.stream())
     return counter
+
+
+# ------------------------------------------------- TencentPretrain tower kernels --
+def mha_fwd(qkv, B, S, H, key_bias=None, scale=None, drop_p=0.0, seed=0, seed_dev=None, want_lse=True):
+    """qkv: bf16 [B*S, 3*E] merged projection output (q | k | v).  Returns (o [B*S, E], lse [B,H,S])."""
+    L = _L()
+    _cuda(qkv, bf16, "qkv"); _cuda(key_bias, f32, "key_bias")
+    E = qkv.shape[1] // 3
+    dh = E // H
+    o = torch.empty((B * S, E), dtype=bf16, device=qkv.device)
+    lse = torch.empty((B, H, S), dtype=f32, device=qkv.device) if want_lse else None
+    sc = 1.0 / math.sqrt(dh) if scale is None else scale
+    _lib.run(L.lr2_mha_fwd, ptr(qkv), qkv.data_ptr() + 2 * E, qkv.data_ptr() + 4 * E, qkv.stride(0), ptr(key_bias),
+             ptr(o), E, ptr(lse), B, S, H, dh, float(sc), float(drop_p), int(seed), ptr(seed_dev), _lib.stream())
+    return o, lse
+
+
+def mha_bwd(qkv, o, d_o, lse, B, S, H, key_bias=None, scale=None, drop_p=0.0, seed=0, seed_dev=None):
+    """Returns dqkv bf16 [B*S, 3*E] (dq | dk | dv)."""
+    L = _L()
+    _cuda(qkv, bf16); _cuda(o, bf16); _cuda(d_o, bf16); _cuda(lse, f32)
+    E = qkv.shape[1] // 3
+    dh = E // H
+    d = torch.empty_like(qkv)
+    sc = 1.0 / math.sqrt(dh) if scale is None else scale
+    _lib.run(L.lr2_mha_bwd, ptr(qkv), qkv.data_ptr() + 2 * E, qkv.data_ptr() + 4 * E, qkv.stride(0), ptr(key_bias),
+             ptr(o), ptr(d_o), E, ptr(lse), ptr(d), d.data_ptr() + 2 * E, d.data_ptr() + 4 * E, d.stride(0), B, S, H, dh,
+             float(sc), float(drop_p), int(seed), ptr(seed_dev), _lib.stream())
+    return d
+
+
+def embed_sum(src, seg, word, pos, seg_table=None):
+    L = _L()
+    _cuda(src, i64); _cuda(word, f32); _cuda(pos, f32); _cuda(seg_table, f32)
+    B, S = src.shape
+    D = word.shape[1]
+    out = torch.empty((B * S, D), dtype=bf16, device=src.device)
+    segp = seg.to(i64).contiguous() if seg_table is not None else None
+    _lib.run(L.lr2_embed_sum, ptr(src.contiguous()), ptr(segp), ptr(word), ptr(pos), ptr(seg_table), ptr(out), B * S, S,
+             D, _lib.stream())
+    return out
+
+
+def embed_scatter_add(idx, d, table):
+    L = _L()
+    _cuda(idx, i64); _cuda(d, bf16); _cuda(table, f32)
+    _lib.run(L.lr2_embed_scatter_add, ptr(idx.contiguous()), ptr(d), ptr(table), d.shape[0], d.shape[1], _lib.stream())
+    return table
+
+
+def patchify(img, ps):
+    L = _L()
+    _cuda(img, f32, "img")
+    B, C, Hh, Ww = img.shape
+    out = torch.empty((B * (Hh // ps) * (Ww // ps), C * ps * ps), dtype=bf16, device=img.device)
+    _lib.run(L.lr2_patchify, ptr(img), ptr(out), B, C, Hh, Ww, ps, _lib.stream())
+    return out
+
+
+def dropout(x, p, seed, site, seed_dev=None):
+    L = _L()
+    _cuda(x, bf16)
+    out = torch.empty_like(x)
+    _lib.run(L.lr2_dropout_bf16, ptr(x), ptr(out), x.numel(), float(p), int(seed), int(site), ptr(seed_dev),
+             _lib.stream())
+    return out

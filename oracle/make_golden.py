@@ -327,3 +327,54 @@ if __name__ == "__main__":
         gen_trad()
     if "stage12" in which:
         gen_stage12()
+
+
+def _tower_args(kind):
+    """argparse namespace the reference's build_model needs: opts defaults < JSON config (utils/config.py:6-23)."""
+    import argparse
+    import json as js
+    opts = ref_loader.load("tencentpretrain.opts")
+    parser = argparse.ArgumentParser()
+    opts.model_opts(parser)
+    args = parser.parse_args([])
+    cfg = js.load(open(os.path.join(ref_loader.REF, "models", "vit/base-16-224_config.json" if kind == "vit"
+                                    else "xlm-roberta/base_config.json")))
+    for k, v in cfg.items():
+        setattr(args, k, v)
+    args.tokenizer = argparse.Namespace(vocab=list(range(golden_util.TOWER_VOCAB)))
+    args.tie_weights = False
+    args.has_lmtarget_bias = False
+    args.labels_num = 3
+    return args
+
+
+def gen_tower():
+    """Reference build_model (tencentpretrain/model_builder.py:8) ViT-B/16 and RoBERTa-base: embedding + encoder
+    forward and backward on seeded inputs."""
+    mb = ref_loader.load("tencentpretrain.model_builder")
+    out = {}
+    for kind in ("vit", "roberta"):
+        args = _tower_args(kind)
+        model = mb.build_model(args)
+        model.eval()
+        names = [(n, tuple(p.shape)) for n, p in model.named_parameters() if not n.startswith("target.")]
+        sd = golden_util.make_tower_state_dict(names, golden_util.TOWER_SEEDS[kind])
+        missing = model.load_state_dict(sd, strict=False)
+        assert all(k.startswith("target.") for k in missing.missing_keys), missing
+        src, seg = golden_util.tower_inputs(kind)
+        hidden = model.encoder(model.embedding(src, seg), seg)
+        gw = golden_util.out_grad("actor", hidden.numel()).view_as(hidden)
+        (hidden * gw).sum().backward()
+        rec = {"names": names, "hidden": hidden.detach().clone()}
+        for n, p in model.named_parameters():
+            if n.startswith("target.") or p.grad is None:
+                continue
+            rec["gnorm/" + n] = p.grad.double().norm().float()
+            rec["grad/" + n] = (p.grad if p.grad.numel() <= 4096 else golden_util.grad_sample(p.grad)).clone()
+        out[kind] = rec
+        print("tower", kind, hidden.shape, hidden.flatten()[:3].tolist())
+    torch.save(out, os.path.join(GOLD, "tower.pt"))
+
+
+if __name__ == "__main__" and "tower" in sys.argv[1:]:
+    gen_tower()

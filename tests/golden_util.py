@@ -156,3 +156,36 @@ def stage_inputs(stage):
         chosen = torch.tensor([[0, 1, 0, 1], [1, 0, 0, 1]])[pick]       # reward_pair_dataloader.py:128-141
         reject = torch.tensor([[0, 1, 1, 0], [1, 0, 1, 0]])[pick]
     return text, img, tgts, chosen, reject
+
+
+# ---- TencentPretrain towers (build_model with the ViT-B/16 and xlm-roberta base configs) ------------------
+TOWER_VOCAB = 50265
+TOWER_SEEDS = dict(vit=511, roberta=522)
+
+
+def make_tower_state_dict(names, seed):
+    """names: [(param name, shape)] in the reference's named_parameters() order (stored in the golden file)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in names:
+        r = torch.randn(shape, generator=g)
+        if name.endswith("gamma"):
+            sd[name] = 1.0 + 0.1 * r
+        elif len(shape) >= 2:
+            sd[name] = r * 0.02
+        else:
+            sd[name] = r * 0.02
+    return sd
+
+
+def tower_inputs(kind):
+    g = torch.Generator().manual_seed(7700 + TOWER_SEEDS[kind])
+    if kind == "vit":
+        src = torch.randn(2, 3, 224, 224, generator=g)
+        seg = torch.ones(2, 197, dtype=torch.int64)
+    else:
+        src = torch.randint(5, TOWER_VOCAB, (3, 64), generator=g)
+        seg = torch.ones(3, 64, dtype=torch.int64)
+        seg[1, 40:] = 0                      # padded tail: masked keys (transformer_encoder.py:62-68)
+        seg[2, 56:] = 0
+    return src, seg

@@ -211,3 +211,18 @@ def test_trad_restatement_vs_reference_modules(kind):
             fusion_ref.trad_critic_forward(sd, text, index)
     ref = gold[kind]["logits"]
     assert (logits - ref).abs().max() <= 1e-5 * ref.abs().max().clamp_min(1.0)
+
+
+@pytest.mark.parametrize("kind", ["vit", "roberta"])
+def test_tower_restatement_vs_reference_build_model(kind):
+    """oracle/tower_ref.py == reference build_model(ViT-B/16 | RoBERTa-base).embedding/encoder on seeded tensors."""
+    from oracle import tower_ref
+    from tests import golden_util
+    gold = torch.load(os.path.join(GOLD, "tower.pt"))[kind]
+    sd = golden_util.make_tower_state_dict(gold["names"], golden_util.TOWER_SEEDS[kind])
+    src, seg = golden_util.tower_inputs(kind)
+    with torch.no_grad():
+        emb = tower_ref.embed_patch(sd, src) if kind == "vit" else tower_ref.embed_word(sd, src, seg)
+        hid = tower_ref.encoder(sd, emb, seg, 12, 12, pre_ln=(kind == "vit"))
+    ref = gold["hidden"]
+    assert (hid - ref).abs().max() <= 2e-5 * ref.abs().max()
