@@ -36,6 +36,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--fp32-fc1-grad", action="store_true",
+                    help="materialise the out_layer.fc1 weight gradient in fp32 (.grad) instead of the bf16 side buffer")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     return ap.parse_args()
 
@@ -197,7 +199,7 @@ def main():
     model, reward = build_models(torch, dev)
     hp = argparse.Namespace(learning_rate=LR, critic_learning_rate=CRITIC_LR, optimizer="adamw", scheduler="linear",
                             train_steps=TRAIN_STEPS, warmup=0.1, kl_div_loss_weight=0.001, entropy_weight=0.001,
-                            value_clip=0.5, mode="reg")
+                            value_clip=0.5, mode="reg", fc1_grad_bf16=not args.fp32_fc1_grad)
     opt, copt, sch, csch = ppo.build_optimizer(hp, model)
     sync = GradSync(world) if world > 1 else None
     if sync is not None:
@@ -359,7 +361,8 @@ def main():
                                        "advantage, fused policy/value losses, 2x AdamW) on synthetic LRMovieNet-shaped "
                                        "data; per-GPU batch 24 queries x 2 tags, text [24,2,196,768], img [24,2,16,768], "
                                        "fusion models 519M (actor) + 526M (critic) + 526M (reward) params, bf16 compute "
-                                       "/ fp32 master weights + fp32 Adam state",
+                                       "/ fp32 master weights + fp32 Adam state"
+                                       + ("" if args.fp32_fc1_grad else "; out_layer.fc1 weight gradient kept in bf16"),
                            "queries_per_step_per_gpu": BS, "parallelism": f"dp{world}",
                            "l2": "per-step working set (3 GB bf16 weights + 29 GB optimizer traffic) >> 126 MB L2; "
                                  "no explicit flush",

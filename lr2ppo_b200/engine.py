@@ -250,10 +250,20 @@ class FusionEngine:
         self._written = set()
         self.fc1_stash = None      # list of (dY, X) when out_layer.fc1 is updated by the fused wgrad+AdamW kernel
         self.dp_gather = None      # optional callable(t) -> all-gathered rows (data-parallel fused mode)
+        self.fc1_grad_bf16 = None  # bf16 [out, in] gradient buffer of out_layer.fc1.weight (see enable_bf16_fc1_grad)
 
     def begin_step(self):
         """Persistent-gradient mode: start of a new optimizer step (replaces model.zero_grad())."""
         self._written.clear()
+
+    def enable_bf16_fc1_grad(self, optimizer):
+        """Keep the gradient of out_layer.fc1.weight (97 % of the parameters) in a persistent bf16 buffer that
+        FusedAdamW reads directly; `.grad` of that parameter stays None.  One backward per optimizer step only
+        (no accumulation), i.e. stage 1 and stage 3."""
+        w = self.m.out_layer.fc1.weight
+        self.fc1_grad_bf16 = torch.empty(w.shape, dtype=bf16, device=w.device)
+        optimizer.register_shadow(w, self.bank.get(w))
+        optimizer.register_grad(w, self.fc1_grad_bf16)
 
     def enable_fused_fc1(self, optimizer):
         """Route out_layer.fc1.weight through lr2_gemm_wgrad_adamw (gradient never materialised)."""
@@ -381,6 +391,13 @@ class FusionEngine:
         if self.fc1_stash is not None:
             # fused mode: the optimizer consumes (dY, X) in lr2_gemm_wgrad_adamw; no 2 GB gradient is written
             self.fc1_stash.append((dy1p, ctx["cat"]))
+            sink.put_vec(W["o1"].mod.bias, ops.colsum(dy1p))
+        elif self.fc1_grad_bf16 is not None:
+            # bf16 gradient side-buffer read directly by FusedAdamW (1 GB written + read instead of 2 GB); in
+            # data-parallel runs the two small wgrad operands are all-gathered (global-batch gradient, no all-reduce)
+            dy_, x_ = (self.dp_gather(dy1p), self.dp_gather(ctx["cat"])) if self.dp_gather is not None \
+                else (dy1p, ctx["cat"])
+            ops.gemm(dy_, x_, a_mn=True, b_mn=True, out=self.fc1_grad_bf16)
             sink.put_vec(W["o1"].mod.bias, ops.colsum(dy1p))
         elif self.dp_gather is not None:
             # data parallel: gather the two (small) wgrad operands instead of all-reducing the 2 GB gradient

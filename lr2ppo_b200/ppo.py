@@ -45,6 +45,8 @@ def build_optimizer(args, model):
         # opt-in: correct but DRAM-page-locality bound today, so slower than wgrad + AdamW
         if getattr(args, "fused_fc1", False):
             eng.enable_fused_fc1(opt)
+        elif getattr(args, "fc1_grad_bf16", False):
+            eng.enable_bf16_fc1_grad(opt)
     sched = getattr(args, "scheduler", "linear")
     if sched == "constant":
         scheduler = str2scheduler[sched](optimizer)

@@ -21,8 +21,8 @@ def _margs():
                               visual_feat_dim=c["feat"])
 
 
-def _hp(fused):
-    return argparse.Namespace(learning_rate=1e-5, critic_learning_rate=2e-5, optimizer="adamw", scheduler="constant",
+def _hp(fused, bf16_grad=False):
+    return argparse.Namespace(fc1_grad_bf16=bf16_grad, learning_rate=1e-5, critic_learning_rate=2e-5, optimizer="adamw", scheduler="constant",
                               train_steps=1000, warmup=0.1, kl_div_loss_weight=0.001, entropy_weight=0.001,
                               value_clip=0.5, mode="reg", fused_fc1=fused)
 
@@ -57,9 +57,9 @@ def test_stage3_step_vs_cpu_oracle(sds):
     ra = stage3_ref.RefModel(sds["actor"]); rc = stage3_ref.RefModel(sds["critic"])
     rr = stage3_ref.RefModel(sds["reward"], trainable=False)
     mem_ref, out_ref = stage3_ref.step(ra, rc, rr, text, img, 1e-5, 2e-5)
-    # ---- CUDA engine (fused out_layer.fc1 wgrad+AdamW on)
+    # ---- CUDA engine
     model, reward = _build_gpu(sds)
-    hp = _hp(True)
+    hp = _hp(False, bf16_grad=True)              # the configuration bench.py runs: bf16 out_layer.fc1 gradient
     opt, copt, sch, csch = ppo.build_optimizer(hp, model)
     mem = ppo.rollout(model, reward, text.cuda(), img.cuda(), tgts.cuda())
     state, next_state, scores, rewards, value = mem[:5]
