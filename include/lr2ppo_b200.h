@@ -42,6 +42,8 @@ extern "C" {
 #define LR2_EPI_DGELU 4         /* out = acc * gelu_erf'(aux[r,c]) * dropout_mask             */
 #define LR2_EPI_ADD 5           /* out = acc + aux[r,c]                                       */
 #define LR2_EPI_ADAMW 6         /* internal: fused wgrad + AdamW (lr2_gemm_wgrad_adamw)       */
+#define LR2_EPI_BIAS_QGELU 7    /* like BIAS_GELU with QuickGELU x*sigmoid(1.702x) (video_transformer.py:91) */
+#define LR2_EPI_DQGELU 8        /* like DGELU with QuickGELU'                                 */
 
 int lr2_abi_version(void);
 const char* lr2_last_error_string(int code);

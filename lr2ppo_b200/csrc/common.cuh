@@ -73,6 +73,15 @@ __device__ __forceinline__ float gelu_fast_grad(float x) {
   return cdf + x * 0.39894228040143267794f * e;
 }
 
+// QuickGELU x * sigmoid(1.702 x) (CLIP-style blocks, ref: finetune/video_transformer.py:91-93)
+__device__ __forceinline__ float qgelu(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.702f * 1.4426950408889634f * x)); }
+__device__ __forceinline__ float qgelu_grad(float x) {
+  const float s = rcp_approx(1.0f + ex2_approx(-1.702f * 1.4426950408889634f * x));
+  return s + 1.702f * x * s * (1.0f - s);
+}
+__device__ __forceinline__ float act_fwd(int act, float x) { return act == 1 ? qgelu(x) : gelu_fast(x); }
+__device__ __forceinline__ float act_grad(int act, float x) { return act == 1 ? qgelu_grad(x) : gelu_fast_grad(x); }
+
 // ---- Philox4x32-10 counter RNG (dropout masks are a pure function of
 // (seed, site, element index), so backward regenerates them) -------------
 struct Philox4 {

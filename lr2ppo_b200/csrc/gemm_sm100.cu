@@ -58,6 +58,7 @@ struct GemmParams {
   float* ws;           // split-K workspace [splits][out_rows*ldc]
   long long ws_slab;   // elements per slab
   int raster;          // 0: tiles strided over CTAs, m fastest; 1: contiguous chunk per CTA, n fastest
+  int act;             // activation of the GELU epilogues: 0 = exact erf GELU, 1 = QuickGELU x*sigmoid(1.702x)
   // LR2_EPI_ADAMW (fused wgrad + AdamW): C = fp32 parameter (in/out)
   float* adam_m; float* adam_v; bf16* adam_shadow; const float* adam_hyper; float adam_wd;
 };
@@ -233,13 +234,13 @@ __device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], ui
     t = unpack_bf16x2(pre.z); x[4] = t.x; x[5] = t.y;
     t = unpack_bf16x2(pre.w); x[6] = t.x; x[7] = t.y;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? gelu_fast(x[i]) * dscale : 0.f;
+    for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? act_fwd(p.act, x[i]) * dscale : 0.f;
   } else if (p.epi == LR2_EPI_BIAS_DROP_RES) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = (((keep >> i) & 1u) ? v[i] * dscale : 0.f) + a[i];
   } else if (p.epi == LR2_EPI_DGELU) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * gelu_fast_grad(a[i]) * dscale : 0.f;
+    for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * act_grad(p.act, a[i]) * dscale : 0.f;
   } else if (p.epi == LR2_EPI_ADD) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += a[i];
@@ -280,11 +281,11 @@ __device__ __forceinline__ void epi_store1(const GemmParams& p, float v, long lo
       a = __bfloat162float(p.aux[r * p.ldaux + c]);
     if (p.epi == LR2_EPI_BIAS_GELU) {
       if (p.C2 != nullptr) p.C2[off] = __float2bfloat16(v);
-      v = gelu_fast(__bfloat162float(__float2bfloat16(v)));
+      v = act_fwd(p.act, __bfloat162float(__float2bfloat16(v)));
     } else if (p.epi == LR2_EPI_BIAS_DROP_RES || p.epi == LR2_EPI_ADD) {
       v += a;
     } else if (p.epi == LR2_EPI_DGELU) {
-      v *= gelu_fast_grad(a);
+      v *= act_grad(p.act, a);
     }
   }
   if (p.c_f32) ((float*)p.C)[off] = v;
@@ -675,7 +676,10 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
                              void* workspace, int block_n, void* stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   if (M <= 0 || N <= 0 || K <= 0) return LR2_ERR_BAD_SHAPE;
-  if (epilogue < 0 || epilogue > LR2_EPI_ADD) return LR2_ERR_UNSUPPORTED;
+  if (epilogue < 0 || epilogue > LR2_EPI_DQGELU || epilogue == LR2_EPI_ADAMW) return LR2_ERR_UNSUPPORTED;
+  int act = 0;
+  if (epilogue == LR2_EPI_BIAS_QGELU) { epilogue = LR2_EPI_BIAS_GELU; act = 1; }
+  if (epilogue == LR2_EPI_DQGELU) { epilogue = LR2_EPI_DGELU; act = 1; }
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B) | reinterpret_cast<uintptr_t>(C)) & 15)
     return LR2_ERR_MISALIGNED;
   if ((lda % 8) || (ldb % 8)) return LR2_ERR_MISALIGNED;
@@ -707,7 +711,7 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   memset(&p, 0, sizeof(p));
   p.M = M; p.N = N; p.K = K;
   p.splits = splits; p.kb_per_split = kb_per;
-  p.epi = epilogue; p.transposed_out = transposed_out; p.c_f32 = c_is_f32;
+  p.epi = epilogue; p.transposed_out = transposed_out; p.c_f32 = c_is_f32; p.act = act;
   p.C = C; p.ldc = ldc; p.C2 = reinterpret_cast<bf16*>(C2);
   p.bias = bias; p.aux = reinterpret_cast<const bf16*>(aux); p.ldaux = ldaux;
   p.beta = beta; p.drop_p = drop_p; p.seed = seed; p.site = site;

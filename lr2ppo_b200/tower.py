@@ -99,6 +99,9 @@ class _LayerW:
             bank.get_into(lin.weight, merged[i * inner:(i + 1) * inner])
         self.wqkv = merged
         self.bqkv = torch.cat([lin.bias.detach() for lin in att.linear_layers])
+        self.qkv_targets = [(lin.weight, lin.bias, i * inner, (i + 1) * inner) for i, lin in enumerate(att.linear_layers)]
+        self.lin_o, self.lin_1, self.lin_2 = att.final_linear, ff.linear_1, ff.linear_2
+        self.epi_act, self.epi_dact = EPI_BIAS_GELU, EPI_DGELU
         self.att, self.ff, self.layer = att, ff, layer
         self.wo, self.bo = bank.get(att.final_linear.weight), att.final_linear.bias.detach()
         self.w1, self.b1 = bank.get(ff.linear_1.weight), ff.linear_1.bias.detach()
@@ -111,8 +114,23 @@ class _LayerW:
         self.pre = layer.layernorm_positioning == "pre"
 
 
+def _lnp(ln):
+    """(gamma, beta, eps, kernel mode) of a TencentPretrain LayerNorm (gamma/beta) or a torch nn.LayerNorm."""
+    if hasattr(ln, "gamma"):
+        return ln.gamma, ln.beta, ln.eps, LN_MODE
+    return ln.weight, ln.bias, ln.eps, 0
+
+
 def _ln(x, ln, save, out=None):
-    return ops.layernorm_fwd(x, ln.gamma.detach(), ln.beta.detach(), ln.eps, LN_MODE, out=out, want_stats=save)
+    g, b, eps, mode = _lnp(ln)
+    return ops.layernorm_fwd(x, g.detach(), b.detach(), eps, mode, out=out, want_stats=save)
+
+
+def _ln_bwd(sink, ln, dy, x, st, **kw):
+    g, b, eps, mode = _lnp(ln)
+    dx, dxm, dg, db = ops.layernorm_bwd(dy, x, g.detach(), st, eps, mode, **kw)
+    sink.put_vec(g, dg); sink.put_vec(b, db)
+    return dx, dxm
 
 
 def layer_forward(W, h, kbias, B, S, train, seed, seed_dev, site, save):
@@ -137,7 +155,7 @@ def layer_forward(W, h, kbias, B, S, train, seed, seed_dev, site, save):
         i1, st2 = _ln(t, W.ln1, save)                                 # post-LN: layer_norm_1(inter + hidden)
         f_in, res2 = i1, i1
     pre = torch.empty((h.shape[0], W.w1.shape[0]), dtype=bf16, device=h.device) if save else None
-    f = ops.gemm(f_in, W.w1, epilogue=EPI_BIAS_GELU, bias=W.b1, c2=pre)
+    f = ops.gemm(f_in, W.w1, epilogue=W.epi_act, bias=W.b1, c2=pre)
     t2 = ops.gemm(f, W.w2, epilogue=EPI_BIAS_DROP_RES, bias=W.b2, aux=res2, drop_p=p2, seed=seed, site=site + 1,
                   seed_dev=seed_dev)                                  # dropout_2(ffn) + residual
     if W.pre:
@@ -161,50 +179,37 @@ def layer_backward(W, c, dout, dout_m, sink, prev_site2=None, prev_p2=0.0):
     post-LN: dout = grad wrt out = LN2(t2); dout_m unused. Returns (dh, None)."""
     pa, p1, p2 = c["p"]
     seed, sdev, site, B, S = c["seed"], c["seed_dev"], c["site"], c["B"], c["S"]
-    ff, att = W.ff, W.att
-    E = W.wo.shape[0]
     if W.pre:
-        dy2 = dout_m                                                     # grad into dropout_2's input
+        dy2 = dout_m if dout_m is not None else dout                     # grad into dropout_2's input
         res_grad = dout
     else:
-        ln2 = W.ln2
-        dt2, dy2, dg, db = ops.layernorm_bwd(dout, c["t2"], ln2.gamma.detach(), c["st3"], ln2.eps, LN_MODE, drop_p=p2,
-                                             seed=seed, site=site + 1, want_masked=True, seed_dev=sdev)
-        sink.put_vec(ln2.gamma, dg); sink.put_vec(ln2.beta, db)
+        dt2, dy2 = _ln_bwd(sink, W.ln2, dout, c["t2"], c["st3"], drop_p=p2, seed=seed, site=site + 1,
+                           want_masked=True, seed_dev=sdev)
         res_grad = dt2
-    _put_lin(sink, ff.linear_2, dy2, c["f"])
-    dfp = eng._dgrad(dy2, W.w2, epilogue=EPI_DGELU, aux=c["pre"])
-    _put_lin(sink, ff.linear_1, dfp, c["f_in"])
+    _put_lin(sink, W.lin_2, dy2, c["f"])
+    dfp = eng._dgrad(dy2, W.w2, epilogue=W.epi_dact, aux=c["pre"])
+    _put_lin(sink, W.lin_1, dfp, c["f_in"])
     if W.pre:
         dl2 = eng._dgrad(dfp, W.w1)
-        ln = W.ln2
-        dt, dy1, dg, db = ops.layernorm_bwd(dl2, c["t"], ln.gamma.detach(), c["st2"], ln.eps, LN_MODE, add=res_grad,
-                                            drop_p=p1, seed=seed, site=site, want_masked=True, seed_dev=sdev)
-        sink.put_vec(ln.gamma, dg); sink.put_vec(ln.beta, db)
+        dt, dy1 = _ln_bwd(sink, W.ln2, dl2, c["t"], c["st2"], add=res_grad, drop_p=p1, seed=seed, site=site,
+                          want_masked=True, seed_dev=sdev)
     else:
         di1 = eng._dgrad(dfp, W.w1, epilogue=EPI_ADD, aux=res_grad)     # + residual branch of i1
-        ln = W.ln1
-        dt, dy1, dg, db = ops.layernorm_bwd(di1, c["t"], ln.gamma.detach(), c["st2"], ln.eps, LN_MODE, drop_p=p1,
-                                            seed=seed, site=site, want_masked=True, seed_dev=sdev)
-        sink.put_vec(ln.gamma, dg); sink.put_vec(ln.beta, db)
+        dt, dy1 = _ln_bwd(sink, W.ln1, di1, c["t"], c["st2"], drop_p=p1, seed=seed, site=site, want_masked=True,
+                          seed_dev=sdev)
     # attention output projection, core, merged QKV projection
-    _put_lin(sink, att.final_linear, dy1, c["a"])
+    _put_lin(sink, W.lin_o, dy1, c["a"])
     da = eng._dgrad(dy1, W.wo)
     dqkv = ops.mha_bwd(c["qkv"], c["a"], da, c["lse"], B, S, W.heads, c["kbias"], W.scale, pa, seed + 7919 * site, sdev)
-    inner = att.inner_hidden_size
     gw = ops.gemm(dqkv, c["a_in"], a_mn=True, b_mn=True, out_dtype=torch.float32)          # [3*inner, E]
     gb = ops.colsum(dqkv)
-    for i, lin in enumerate(att.linear_layers):
-        sink.put_vec(lin.weight, gw[i * inner:(i + 1) * inner])
-        sink.put_vec(lin.bias, gb[i * inner:(i + 1) * inner])
+    for wp, bp, lo, hi in W.qkv_targets:
+        sink.put_vec(wp, gw[lo:hi])
+        sink.put_vec(bp, gb[lo:hi])
     if W.pre:
         dl1 = eng._dgrad(dqkv, W.wqkv)
-        ln = W.ln1
-        dh, dh_m, dg, db = ops.layernorm_bwd(dl1, c["h"], ln.gamma.detach(), c["st1"], ln.eps, LN_MODE, add=dt,
-                                             drop_p=prev_p2, seed=seed, site=(prev_site2 or 0),
-                                             want_masked=prev_site2 is not None, seed_dev=sdev)
-        sink.put_vec(ln.gamma, dg); sink.put_vec(ln.beta, db)
-        return dh, dh_m
+        return _ln_bwd(sink, W.ln1, dl1, c["h"], c["st1"], add=dt, drop_p=prev_p2, seed=seed, site=(prev_site2 or 0),
+                       want_masked=prev_site2 is not None, seed_dev=sdev)
     dh = eng._dgrad(dqkv, W.wqkv, epilogue=EPI_ADD, aux=dt)
     return dh, None
 
@@ -276,12 +281,9 @@ class TransformerEncoder(nn.Module):
         d, dm = dhid, None
         if self.layernorm_positioning == "pre":
             x_last, st = ctx["fin"]
-            ln = self.layer_norm
             last = ctxs[-1]
-            d, dm, dg, db = ops.layernorm_bwd(dhid, x_last, ln.gamma.detach(), st, ln.eps, LN_MODE,
-                                              drop_p=last["p"][2], seed=ctx["seed"], site=last["site"] + 1,
-                                              want_masked=True, seed_dev=ctx["sdev"])
-            sink.put_vec(ln.gamma, dg); sink.put_vec(ln.beta, db)
+            d, dm = _ln_bwd(sink, self.layer_norm, dhid, x_last, st, drop_p=last["p"][2], seed=ctx["seed"],
+                            site=last["site"] + 1, want_masked=True, seed_dev=ctx["sdev"])
         for i in range(n - 1, -1, -1):
             prev = ctxs[i - 1] if i > 0 else None
             d, dm = layer_backward(Ws[i], ctxs[i], d, dm, sink,
@@ -427,9 +429,7 @@ class Embedding(nn.Module):
             d = ops.dropout(d, p, seed, 9, sdev)
         if "ln" in c:
             x, st = c["ln"]
-            ln = self.layer_norm
-            d, _, dg, db = ops.layernorm_bwd(d, x, ln.gamma.detach(), st, ln.eps, LN_MODE)
-            sink.put_vec(ln.gamma, dg); sink.put_vec(ln.beta, db)
+            d, _ = _ln_bwd(sink, self.layer_norm, d, x, st)
         dpos = ops.add_pos_bwd(d, B, S)                                               # sum over the batch
         gpos = torch.zeros_like(self.pos.embedding.weight)
         gpos[:S] = dpos

@@ -51,7 +51,13 @@ def rep(src, dst):
             name = short(r[hdr.index("Kernel Name")])
             f.write(f"## {name}  grid {r[hdr.index('Grid Size')]} block {r[hdr.index('Block Size')]}\n\n")
             for m in hdr:
-                if any(m.startswith(w) for w in METRICS) or "tensor" in m and "pct" in m:
+                if m in METRICS or m in ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+                                         "sm__inst_executed_pipe_tensor.sum",
+                                         "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+                                         "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed",
+                                         "dram__bytes_read.sum.per_second", "dram__bytes_write.sum.per_second",
+                                         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+                                         "smsp__inst_executed.sum", "sm__cycles_elapsed.max"):
                     f.write(f"- {m} = {r[hdr.index(m)]} {units[hdr.index(m)]}\n")
             f.write("\n")
     print(open(dst).read()[:4000])
