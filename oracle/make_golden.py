@@ -378,3 +378,31 @@ def gen_tower():
 
 if __name__ == "__main__" and "tower" in sys.argv[1:]:
     gen_tower()
+
+
+def gen_api():
+    """Reference VideoTransformer (finetune/video_transformer.py:8) and ProjectionLayer
+    (finetune/project_embedding.py:5), never built by the scripts: API-parity goldens."""
+    vt = ref_loader.load("video_transformer")
+    pe = ref_loader.load("project_embedding")
+    out = {}
+    for kind in ("video", "proj"):
+        model = vt.VideoTransformer(**golden_util.VIDEO_CFG) if kind == "video" else pe.ProjectionLayer(768, 512, 0.2)
+        model.eval()
+        names = [(n, tuple(p.shape)) for n, p in model.named_parameters()]
+        model.load_state_dict(golden_util.make_api_state_dict(names, golden_util.API_SEEDS[kind]), strict=True)
+        x = golden_util.api_input(kind).requires_grad_(True)
+        y = model(x)
+        gw = golden_util.out_grad("critic", y.numel()).view_as(y)
+        (y * gw).sum().backward()
+        rec = {"names": names, "y": y.detach().clone(), "dx": x.grad.clone()}
+        for n, p in model.named_parameters():
+            rec["gnorm/" + n] = p.grad.double().norm().float()
+            rec["grad/" + n] = (p.grad if p.grad.numel() <= 4096 else golden_util.grad_sample(p.grad)).clone()
+        out[kind] = rec
+        print("api", kind, y.shape, y.flatten()[:3].tolist())
+    torch.save(out, os.path.join(GOLD, "api.pt"))
+
+
+if __name__ == "__main__" and "api" in sys.argv[1:]:
+    gen_api()

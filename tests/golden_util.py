@@ -189,3 +189,23 @@ def tower_inputs(kind):
         seg[1, 40:] = 0                      # padded tail: masked keys (transformer_encoder.py:62-68)
         seg[2, 56:] = 0
     return src, seg
+
+
+# ---- API-parity modules (VideoTransformer, ProjectionLayer) ---------------------------------------------
+VIDEO_CFG = dict(frame_size=16, emb_size=768, layers=2, heads=12, output_dim=512)
+API_SEEDS = dict(video=611, proj=622)
+
+
+def make_api_state_dict(names, seed):
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name, shape in names:
+        r = torch.randn(shape, generator=g)
+        is_ln_w = name.endswith("weight") and ("ln_" in name or "layer_norm" in name)
+        sd[name] = 1.0 + 0.1 * r if is_ln_w else (r * 0.03 if len(shape) >= 2 else r * 0.02)
+    return sd
+
+
+def api_input(kind):
+    g = torch.Generator().manual_seed(7900 + API_SEEDS[kind])
+    return torch.randn(5, 16, 768, generator=g) if kind == "video" else torch.randn(7, 33, 768, generator=g)

@@ -96,3 +96,21 @@ def test_stage_train_step_vs_reference_train_model(stage):
         big = ref.abs() > 0.5 * ref.abs().max()                      # entries whose gradient is well above bf16 noise
         if big.sum() > 0 and gold["mnorm/" + n].item() > 0:
             assert (torch.sign(got[big]) == torch.sign(ref[big])).float().mean() > 0.98, n
+
+
+@pytest.mark.parametrize("kind", ["video", "proj"])
+def test_api_modules_vs_reference(kind):
+    """VideoTransformer / ProjectionLayer (imported-but-unused reference modules): same constructor, same
+    state_dict keys, outputs and gradients vs the reference's own modules (tests/golden/api.pt)."""
+    from lr2ppo_b200.project_embedding import ProjectionLayer
+    from lr2ppo_b200.video_transformer import VideoTransformer
+    gold = torch.load(os.path.join(GOLD, "api.pt"))[kind]
+    model = VideoTransformer(**golden_util.VIDEO_CFG) if kind == "video" else ProjectionLayer(768, 512, 0.2)
+    model.load_state_dict(golden_util.make_api_state_dict(gold["names"], golden_util.API_SEEDS[kind]), strict=True)
+    model = model.cuda().eval()
+    x = golden_util.api_input(kind).cuda().requires_grad_(True)
+    y = model(x)
+    assert y.shape == gold["y"].shape and _rel(y, gold["y"]) < TOL
+    (y * golden_util.out_grad("critic", y.numel()).view_as(y).cuda()).sum().backward()
+    assert _rel(x.grad, gold["dx"]) < 2 * TOL
+    _check_grads(list(model.named_parameters()), lambda p: p.grad, gold, "grad/", "gnorm/")
