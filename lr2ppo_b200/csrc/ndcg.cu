@@ -33,6 +33,8 @@ __device__ __forceinline__ float gain_of(long long rel) {
   return (float)g;
 }
 
+constexpr int NDCG_MAX_K = 32;
+
 template <typename K>
 __device__ __forceinline__ void bitonic_sort(K* keys, int npad) {
   for (int k = 2; k <= npad; k <<= 1) {
@@ -57,41 +59,79 @@ __global__ void ndcg_kernel(const float* __restrict__ scores, const long long* _
   extern __shared__ __align__(16) unsigned char nsm[];
   unsigned long long* skey = reinterpret_cast<unsigned long long*>(nsm);  // [npad] (score,idx) keys
   unsigned long long* lkey = skey + npad;                                  // [npad] label keys
-  float* tp = reinterpret_cast<float*>(lkey + npad);                       // [npad] predicted terms -> prefix
-  float* ti = tp + npad;                                                   // [npad] ideal terms -> prefix
+  float* tp = reinterpret_cast<float*>(lkey + npad);                       // [npad] predicted terms
+  float* ti = tp + npad;                                                   // [npad] ideal terms (fallback path)
+  __shared__ int hist[64];        // label histogram (labels in [0, 62]: every realistic relevance scale)
+  __shared__ int out_of_range;
+  __shared__ float cut_p[NDCG_MAX_K], cut_i[NDCG_MAX_K];
   const int q = blockIdx.x;
   const int n = lens ? min(lens[q], N) : N;
   const float* sq = scores + (long long)q * ld;
   const long long* lq = labels + (long long)q * ld;
+  if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+  if (threadIdx.x == 0) out_of_range = 0;
+  __syncthreads();
   for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-    if (i < n) { skey[i] = score_key(sq[i], (unsigned int)i); lkey[i] = label_key(lq[i]); }
-    else { skey[i] = ~0ull; lkey[i] = ~0ull; }
+    if (i < n) {
+      const long long lab = lq[i];
+      skey[i] = score_key(sq[i], (unsigned int)i);
+      lkey[i] = label_key(lab);
+      if (lab >= 0 && lab <= 62) atomicAdd(&hist[(int)lab], 1);
+      else out_of_range = 1;
+    } else { skey[i] = ~0ull; lkey[i] = ~0ull; }
   }
   __syncthreads();
   bitonic_sort(skey, npad);
-  bitonic_sort(lkey, npad);
+  const bool fallback = out_of_range != 0;   // arbitrary int64 labels: sort them too
+  if (fallback) bitonic_sort(lkey, npad);
+  // sorted cut positions (min(N, k), ascending) and their original slots
+  __shared__ int cut_pos[NDCG_MAX_K], cut_slot[NDCG_MAX_K];
+  __shared__ int hstart[64];      // first ideal position of label L
+  if (threadIdx.x == 0) {
+    for (int j = 0; j < nk; ++j) {
+      const long long c = ks[j] < (long long)n ? ks[j] : (long long)n;
+      int p = j;
+      while (p > 0 && cut_pos[p - 1] > (int)c) { cut_pos[p] = cut_pos[p - 1]; cut_slot[p] = cut_slot[p - 1]; --p; }
+      cut_pos[p] = (int)(c < 0 ? 0 : c); cut_slot[p] = j;
+    }
+  } else if (threadIdx.x == 32) {
+    int pos = 0;
+    for (int L = 62; L >= 0; --L) { hstart[L] = pos; pos += hist[L]; }
+  }
+  __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     const unsigned int idx = (unsigned int)(skey[i] & 0xFFFFFFFFull);
     if (order != nullptr) order[(long long)q * ld + i] = idx;
     const float lg = log2_table[i];
     tp[i] = gain_of(lq[idx]) / lg;
-    ti[i] = gain_of(label_from_key(lkey[i])) / lg;
+    if (fallback) {
+      ti[i] = gain_of(label_from_key(lkey[i])) / lg;
+    } else {
+      // ideal order = labels descending: position i holds the label L with hstart[L] <= i < hstart[L] + hist[L]
+      int lo = 0, hi = 62;                       // hstart is non-increasing in L
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (hstart[mid] <= i) hi = mid; else lo = mid + 1; }
+      // lo = smallest L with hstart[L] <= i; skip empty bins above the true one
+      int L = lo;
+      while (L < 62 && hist[L] == 0) ++L;
+      ti[i] = gain_of((long long)L) / lg;
+    }
   }
   __syncthreads();
-  // strictly sequential fp32 prefix sums (two lists -> two warps)
-  if (threadIdx.x == 0) {
+  // strictly sequential fp32 sums (two lists -> two warps), walked cut to cut
+  if (threadIdx.x == 0 || threadIdx.x == 32) {
+    const float* t = threadIdx.x == 0 ? tp : ti;
+    float* outc = threadIdx.x == 0 ? cut_p : cut_i;
     float acc = 0.f;
-    for (int i = 0; i < n; ++i) { acc = acc + tp[i]; tp[i] = acc; }
-  } else if (threadIdx.x == 32) {
-    float acc = 0.f;
-    for (int i = 0; i < n; ++i) { acc = acc + ti[i]; ti[i] = acc; }
+    int i = 0;
+    for (int j = 0; j < nk; ++j) {
+      const int c = cut_pos[j];
+      for (; i < c; ++i) acc = acc + t[i];
+      outc[cut_slot[j]] = acc;
+    }
   }
   __syncthreads();
   for (int j = threadIdx.x; j < nk; j += blockDim.x) {
-    const long long k = ks[j];
-    const int cut = (int)((k < (long long)n) ? k : (long long)n);
-    const float p = cut > 0 ? tp[cut - 1] : 0.f;
-    const float t = cut > 0 ? ti[cut - 1] : 0.f;
+    const float p = cut_p[j], t = cut_i[j];
     ndcg[(long long)q * nk + j] = (t <= 1e-6f) ? 1.0f : p / t;
   }
 }
@@ -104,11 +144,11 @@ extern "C" int lr2_ndcg_at_k(const float* scores, const long long* labels, const
                              const long long* ks, int nk, const float* log2_table, float* ndcg, long long* order,
                              void* stream) {
   if (B <= 0 || N <= 0 || nk <= 0 || ld < N) return LR2_ERR_BAD_SHAPE;
-  if (N > 4096) return LR2_ERR_UNSUPPORTED;
+  if (N > 4096 || nk > lr2::NDCG_MAX_K) return LR2_ERR_UNSUPPORTED;
   int npad = 2;
   while (npad < N) npad <<= 1;
   const size_t smem = (size_t)npad * (8 + 8 + 4 + 4);
-  static size_t configured = 48 * 1024;
+  static size_t configured = 40 * 1024;   // static shared memory of the kernel counts against the 48 KB default
   if (smem > configured) {
     if (cudaFuncSetAttribute(ndcg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return LR2_ERR_CUDA;

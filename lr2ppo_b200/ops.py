@@ -11,6 +11,7 @@ from . import _lib
 from ._lib import ptr, check
 
 EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_BIAS_DROP_RES, EPI_DGELU, EPI_ADD = range(6)
+EPI_BIAS_QGELU, EPI_DQGELU = 7, 8   # QuickGELU variants (6 is the internal fused-AdamW epilogue)
 
 bf16 = torch.bfloat16
 f32 = torch.float32
@@ -350,6 +351,16 @@ def log2_table(n, device):
     return _log2_tables[key]
 
 
+_ks_cache = {}
+
+
+def _ks_tensor(ks, dev):
+    key = (str(dev), tuple(ks))
+    if key not in _ks_cache:
+        _ks_cache[key] = torch.tensor(list(ks), dtype=i64, device=dev)
+    return _ks_cache[key]
+
+
 def ndcg_at_k(scores, labels, ks, lens=None, want_order=False):
     """scores f32 [B,N], labels i64 [B,N], ks list[int] -> ndcg f32 [B, len(ks)] (+ order i64 [B,N])."""
     L = _L()
@@ -358,7 +369,7 @@ def ndcg_at_k(scores, labels, ks, lens=None, want_order=False):
         _cuda(lens, torch.int32)
     B, N = scores.shape
     dev = scores.device
-    ks_t = torch.tensor(list(ks), dtype=i64, device=dev)
+    ks_t = _ks_tensor(ks, dev)
     out = torch.empty((B, len(ks)), dtype=f32, device=dev)
     order = torch.full((B, N), -1, dtype=i64, device=dev) if want_order else None
     _lib.run(L.lr2_ndcg_at_k, ptr(scores), ptr(labels), ptr(lens), B, N, N, ptr(ks_t), len(ks), ptr(log2_table(N, dev)),
