@@ -31,7 +31,7 @@ FLOP_PER_QUERY = 107.5e9
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -42,31 +42,40 @@ def parse():
     return ap.parse_args()
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms DURING the timed region (B200_PROFILING.md)."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.proc, self.rows = index, None, []
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.rows.append([c.strip() for c in line.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        for line in out.strip().splitlines():
+            self.rows.append([c.strip() for c in line.split(",")])
 
     def summary(self):
         sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
         mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in self.rows if len(r) >= 8 and r[3].replace(".", "").isdigit()]
         reasons = set()
         for r in self.rows:
             if len(r) >= 8:
@@ -74,7 +83,7 @@ class ClockSampler(threading.Thread):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ------------------------------------------------------------------ reference arm (CPU oracle port) ------
@@ -155,6 +164,24 @@ def build_models(torch, device):
                     mod.weight.fill_(1.0)
     model.eval(); reward.eval()
     return model, reward
+
+
+def ncu_traffic(name):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes, largest captured launch) from the committed ncu
+    --set full summary under profiles/, or None."""
+    try:
+        best = None
+        rd = wr = None
+        for line in open(os.path.join(ROOT, "profiles", name)):
+            if line.startswith("- dram__bytes_read.sum ="):
+                rd = float(line.split("=")[1].split()[0]) * (1e9 if "Gbyte" in line else 1e6)
+            if line.startswith("- dram__bytes_write.sum ="):
+                wr = float(line.split("=")[1].split()[0]) * (1e9 if "Gbyte" in line else 1e6)
+                if rd is not None:
+                    best = max(best or 0.0, rd + wr)
+        return best
+    except Exception:
+        return None
 
 
 def summarize_profile(torch, prof, steps):
@@ -276,9 +303,10 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)                      # let the sampler take its first readings under the tail of the warm-up
     ms, launches = timed(lambda i: step(resident[i % len(resident)]), args.steps)
     if rank == 0:
-        sampler.stop_flag = True
+        sampler.stop()
     value = world * BS * args.steps / (ms / 1e3)
 
     # ---- (2) end-to-end: pinned host -> device every step, stats read back every step ---------------------
@@ -320,11 +348,13 @@ def main():
         gp = groups[top]
         n_params = sum(p.numel() for p in model.parameters())
         if top == "lr2_adamw_multi":
-            # 28 B/param (p,g,m,v read; p,m,v write, fp32) + 2 B/param bf16 shadow for matrices
-            per_launch = 30.0 * n_params / gp["calls"] * args.profile_steps
-            ach = per_launch / (gp["ms"] / gp["calls"] * 1e-3) / 1e9
+            # the two weight-matrix launches (actor, critic): read p, g, m, v + write p, m, v + bf16 shadow
+            big = sorted((e0.elapsed_time(e1) for nm, a, e0, e1 in prof if nm == "lr2_adamw_multi" and a[3] > 1000))
+            per_launch = (opt.algorithmic_bytes(0) + copt.algorithmic_bytes(0)) / 2.0
+            ach = per_launch / (sum(big) / len(big) * 1e-3) / 1e9
             roofline = {"kernel": "adamw_multi_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
-                        "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None, "peak_source": hbm_src,
+                        "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic("r01_adamw_full.md"),
+                        "peak_source": hbm_src,
                         "share_of_step": gp["ms_per_step"] / total_ms,
                         "algorithmic_bytes_per_launch": per_launch}
         elif top.startswith("gemm"):

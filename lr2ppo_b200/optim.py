@@ -136,6 +136,16 @@ class FusedAdamW(Optimizer):
             ent["host"] = hv
         return ent["dev"]
 
+    def algorithmic_bytes(self, gi):
+        """HBM bytes one lr2_adamw_multi launch of group gi must move: read p, g, m, v + write p, m, v (+ bf16 shadow)."""
+        total = 0
+        for p in self.param_groups[gi]["params"]:
+            g = self._grad_of(p)
+            if g is None or id(p) in self._fused:
+                continue
+            total += p.numel() * (4 + g.element_size() + 4 + 4 + 4 + 4 + 4 + (2 if id(p) in self._shadows else 0))
+        return total
+
     def update_hyper(self):
         """Recompute lr / bias-correction on the host and upload the 8 floats of every group asynchronously
         (pinned staging).  Used with CUDA graphs, where `step()` itself must not copy from the host."""
