@@ -304,6 +304,97 @@ struct SmemLayout {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024;  // +1024 for manual alignment
 };
 
+// Drain one accumulator tile (this warp's TMEM lane quadrant and column part): TMEM -> registers -> per-warp smem
+// staging -> coalesced 8-wide groups through the fused epilogue.  Shared by the 1-CTA and 2-CTA kernels.
+template <int BN, bool ADAMW>
+__device__ __forceinline__ void drain_tile(const GemmParams& q, uint32_t taddr, int m_base, int nt,
+                                           float* stg, int lane, int half) {
+  constexpr int COLS_PER_WARP = (BN / 4 < 32) ? 32 : BN / 4;    // BN=64: only parts 0,1 have columns
+  constexpr int CW = 32;                                        // chunk width
+  constexpr int TPR = CW / 8;                                   // lanes per row in the coalesced phase
+  constexpr int RPI = 32 / TPR;                                 // rows per iteration
+#pragma unroll 1
+  for (int c0 = half * COLS_PER_WARP; c0 < (half + 1) * COLS_PER_WARP && c0 < BN; c0 += CW) {
+    const int n_base = nt * BN + c0;
+    if (n_base >= q.N) break;  // warp-uniform
+    if (!q.transposed_out) {
+#pragma unroll
+      for (int cc = 0; cc < CW; cc += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)(c0 + cc), r);
+        tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(stg + lane * STG_PITCH + cc);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                               __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+      }
+      __syncwarp();
+      const int cg = (lane % TPR) * 8;
+#pragma unroll 1
+      for (int rr = 0; rr < 32; rr += 2 * RPI) {
+        const int rl0 = rr + lane / TPR, rl1 = rl0 + RPI;
+        const int m0 = m_base + rl0, m1 = m_base + rl1;
+        const int n = n_base + cg;
+        const bool full = (n + 8 <= q.N);
+        if (full && m1 < q.M) {
+          // two independent 8-wide groups in flight (rows rl0 and rl1)
+          const float4* s0 = reinterpret_cast<const float4*>(stg + rl0 * STG_PITCH + cg);
+          const float4* s1 = reinterpret_cast<const float4*>(stg + rl1 * STG_PITCH + cg);
+          const float4 x0 = s0[0], x1 = s0[1], y0 = s1[0], y1 = s1[1];
+          float v0[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          float v1[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+          uint4 p0 = make_uint4(0, 0, 0, 0), p1 = make_uint4(0, 0, 0, 0);
+          if constexpr (ADAMW) {   // HBM-bound: one group at a time keeps the register budget
+            epi_math8<true>(q, v0, p0, m0, n);
+            epi_write8(q, v0, p0, m0, n);
+            epi_math8<true>(q, v1, p1, m1, n);
+            epi_write8(q, v1, p1, m1, n);
+          } else {
+            epi_math8<false>(q, v0, p0, m0, n);
+            epi_math8<false>(q, v1, p1, m1, n);
+            epi_write8(q, v0, p0, m0, n);
+            epi_write8(q, v1, p1, m1, n);
+          }
+        } else {
+#pragma unroll 1
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const int row_l = h2 ? rl1 : rl0;
+            const int m = m_base + row_l;
+            if (m < q.M && n < q.N) {
+              const float4* src = reinterpret_cast<const float4*>(stg + row_l * STG_PITCH + cg);
+              const float4 x0 = src[0], x1 = src[1];
+              float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+              if (full) {
+                epi_store8(q, v, m, n);
+              } else {
+                for (int i = 0; i < 8; ++i)
+                  if (n + i < q.N) epi_store1(q, v[i], m, n + i);
+              }
+            }
+          }
+        }
+      }
+      __syncwarp();
+    } else {
+      // transposed tile (skinny GEMMs): lane = output column m, registers = output rows; a warp store
+      // writes 32 consecutive columns of one output row.
+      const int m = m_base + lane;
+#pragma unroll 1
+      for (int cc = 0; cc < CW; cc += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + (uint32_t)(c0 + cc), r);
+        tmem_ld_wait();
+        if (m < q.M) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (n_base + cc + i < q.N) epi_store1(q, __uint_as_float(r[i]), n_base + cc + i, m);
+        }
+      }
+    }
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN, bool ADAMW>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -435,10 +526,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;                             // column part 0..3
     float* stg = stg_all + (size_t)(warp - 2) * 32 * STG_PITCH;
-    constexpr int COLS_PER_WARP = (BN / 4 < 32) ? 32 : BN / 4;    // BN=64: only parts 0,1 have columns
-    constexpr int CW = 32;                                        // chunk width
-    constexpr int TPR = CW / 8;                                   // lanes per row in the coalesced phase
-    constexpr int RPI = 32 / TPR;                                 // rows per iteration
     int it = 0;
     for (int w = w_begin; w < w_end; w += w_step, ++it) {
       const int split = w % p.splits;
@@ -455,86 +542,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         q.epi = LR2_EPI_NONE; q.c_f32 = 1; q.beta = 0.f; q.drop_p = 0.f;
         q.C = p.ws + (long long)split * p.ws_slab;
       }
-#pragma unroll 1
-      for (int c0 = half * COLS_PER_WARP; c0 < (half + 1) * COLS_PER_WARP && c0 < BN; c0 += CW) {
-        const int n_base = nt * BN + c0;
-        if (n_base >= p.N) break;  // warp-uniform
-        if (!p.transposed_out) {
-#pragma unroll
-          for (int cc = 0; cc < CW; cc += 32) {
-            uint32_t r[32];
-            tmem_ld32(taddr + (uint32_t)(c0 + cc), r);
-            tmem_ld_wait();
-            float4* dst = reinterpret_cast<float4*>(stg + lane * STG_PITCH + cc);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-          }
-          __syncwarp();
-          const int cg = (lane % TPR) * 8;
-#pragma unroll 1
-          for (int rr = 0; rr < 32; rr += 2 * RPI) {
-            const int rl0 = rr + lane / TPR, rl1 = rl0 + RPI;
-            const int m0 = m_base + rl0, m1 = m_base + rl1;
-            const int n = n_base + cg;
-            const bool full = (n + 8 <= p.N);
-            if (full && m1 < p.M) {
-              // two independent 8-wide groups in flight (rows rl0 and rl1)
-              const float4* s0 = reinterpret_cast<const float4*>(stg + rl0 * STG_PITCH + cg);
-              const float4* s1 = reinterpret_cast<const float4*>(stg + rl1 * STG_PITCH + cg);
-              const float4 x0 = s0[0], x1 = s0[1], y0 = s1[0], y1 = s1[1];
-              float v0[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-              float v1[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-              uint4 p0 = make_uint4(0, 0, 0, 0), p1 = make_uint4(0, 0, 0, 0);
-              if constexpr (ADAMW) {   // HBM-bound: one group at a time keeps the register budget
-                epi_math8<true>(q, v0, p0, m0, n);
-                epi_write8(q, v0, p0, m0, n);
-                epi_math8<true>(q, v1, p1, m1, n);
-                epi_write8(q, v1, p1, m1, n);
-              } else {
-                epi_math8<false>(q, v0, p0, m0, n);
-                epi_math8<false>(q, v1, p1, m1, n);
-                epi_write8(q, v0, p0, m0, n);
-                epi_write8(q, v1, p1, m1, n);
-              }
-            } else {
-#pragma unroll 1
-              for (int h2 = 0; h2 < 2; ++h2) {
-                const int row_l = h2 ? rl1 : rl0;
-                const int m = m_base + row_l;
-                if (m < p.M && n < p.N) {
-                  const float4* src = reinterpret_cast<const float4*>(stg + row_l * STG_PITCH + cg);
-                  const float4 x0 = src[0], x1 = src[1];
-                  float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-                  if (full) {
-                    epi_store8(q, v, m, n);
-                  } else {
-                    for (int i = 0; i < 8; ++i)
-                      if (n + i < p.N) epi_store1(q, v[i], m, n + i);
-                  }
-                }
-              }
-            }
-          }
-          __syncwarp();
-        } else {
-          // transposed tile (skinny GEMMs): lane = output column m, registers = output rows; a warp store
-          // writes 32 consecutive columns of one output row.
-          const int m = m_base + lane;
-#pragma unroll 1
-          for (int cc = 0; cc < CW; cc += 32) {
-            uint32_t r[32];
-            tmem_ld32(taddr + (uint32_t)(c0 + cc), r);
-            tmem_ld_wait();
-            if (m < p.M) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (n_base + cc + i < p.N) epi_store1(q, __uint_as_float(r[i]), n_base + cc + i, m);
-            }
-          }
-        }
-      }
+      drain_tile<BN, ADAMW>(q, taddr, m_base, nt, stg, lane, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
