@@ -111,6 +111,40 @@ __device__ __forceinline__ uint32_t dropout_keep4(uint64_t seed, uint32_t site, 
          (r.w >= thresh ? 8u : 0u);
 }
 
+// ---- 8-wide dropout stream (GEMM epilogues, LayerNorm backward, lr2_dropout_bf16) -------------------------------
+// ONE Philox4x32-7 call yields 8 x 16 random bits: element j of the aligned group idx8 is kept iff its 16-bit field
+// >= thresh16 = round(p * 65536).  The drop probability is therefore quantised to thresh16 / 65536 (|error| < 8e-6)
+// and the survivors are scaled by exactly 65536 / (65536 - thresh16), so E[mult] == 1.  7 rounds is the smallest
+// Philox4x32 variant that passes BigCrush (Salmon et al., SC'11); the shorter chain halves the epilogue ALU cost.
+__host__ __device__ __forceinline__ uint32_t dropout_thresh16(float p) {
+  float t = p * 65536.0f + 0.5f;
+  if (t < 0.f) t = 0.f;
+  if (t > 65535.f) t = 65535.f;
+  return (uint32_t)t;
+}
+__host__ __device__ __forceinline__ float dropout_scale16(float p) {
+  return p > 0.f ? 65536.0f / (65536.0f - (float)dropout_thresh16(p)) : 1.0f;
+}
+// m[j] = keep_j ? scale : 0 for the 8 elements [idx8*8, idx8*8 + 8)
+__device__ __forceinline__ void dropout_mult8(uint64_t seed, uint32_t site, uint64_t idx8, uint32_t thresh16,
+                                              float scale, float (&m)[8]) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+  uint32_t c0 = (uint32_t)idx8, c1 = (uint32_t)(idx8 >> 32), c2 = site, c3 = 0x38u;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int i = 0; i < 7; ++i) {
+    const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+    const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  m[0] = (c0 & 0xFFFFu) >= thresh16 ? scale : 0.f;  m[1] = (c0 >> 16) >= thresh16 ? scale : 0.f;
+  m[2] = (c1 & 0xFFFFu) >= thresh16 ? scale : 0.f;  m[3] = (c1 >> 16) >= thresh16 ? scale : 0.f;
+  m[4] = (c2 & 0xFFFFu) >= thresh16 ? scale : 0.f;  m[5] = (c2 >> 16) >= thresh16 ? scale : 0.f;
+  m[6] = (c3 & 0xFFFFu) >= thresh16 ? scale : 0.f;  m[7] = (c3 >> 16) >= thresh16 ? scale : 0.f;
+}
+
 __host__ __device__ __forceinline__ uint32_t dropout_thresh(float p) {
   double t = (double)p * 4294967296.0;
   if (t < 0) t = 0;

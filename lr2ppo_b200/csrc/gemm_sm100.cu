@@ -50,8 +50,8 @@ struct GemmParams {
   long long ldaux;
   float beta;          // fp32 out only: out += beta * C_old
   float drop_p;        // 0 = no dropout
-  unsigned int drop_thresh;  // drop_p * 2^32 (host-computed)
-  float drop_scale;    // 1/(1-p)
+  unsigned int drop_thresh;  // round(drop_p * 2^16) (host-computed, see dropout_mult8)
+  float drop_scale;    // 65536 / (65536 - drop_thresh)
   unsigned long long seed;
   const unsigned long long* seed_dev;  // optional device-resident seed offset (CUDA-graph replay safe)
   unsigned int site;
@@ -59,6 +59,7 @@ struct GemmParams {
   long long ws_slab;   // elements per slab
   int raster;          // 0: tiles strided over CTAs, m fastest; 1: contiguous chunk per CTA, n fastest
   int act;             // activation of the GELU epilogues: 0 = exact erf GELU, 1 = QuickGELU x*sigmoid(1.702x)
+  int mode;            // EpiMode resolved on the host from (epi, act, drop_p, bias)
   // LR2_EPI_ADAMW (fused wgrad + AdamW): C = fp32 parameter (in/out)
   float* adam_m; float* adam_v; bf16* adam_shadow; const float* adam_hyper; float adam_wd;
 };
@@ -150,18 +151,55 @@ __host__ __device__ constexpr uint32_t make_idesc(int n, bool a_mn, bool b_mn) {
 }
 
 // -------------------------------------------------------------- epilogue --
+// Host-resolved epilogue mode (GemmParams::mode): one warp-uniform switch instead of per-element conditionals.
+enum EpiMode {
+  EM_GENERIC = 0, EM_NONE, EM_BETA, EM_BIAS, EM_BIAS_GELU, EM_BIAS_GELU_DROP, EM_BIAS_RES, EM_BIAS_DROP_RES,
+  EM_DGELU, EM_DGELU_DROP, EM_ADD
+};
+
+static int resolve_mode(int epi, int act, float drop_p, const float* bias, int c_f32, float beta) {
+  switch (epi) {
+    case LR2_EPI_NONE: return (c_f32 && beta != 0.f) ? EM_BETA : EM_NONE;
+    case LR2_EPI_BIAS: return bias ? EM_BIAS : EM_GENERIC;
+    case LR2_EPI_BIAS_GELU: return (bias && act == 0) ? (drop_p > 0.f ? EM_BIAS_GELU_DROP : EM_BIAS_GELU) : EM_GENERIC;
+    case LR2_EPI_BIAS_DROP_RES: return bias ? (drop_p > 0.f ? EM_BIAS_DROP_RES : EM_BIAS_RES) : EM_GENERIC;
+    case LR2_EPI_DGELU: return act == 0 ? (drop_p > 0.f ? EM_DGELU_DROP : EM_DGELU) : EM_GENERIC;
+    case LR2_EPI_ADD: return EM_ADD;
+    default: return EM_GENERIC;
+  }
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&x)[8]) {
+  x[0] = __uint_as_float(u.x << 16); x[1] = __uint_as_float(u.x & 0xFFFF0000u);
+  x[2] = __uint_as_float(u.y << 16); x[3] = __uint_as_float(u.y & 0xFFFF0000u);
+  x[4] = __uint_as_float(u.z << 16); x[5] = __uint_as_float(u.z & 0xFFFF0000u);
+  x[6] = __uint_as_float(u.w << 16); x[7] = __uint_as_float(u.w & 0xFFFF0000u);
+}
 // One output row r, 8 consecutive output columns c..c+7 (c % 8 == 0, c + 8 <= ncols).
 // epi_math8 loads bias / aux / old C and transforms v in registers (pre = bf16 pre-activation for C2);
 // epi_write8 issues the stores.  Split so that the caller can interleave two independent groups.
+// Output selection of one tile: the caller's epilogue, or (split-K) a raw fp32 partial into this split's slab.
+// Kept separate from GemmParams so that the kernel parameter block is never copied per tile.
+struct OutSel {
+  void* C; int c_f32; int mode; int epi; float beta;
+};
+
+__device__ __forceinline__ void add_bias8(const GemmParams& p, float (&v)[8], int c) {
+  const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+  const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
+  v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+  v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+}
+
 template <bool ADAMW>
-__device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], uint4& pre, long long r, int c) {
+__device__ __forceinline__ void epi_math8(const GemmParams& p, const OutSel& o, float (&v)[8], uint4& pre, long long r, int c) {
   const long long off = r * p.ldc + c;
-  if (!ADAMW && p.epi == LR2_EPI_NONE) {
-    if (p.c_f32 && p.beta != 0.f) {
-      const float4* o = reinterpret_cast<const float4*>((const float*)p.C + off);
-      float4 a = o[0], b = o[1];
-      v[0] += p.beta * a.x; v[1] += p.beta * a.y; v[2] += p.beta * a.z; v[3] += p.beta * a.w;
-      v[4] += p.beta * b.x; v[5] += p.beta * b.y; v[6] += p.beta * b.z; v[7] += p.beta * b.w;
+  if (!ADAMW && o.epi == LR2_EPI_NONE) {
+    if (o.c_f32 && o.beta != 0.f) {
+      const float4* cp = reinterpret_cast<const float4*>((const float*)o.C + off);
+      float4 a = cp[0], b = cp[1];
+      v[0] += o.beta * a.x; v[1] += o.beta * a.y; v[2] += o.beta * a.z; v[3] += o.beta * a.w;
+      v[4] += o.beta * b.x; v[5] += o.beta * b.y; v[6] += o.beta * b.z; v[7] += o.beta * b.w;
     }
     return;
   }
@@ -169,7 +207,7 @@ __device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], ui
     // ref: tencentpretrain/utils/optimizers.py:374-402; acc = this tile of the weight gradient
     const float lr = p.adam_hyper[0], b1 = p.adam_hyper[1], b2 = p.adam_hyper[2], eps = p.adam_hyper[3],
                 omb1 = p.adam_hyper[4], omb2 = p.adam_hyper[5], gs = p.adam_hyper[6], lrd = p.adam_hyper[7];
-    float* P = (float*)p.C + off; float* Mm = p.adam_m + off; float* Vv = p.adam_v + off;
+    float* P = (float*)o.C + off; float* Mm = p.adam_m + off; float* Vv = p.adam_v + off;
     const float4 p0 = *reinterpret_cast<const float4*>(P), p1 = *reinterpret_cast<const float4*>(P + 4);
     const float4 m0 = *reinterpret_cast<const float4*>(Mm), m1 = *reinterpret_cast<const float4*>(Mm + 4);
     const float4 v0 = *reinterpret_cast<const float4*>(Vv), v1 = *reinterpret_cast<const float4*>(Vv + 4);
@@ -198,98 +236,253 @@ __device__ __forceinline__ void epi_math8(const GemmParams& p, float (&v)[8], ui
     }
     return;  // epi_write8 stores v (the new parameter) as fp32 into C
   } else {
-  if (p.bias != nullptr && (p.epi == LR2_EPI_BIAS || p.epi == LR2_EPI_BIAS_GELU || p.epi == LR2_EPI_BIAS_DROP_RES)) {
-    const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
-    const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
-    v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-    v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+  // Warp-uniform switch on the host-resolved mode; every hot case is straight-line code over the 8 elements.
+  switch (o.mode) {
+    case EM_BIAS: {
+      add_bias8(p, v, c);
+      return;
+    }
+    case EM_BIAS_GELU:
+    case EM_BIAS_GELU_DROP: {
+      add_bias8(p, v, c);
+      // GELU is evaluated on the bf16-rounded pre-activation so that backward (which only has the stored bf16
+      // copy) differentiates the same function.
+      pre.x = pack_bf16x2(v[0], v[1]); pre.y = pack_bf16x2(v[2], v[3]);
+      pre.z = pack_bf16x2(v[4], v[5]); pre.w = pack_bf16x2(v[6], v[7]);
+      float x[8];
+      unpack8(pre, x);
+      if (o.mode == EM_BIAS_GELU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = gelu_fast(x[i]);
+      } else {
+        float m[8];
+        dropout_mult8(p.seed + (p.seed_dev ? *p.seed_dev : 0ull), p.site, (uint64_t)off >> 3, p.drop_thresh,
+                      p.drop_scale, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = gelu_fast(x[i]) * m[i];
+      }
+      return;
+    }
+    case EM_BIAS_RES:
+    case EM_BIAS_DROP_RES: {
+      add_bias8(p, v, c);
+      float a[8];
+      unpack8(*reinterpret_cast<const uint4*>(p.aux + r * p.ldaux + c), a);
+      if (o.mode == EM_BIAS_RES) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] += a[i];
+      } else {
+        float m[8];
+        dropout_mult8(p.seed + (p.seed_dev ? *p.seed_dev : 0ull), p.site, (uint64_t)off >> 3, p.drop_thresh,
+                      p.drop_scale, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], m[i], a[i]);
+      }
+      return;
+    }
+    case EM_DGELU:
+    case EM_DGELU_DROP: {
+      float a[8];
+      unpack8(*reinterpret_cast<const uint4*>(p.aux + r * p.ldaux + c), a);
+      if (o.mode == EM_DGELU) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= gelu_fast_grad(a[i]);
+      } else {
+        float m[8];
+        dropout_mult8(p.seed + (p.seed_dev ? *p.seed_dev : 0ull), p.site, (uint64_t)off >> 3, p.drop_thresh,
+                      p.drop_scale, m);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] *= gelu_fast_grad(a[i]) * m[i];
+      }
+      return;
+    }
+    case EM_ADD: {
+      float a[8];
+      unpack8(*reinterpret_cast<const uint4*>(p.aux + r * p.ldaux + c), a);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += a[i];
+      return;
+    }
+    default:
+      break;
   }
+  // Generic path (QuickGELU variants): same semantics, runtime-selected activation.
+  if (p.bias != nullptr && (o.epi == LR2_EPI_BIAS || o.epi == LR2_EPI_BIAS_GELU || o.epi == LR2_EPI_BIAS_DROP_RES))
+    add_bias8(p, v, c);
   float a[8];
-  if (p.epi == LR2_EPI_BIAS_DROP_RES || p.epi == LR2_EPI_DGELU || p.epi == LR2_EPI_ADD) {
-    const uint4 u = *reinterpret_cast<const uint4*>(p.aux + r * p.ldaux + c);
-    float2 t;
-    t = unpack_bf16x2(u.x); a[0] = t.x; a[1] = t.y;
-    t = unpack_bf16x2(u.y); a[2] = t.x; a[3] = t.y;
-    t = unpack_bf16x2(u.z); a[4] = t.x; a[5] = t.y;
-    t = unpack_bf16x2(u.w); a[6] = t.x; a[7] = t.y;
-  }
-  uint32_t keep = 0xFFu;
-  float dscale = 1.f;
-  if (p.drop_p > 0.f) {
-    const uint32_t th = p.drop_thresh;
-    const uint64_t lin = (uint64_t)off;  // ldc-strided linear index; multiple of 8
-    const unsigned long long sd = p.seed + (p.seed_dev ? *p.seed_dev : 0ull);
-    keep = dropout_keep4(sd, p.site, lin >> 2, th) | (dropout_keep4(sd, p.site, (lin >> 2) + 1, th) << 4);
-    dscale = p.drop_scale;
-  }
-  if (p.epi == LR2_EPI_BIAS_GELU) {
+  if (o.epi == LR2_EPI_BIAS_DROP_RES || o.epi == LR2_EPI_DGELU || o.epi == LR2_EPI_ADD)
+    unpack8(*reinterpret_cast<const uint4*>(p.aux + r * p.ldaux + c), a);
+  float m[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+  if (p.drop_p > 0.f)
+    dropout_mult8(p.seed + (p.seed_dev ? *p.seed_dev : 0ull), p.site, (uint64_t)off >> 3, p.drop_thresh, p.drop_scale, m);
+  if (o.epi == LR2_EPI_BIAS_GELU) {
     pre.x = pack_bf16x2(v[0], v[1]); pre.y = pack_bf16x2(v[2], v[3]);
     pre.z = pack_bf16x2(v[4], v[5]); pre.w = pack_bf16x2(v[6], v[7]);
-    // GELU is evaluated on the bf16-rounded pre-activation so that backward (which only has the
-    // stored bf16 copy) differentiates the same function.
-    float2 t;
     float x[8];
-    t = unpack_bf16x2(pre.x); x[0] = t.x; x[1] = t.y;
-    t = unpack_bf16x2(pre.y); x[2] = t.x; x[3] = t.y;
-    t = unpack_bf16x2(pre.z); x[4] = t.x; x[5] = t.y;
-    t = unpack_bf16x2(pre.w); x[6] = t.x; x[7] = t.y;
+    unpack8(pre, x);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? act_fwd(p.act, x[i]) * dscale : 0.f;
-  } else if (p.epi == LR2_EPI_BIAS_DROP_RES) {
+    for (int i = 0; i < 8; ++i) v[i] = act_fwd(p.act, x[i]) * m[i];
+  } else if (o.epi == LR2_EPI_BIAS_DROP_RES) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = (((keep >> i) & 1u) ? v[i] * dscale : 0.f) + a[i];
-  } else if (p.epi == LR2_EPI_DGELU) {
+    for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], m[i], a[i]);
+  } else if (o.epi == LR2_EPI_DGELU) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = ((keep >> i) & 1u) ? v[i] * act_grad(p.act, a[i]) * dscale : 0.f;
-  } else if (p.epi == LR2_EPI_ADD) {
+    for (int i = 0; i < 8; ++i) v[i] *= act_grad(p.act, a[i]) * m[i];
+  } else if (o.epi == LR2_EPI_ADD) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] += a[i];
   }
   }
 }
-__device__ __forceinline__ void epi_write8(const GemmParams& p, const float (&v)[8], const uint4& pre, long long r,
-                                           int c) {
+__device__ __forceinline__ void epi_write8(const GemmParams& p, const OutSel& o, const float (&v)[8], const uint4& pre,
+                                           long long r, int c) {
   const long long off = r * p.ldc + c;
-  if (p.epi == LR2_EPI_BIAS_GELU && p.C2 != nullptr) *reinterpret_cast<uint4*>(p.C2 + off) = pre;
-  if (p.c_f32) {
-    float4* o = reinterpret_cast<float4*>((float*)p.C + off);
-    o[0] = make_float4(v[0], v[1], v[2], v[3]);
-    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+  if (o.epi == LR2_EPI_BIAS_GELU && p.C2 != nullptr) *reinterpret_cast<uint4*>(p.C2 + off) = pre;
+  if (o.c_f32) {
+    float4* cp = reinterpret_cast<float4*>((float*)o.C + off);
+    cp[0] = make_float4(v[0], v[1], v[2], v[3]);
+    cp[1] = make_float4(v[4], v[5], v[6], v[7]);
   } else {
     uint4 u;
     u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
     u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
-    *reinterpret_cast<uint4*>((bf16*)p.C + off) = u;
+    *reinterpret_cast<uint4*>((bf16*)o.C + off) = u;
   }
 }
-__device__ __forceinline__ void epi_store8(const GemmParams& p, float (&v)[8], long long r, int c) {
+__device__ __forceinline__ void epi_store8(const GemmParams& p, const OutSel& o, float (&v)[8], long long r, int c) {
   uint4 pre = make_uint4(0, 0, 0, 0);
-  epi_math8<false>(p, v, pre, r, c);
-  epi_write8(p, v, pre, r, c);
+  epi_math8<false>(p, o, v, pre, r, c);
+  epi_write8(p, o, v, pre, r, c);
 }
 
 // Scalar epilogue (transposed tiles and ragged edges). No dropout on this path.
-__device__ __forceinline__ void epi_store1(const GemmParams& p, float v, long long r, int c) {
+__device__ __forceinline__ void epi_store1(const GemmParams& p, const OutSel& o, float v, long long r, int c) {
   const long long off = r * p.ldc + c;
-  if (p.epi == LR2_EPI_NONE) {
-    if (p.c_f32 && p.beta != 0.f) v += p.beta * ((const float*)p.C)[off];
+  if (o.epi == LR2_EPI_NONE) {
+    if (o.c_f32 && o.beta != 0.f) v += o.beta * ((const float*)o.C)[off];
   } else {
-    if (p.bias != nullptr && (p.epi == LR2_EPI_BIAS || p.epi == LR2_EPI_BIAS_GELU || p.epi == LR2_EPI_BIAS_DROP_RES))
+    if (p.bias != nullptr && (o.epi == LR2_EPI_BIAS || o.epi == LR2_EPI_BIAS_GELU || o.epi == LR2_EPI_BIAS_DROP_RES))
       v += __ldg(p.bias + c);
     float a = 0.f;
-    if (p.epi == LR2_EPI_BIAS_DROP_RES || p.epi == LR2_EPI_DGELU || p.epi == LR2_EPI_ADD)
+    if (o.epi == LR2_EPI_BIAS_DROP_RES || o.epi == LR2_EPI_DGELU || o.epi == LR2_EPI_ADD)
       a = __bfloat162float(p.aux[r * p.ldaux + c]);
-    if (p.epi == LR2_EPI_BIAS_GELU) {
+    if (o.epi == LR2_EPI_BIAS_GELU) {
       if (p.C2 != nullptr) p.C2[off] = __float2bfloat16(v);
       v = act_fwd(p.act, __bfloat162float(__float2bfloat16(v)));
-    } else if (p.epi == LR2_EPI_BIAS_DROP_RES || p.epi == LR2_EPI_ADD) {
+    } else if (o.epi == LR2_EPI_BIAS_DROP_RES || o.epi == LR2_EPI_ADD) {
       v += a;
-    } else if (p.epi == LR2_EPI_DGELU) {
+    } else if (o.epi == LR2_EPI_DGELU) {
       v *= act_grad(p.act, a);
     }
   }
-  if (p.c_f32) ((float*)p.C)[off] = v;
-  else ((bf16*)p.C)[off] = __float2bfloat16(v);
+  if (o.c_f32) ((float*)o.C)[off] = v;
+  else ((bf16*)o.C)[off] = __float2bfloat16(v);
+}
+
+// Fast path of the accumulator drain: one whole 32-row x 32-column chunk, staged in `stg` (row per lane), is pushed
+// through the host-resolved epilogue MODE with every warp-uniform decision taken outside the row loop: bias (a
+// per-column quantity) is loaded once per chunk, addresses advance by a constant stride, and the four row groups are
+// fully unrolled so that their aux / C loads and Philox chains overlap.
+template <int MODE, bool F32>
+__device__ __forceinline__ void chunk_rows(const GemmParams& q, const OutSel& o, const float* __restrict__ stg, int lane,
+                                           int m_base, int n_base) {
+  constexpr int RPI = 8;                                   // rows per iteration (4 lanes x 8 columns per row)
+  const int cg = (lane & 3) * 8;
+  const int r0 = lane >> 2;
+  const int n = n_base + cg;
+  constexpr bool HAS_BIAS = MODE == EM_BIAS || MODE == EM_BIAS_GELU || MODE == EM_BIAS_GELU_DROP ||
+                            MODE == EM_BIAS_RES || MODE == EM_BIAS_DROP_RES;
+  constexpr bool HAS_AUX = MODE == EM_BIAS_RES || MODE == EM_BIAS_DROP_RES || MODE == EM_DGELU ||
+                           MODE == EM_DGELU_DROP || MODE == EM_ADD;
+  constexpr bool HAS_DROP = MODE == EM_BIAS_GELU_DROP || MODE == EM_BIAS_DROP_RES || MODE == EM_DGELU_DROP;
+  float bias[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if constexpr (HAS_BIAS) {
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(q.bias + n));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(q.bias + n + 4));
+    bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+    bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+  }
+  unsigned long long seed = 0;
+  if constexpr (HAS_DROP) seed = q.seed + (q.seed_dev ? *q.seed_dev : 0ull);
+  const long long off0 = (long long)(m_base + r0) * q.ldc + n;
+  const long long step = (long long)RPI * q.ldc;
+  const bf16* aux = nullptr;
+  long long astep = 0;
+  if constexpr (HAS_AUX) { aux = q.aux + (long long)(m_base + r0) * q.ldaux + n; astep = (long long)RPI * q.ldaux; }
+  const bool want_pre = (MODE == EM_BIAS_GELU || MODE == EM_BIAS_GELU_DROP) && q.C2 != nullptr;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const long long off = off0 + it * step;
+    const float4* sp = reinterpret_cast<const float4*>(stg + (it * RPI + r0) * STG_PITCH + cg);
+    const float4 x0 = sp[0], x1 = sp[1];
+    float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    float a[8];
+    if constexpr (HAS_AUX) unpack8(*reinterpret_cast<const uint4*>(aux + it * astep), a);
+    float m[8];
+    if constexpr (HAS_DROP) dropout_mult8(seed, q.site, (uint64_t)off >> 3, q.drop_thresh, q.drop_scale, m);
+    if constexpr (HAS_BIAS) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += bias[i];
+    }
+    if constexpr (MODE == EM_BETA) {
+      const float4* cp = reinterpret_cast<const float4*>((const float*)o.C + off);
+      const float4 c0 = cp[0], c1 = cp[1];
+      v[0] = fmaf(o.beta, c0.x, v[0]); v[1] = fmaf(o.beta, c0.y, v[1]); v[2] = fmaf(o.beta, c0.z, v[2]);
+      v[3] = fmaf(o.beta, c0.w, v[3]); v[4] = fmaf(o.beta, c1.x, v[4]); v[5] = fmaf(o.beta, c1.y, v[5]);
+      v[6] = fmaf(o.beta, c1.z, v[6]); v[7] = fmaf(o.beta, c1.w, v[7]);
+    } else if constexpr (MODE == EM_BIAS_GELU || MODE == EM_BIAS_GELU_DROP) {
+      // GELU of the bf16-rounded pre-activation: backward only has the stored bf16 copy
+      uint4 pre;
+      pre.x = pack_bf16x2(v[0], v[1]); pre.y = pack_bf16x2(v[2], v[3]);
+      pre.z = pack_bf16x2(v[4], v[5]); pre.w = pack_bf16x2(v[6], v[7]);
+      if (want_pre) *reinterpret_cast<uint4*>(q.C2 + off) = pre;
+      float x[8];
+      unpack8(pre, x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = HAS_DROP ? gelu_fast(x[i]) * m[i] : gelu_fast(x[i]);
+    } else if constexpr (MODE == EM_BIAS_RES || MODE == EM_ADD) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] += a[i];
+    } else if constexpr (MODE == EM_BIAS_DROP_RES) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = fmaf(v[i], m[i], a[i]);
+    } else if constexpr (MODE == EM_DGELU || MODE == EM_DGELU_DROP) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= HAS_DROP ? gelu_fast_grad(a[i]) * m[i] : gelu_fast_grad(a[i]);
+    }
+    if constexpr (F32) {
+      float4* cp = reinterpret_cast<float4*>((float*)o.C + off);
+      cp[0] = make_float4(v[0], v[1], v[2], v[3]);
+      cp[1] = make_float4(v[4], v[5], v[6], v[7]);
+    } else {
+      uint4 u;
+      u.x = pack_bf16x2(v[0], v[1]); u.y = pack_bf16x2(v[2], v[3]);
+      u.z = pack_bf16x2(v[4], v[5]); u.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>((bf16*)o.C + off) = u;
+    }
+  }
+}
+
+// Returns false when (mode, output type) has no fast instantiation; the caller then takes the checked generic loop.
+__device__ __forceinline__ bool chunk_fast(const GemmParams& q, const OutSel& o, const float* stg, int lane, int m_base,
+                                           int n_base) {
+  if (o.c_f32) {
+    if (o.mode == EM_NONE) { chunk_rows<EM_NONE, true>(q, o, stg, lane, m_base, n_base); return true; }
+    if (o.mode == EM_BETA) { chunk_rows<EM_BETA, true>(q, o, stg, lane, m_base, n_base); return true; }
+    return false;
+  }
+  switch (o.mode) {
+    case EM_NONE: chunk_rows<EM_NONE, false>(q, o, stg, lane, m_base, n_base); return true;
+    case EM_BIAS: chunk_rows<EM_BIAS, false>(q, o, stg, lane, m_base, n_base); return true;
+    case EM_BIAS_GELU: chunk_rows<EM_BIAS_GELU, false>(q, o, stg, lane, m_base, n_base); return true;
+    case EM_BIAS_GELU_DROP: chunk_rows<EM_BIAS_GELU_DROP, false>(q, o, stg, lane, m_base, n_base); return true;
+    case EM_BIAS_RES: chunk_rows<EM_BIAS_RES, false>(q, o, stg, lane, m_base, n_base); return true;
+    case EM_BIAS_DROP_RES: chunk_rows<EM_BIAS_DROP_RES, false>(q, o, stg, lane, m_base, n_base); return true;
+    case EM_DGELU: chunk_rows<EM_DGELU, false>(q, o, stg, lane, m_base, n_base); return true;
+    case EM_DGELU_DROP: chunk_rows<EM_DGELU_DROP, false>(q, o, stg, lane, m_base, n_base); return true;
+    case EM_ADD: chunk_rows<EM_ADD, false>(q, o, stg, lane, m_base, n_base); return true;
+    default: return false;
+  }
 }
 
 // ---------------------------------------------------------------- kernel --
@@ -304,113 +497,139 @@ struct SmemLayout {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024;  // +1024 for manual alignment
 };
 
+// Checked generic path of the drain (ragged tile edges, fp32 outputs with fused math, QuickGELU, fused AdamW): one
+// staged 32 x 32 chunk through epi_math8 / epi_store1 with per-group bounds checks.  Deliberately NOT inlined for the
+// plain kernels: its many warp-uniform conditions otherwise get hoisted into the hot per-tile path (ncu showed ~150
+// predicate-packing instructions per tile per warp).
+template <bool ADAMW>
+__device__ __forceinline__ void chunk_checked_body(const GemmParams& q, const OutSel& o, const float* stg, int lane,
+                                                   int m_base, int n_base) {
+  constexpr int TPR = 4, RPI = 8;
+  const int cg = (lane % TPR) * 8;
+#pragma unroll 1
+  for (int rr = 0; rr < 32; rr += 2 * RPI) {
+    const int rl0 = rr + lane / TPR, rl1 = rl0 + RPI;
+    const int m0 = m_base + rl0, m1 = m_base + rl1;
+    const int n = n_base + cg;
+    const bool full = (n + 8 <= q.N);
+    if (full && m1 < q.M) {
+      // two independent 8-wide groups in flight (rows rl0 and rl1)
+      const float4* s0 = reinterpret_cast<const float4*>(stg + rl0 * STG_PITCH + cg);
+      const float4* s1 = reinterpret_cast<const float4*>(stg + rl1 * STG_PITCH + cg);
+      const float4 x0 = s0[0], x1 = s0[1], y0 = s1[0], y1 = s1[1];
+      float v0[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+      float v1[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+      uint4 p0 = make_uint4(0, 0, 0, 0), p1 = make_uint4(0, 0, 0, 0);
+      if constexpr (ADAMW) {   // HBM-bound: one group at a time keeps the register budget
+        epi_math8<true>(q, o, v0, p0, m0, n);
+        epi_write8(q, o, v0, p0, m0, n);
+        epi_math8<true>(q, o, v1, p1, m1, n);
+        epi_write8(q, o, v1, p1, m1, n);
+      } else {
+        epi_math8<false>(q, o, v0, p0, m0, n);
+        epi_math8<false>(q, o, v1, p1, m1, n);
+        epi_write8(q, o, v0, p0, m0, n);
+        epi_write8(q, o, v1, p1, m1, n);
+      }
+    } else {
+#pragma unroll 1
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const int row_l = h2 ? rl1 : rl0;
+        const int m = m_base + row_l;
+        if (m < q.M && n < q.N) {
+          const float4* src = reinterpret_cast<const float4*>(stg + row_l * STG_PITCH + cg);
+          const float4 x0 = src[0], x1 = src[1];
+          float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+          if (full) {
+            if constexpr (ADAMW) {
+              uint4 pz = make_uint4(0, 0, 0, 0);
+              epi_math8<true>(q, o, v, pz, m, n);
+              epi_write8(q, o, v, pz, m, n);
+            } else {
+              epi_store8(q, o, v, m, n);
+            }
+          } else {
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i)
+              if (n + i < q.N) epi_store1(q, o, v[i], m, n + i);
+          }
+        }
+      }
+    }
+  }
+}
+__device__ __noinline__ void chunk_checked(const GemmParams& q, const OutSel o, const float* stg, int lane, int m_base,
+                                           int n_base) {
+  chunk_checked_body<false>(q, o, stg, lane, m_base, n_base);
+}
+// transposed tile (skinny GEMMs): lane = output column m, registers = output rows; a warp store writes 32
+// consecutive columns of one output row.
+__device__ __noinline__ void chunk_transposed(const GemmParams& q, const OutSel o, uint32_t taddr_c, int lane, int m_base,
+                                              int n_base) {
+  const int m = m_base + lane;
+  uint32_t r[32];
+  tmem_ld32(taddr_c, r);
+  tmem_ld_wait();
+  if (m < q.M) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (n_base + i < q.N) epi_store1(q, o, __uint_as_float(r[i]), n_base + i, m);
+  }
+}
+
 // Drain one accumulator tile (this warp's TMEM lane quadrant and column part): TMEM -> registers -> per-warp smem
 // staging -> coalesced 8-wide groups through the fused epilogue.  Shared by the 1-CTA and 2-CTA kernels.
 template <int BN, bool ADAMW>
-__device__ __forceinline__ void drain_tile(const GemmParams& q, uint32_t taddr, int m_base, int nt,
+__device__ __forceinline__ void drain_tile(const GemmParams& q, const OutSel& o, uint32_t taddr, int m_base, int nt,
                                            float* stg, int lane, int half) {
   constexpr int COLS_PER_WARP = (BN / 4 < 32) ? 32 : BN / 4;    // BN=64: only parts 0,1 have columns
   constexpr int CW = 32;                                        // chunk width
-  constexpr int TPR = CW / 8;                                   // lanes per row in the coalesced phase
-  constexpr int RPI = 32 / TPR;                                 // rows per iteration
 #pragma unroll 1
   for (int c0 = half * COLS_PER_WARP; c0 < (half + 1) * COLS_PER_WARP && c0 < BN; c0 += CW) {
     const int n_base = nt * BN + c0;
     if (n_base >= q.N) break;  // warp-uniform
-    if (!q.transposed_out) {
-#pragma unroll
-      for (int cc = 0; cc < CW; cc += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)(c0 + cc), r);
-        tmem_ld_wait();
-        float4* dst = reinterpret_cast<float4*>(stg + lane * STG_PITCH + cc);
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                               __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-      }
-      __syncwarp();
-      const int cg = (lane % TPR) * 8;
-#pragma unroll 1
-      for (int rr = 0; rr < 32; rr += 2 * RPI) {
-        const int rl0 = rr + lane / TPR, rl1 = rl0 + RPI;
-        const int m0 = m_base + rl0, m1 = m_base + rl1;
-        const int n = n_base + cg;
-        const bool full = (n + 8 <= q.N);
-        if (full && m1 < q.M) {
-          // two independent 8-wide groups in flight (rows rl0 and rl1)
-          const float4* s0 = reinterpret_cast<const float4*>(stg + rl0 * STG_PITCH + cg);
-          const float4* s1 = reinterpret_cast<const float4*>(stg + rl1 * STG_PITCH + cg);
-          const float4 x0 = s0[0], x1 = s0[1], y0 = s1[0], y1 = s1[1];
-          float v0[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-          float v1[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
-          uint4 p0 = make_uint4(0, 0, 0, 0), p1 = make_uint4(0, 0, 0, 0);
-          if constexpr (ADAMW) {   // HBM-bound: one group at a time keeps the register budget
-            epi_math8<true>(q, v0, p0, m0, n);
-            epi_write8(q, v0, p0, m0, n);
-            epi_math8<true>(q, v1, p1, m1, n);
-            epi_write8(q, v1, p1, m1, n);
-          } else {
-            epi_math8<false>(q, v0, p0, m0, n);
-            epi_math8<false>(q, v1, p1, m1, n);
-            epi_write8(q, v0, p0, m0, n);
-            epi_write8(q, v1, p1, m1, n);
-          }
-        } else {
-#pragma unroll 1
-          for (int h2 = 0; h2 < 2; ++h2) {
-            const int row_l = h2 ? rl1 : rl0;
-            const int m = m_base + row_l;
-            if (m < q.M && n < q.N) {
-              const float4* src = reinterpret_cast<const float4*>(stg + row_l * STG_PITCH + cg);
-              const float4 x0 = src[0], x1 = src[1];
-              float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-              if (full) {
-                epi_store8(q, v, m, n);
-              } else {
-                for (int i = 0; i < 8; ++i)
-                  if (n + i < q.N) epi_store1(q, v[i], m, n + i);
-              }
-            }
-          }
-        }
-      }
-      __syncwarp();
-    } else {
-      // transposed tile (skinny GEMMs): lane = output column m, registers = output rows; a warp store
-      // writes 32 consecutive columns of one output row.
-      const int m = m_base + lane;
-#pragma unroll 1
-      for (int cc = 0; cc < CW; cc += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + (uint32_t)(c0 + cc), r);
-        tmem_ld_wait();
-        if (m < q.M) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (n_base + cc + i < q.N) epi_store1(q, __uint_as_float(r[i]), n_base + cc + i, m);
-        }
-      }
+    if (q.transposed_out) {
+      chunk_transposed(q, o, taddr + (uint32_t)c0, lane, m_base, n_base);
+      continue;
     }
+    {
+      uint32_t r[32];
+      tmem_ld32(taddr + (uint32_t)c0, r);
+      tmem_ld_wait();
+      float4* dst = reinterpret_cast<float4*>(stg + lane * STG_PITCH);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                             __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+    }
+    __syncwarp();
+    if constexpr (ADAMW) {
+      chunk_checked_body<true>(q, o, stg, lane, m_base, n_base);
+    } else {
+      if (!(m_base + 32 <= q.M && n_base + 32 <= q.N && chunk_fast(q, o, stg, lane, m_base, n_base)))
+        chunk_checked(q, o, stg, lane, m_base, n_base);
+    }
+    __syncwarp();
   }
 }
 
 template <int BN, bool A_MN, bool B_MN, bool ADAMW>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-            const GemmParams p) {
+            const __grid_constant__ GemmParams p) {
   using L = SmemLayout<BN>;
   constexpr int STAGES = L::STAGES;
-  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64 ? 64 : (2 * BN <= 128 ? 128 : (2 * BN <= 256 ? 256 : 512)));
+  constexpr int NBUF = (BN <= 128) ? 4 : 2;          // TMEM accumulator buffers (epilogue of tile i overlaps MMAs of i+1..)
+  constexpr uint32_t TMEM_COLS = (NBUF * BN <= 256) ? 256 : 512;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared space
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
   uint64_t* full_bar = bars;                  // [STAGES]
   uint64_t* empty_bar = bars + STAGES;        // [STAGES]
-  uint64_t* tfull_bar = bars + 2 * STAGES;    // [2]
-  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* tfull_bar = bars + 2 * STAGES;    // [NBUF]
+  uint64_t* tempty_bar = bars + 2 * STAGES + NBUF;  // [NBUF]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NBUF);
   float* stg_all = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
@@ -435,7 +654,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_WARPS); }
+      for (int b = 0; b < NBUF; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], EPI_WARPS); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
@@ -494,8 +713,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
         const int split = w % p.splits;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(num_kb, kb0 + p.kb_per_split);
-        const int buf = it & 1;
-        const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+        const int buf = it & (NBUF - 1);
+        const uint32_t acc_phase = (uint32_t)(it / NBUF) & 1u;
         mbar_wait(&tempty_bar[buf], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
@@ -531,24 +750,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
       const int split = w % p.splits;
       const int t = w / p.splits;
       const int mt = p.raster ? t / n_tiles : t % m_tiles, nt = p.raster ? t % n_tiles : t / m_tiles;
-      const int buf = it & 1;
-      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      const int buf = it & (NBUF - 1);
+      const uint32_t acc_phase = (uint32_t)(it / NBUF) & 1u;
       mbar_wait(&tfull_bar[buf], acc_phase);
       tc_fence_after();
       const int m_base = mt * BM + quad * 32;
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
-      GemmParams q = p;
+      OutSel o{p.C, p.c_f32, p.mode, p.epi, p.beta};
       if (p.splits > 1) {  // raw fp32 partial into this split's slab
-        q.epi = LR2_EPI_NONE; q.c_f32 = 1; q.beta = 0.f; q.drop_p = 0.f;
-        q.C = p.ws + (long long)split * p.ws_slab;
+        o.C = p.ws + (long long)split * p.ws_slab; o.c_f32 = 1; o.mode = EM_NONE; o.epi = LR2_EPI_NONE; o.beta = 0.f;
       }
-      drain_tile<BN, ADAMW>(q, taddr, m_base, nt, stg, lane, half);
+      drain_tile<BN, ADAMW>(p, o, taddr, m_base, nt, stg, lane, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[buf]);
     }
   }
 
+  __syncwarp();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -557,8 +776,249 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ 
   }
 }
 
+// ------------------------------------------------------ 2-CTA pair kernel --
+// cta_group::2 variant for the large GEMMs: a cluster of two CTAs (one TPC) computes a 256 x BN tile with
+// tcgen05.mma.cta_group::2 (UMMA_M = 256).  CTA r of the pair loads rows [r*128, r*128+128) of the A tile and rows
+// [r*BN/2, (r+1)*BN/2) of the B tile into its own shared memory and owns accumulator rows r*128.. in its own TMEM, so
+// each SM receives (128 + BN/2) x 64 operand elements per k-block for 128 x BN outputs: for BN = 256 that is half the
+// L2->SMEM bytes per FLOP of the single-CTA 128x128 tile, which is what bounds that kernel.
+// Protocol (one mbarrier set per CTA at identical smem offsets):
+//   full[s]   leader only : count 1, leader's producer arrives with expect_tx for BOTH CTAs' bytes; the peer's TMA
+//                           signals the leader's barrier (shared::cluster address of rank 0)
+//   empty[s]  both        : count 1, released by the leader's MMA thread with a multicast tcgen05.commit
+//   tfull[b]  both        : count 1, multicast tcgen05.commit after the last k-block of a tile
+//   tempty[b] leader only : count 2*EPI_WARPS, the epilogue warps of both CTAs arrive (remote arrive from the peer)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+__host__ __device__ constexpr uint32_t make_idesc_m(int m, int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+template <int BN>   // BN = N of the pair tile; each CTA stages BN/2 rows of B
+struct SmemLayout2 {
+  static constexpr int HB = BN / 2;
+  static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
+  static constexpr int B_BYTES = HB * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int STG_BYTES = EPI_WARPS * 32 * STG_PITCH * 4;
+  static constexpr int STAGES = (232448 - 1024 - BAR_BYTES - STG_BYTES) / STAGE_BYTES > 8
+                                    ? 8 : (232448 - 1024 - BAR_BYTES - STG_BYTES) / STAGE_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024;
+};
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+             const __grid_constant__ GemmParams p) {
+  using L = SmemLayout2<BN>;
+  constexpr int STAGES = L::STAGES;
+  constexpr int HB = L::HB;
+  constexpr int NBUF = (BN <= 128) ? 4 : 2;
+  constexpr uint32_t TMEM_COLS = (NBUF * BN <= 256) ? 256 : 512;
+  static_assert(NBUF * BN <= 512, "accumulator buffers must fit TMEM");
+
+  extern __shared__ uint8_t smem_raw[];
+  // identical offsets in both CTAs: the dynamic smem base is the same for every CTA of a launch
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared space
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;
+  uint64_t* tempty_bar = bars + 2 * STAGES + NBUF;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NBUF);
+  float* stg_all = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = (rank == 0);
+
+  const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM);
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int total_work = m_tiles * n_tiles * p.splits;
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+  int w_begin, w_end, w_step;
+  if (p.raster == 0) { w_begin = pair; w_end = total_work; w_step = num_pairs; }
+  else {
+    const int per = (total_work + num_pairs - 1) / num_pairs;
+    w_begin = pair * per; w_end = min(total_work, w_begin + per); w_step = 1;
+  }
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int b = 0; b < NBUF; ++b) { mbar_init(&tfull_bar[b], 1); mbar_init(&tempty_bar[b], 2 * EPI_WARPS); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();      // barrier inits and the TMEM allocation of both CTAs are visible pair-wide
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ======================= TMA producer (both CTAs) =======================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = w_begin; w < w_end; w += w_step) {
+        const int split = w % p.splits;
+        const int t = w / p.splits;
+        const int mt = p.raster ? t / n_tiles : t % m_tiles, nt = p.raster ? t % n_tiles : t / m_tiles;
+        const int m0 = mt * 2 * BM + (int)rank * BM;
+        const int n0 = nt * BN + (int)rank * HB;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + p.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);
+          const uint32_t lbar = mapa_rank(smem_u32(&full_bar[stage]), 0);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          if (A_MN) {
+#pragma unroll
+            for (int j = 0; j < BM / 64; ++j)
+              tma_load_2d_pair(sa + j * (64 * BK * 2), &tmap_a, lbar, m0 + j * 64, kb * BK);
+          } else {
+            tma_load_2d_pair(sa, &tmap_a, lbar, kb * BK, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < HB / 64; ++j)
+              tma_load_2d_pair(sb + j * (64 * BK * 2), &tmap_b, lbar, n0 + j * 64, kb * BK);
+          } else {
+            tma_load_2d_pair(sb, &tmap_b, lbar, kb * BK, n0);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+      // tail: do not leave while the leader's multicast commits can still arrive on this CTA's empty barriers
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ======================= MMA issuer (leader CTA only) ===================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_m(2 * BM, BN, A_MN, B_MN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int w = w_begin; w < w_end; w += w_step, ++it) {
+        const int split = w % p.splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(num_kb, kb0 + p.kb_per_split);
+        const int buf = it & (NBUF - 1);
+        const uint32_t acc_phase = (uint32_t)(it / NBUF) & 1u;
+        mbar_wait(&tempty_bar[buf], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t ad = A_MN ? make_sdesc(sa + k * 2048, 64 * BK * 2, 1024) : make_sdesc(sa + k * 32, 16, 1024);
+            const uint64_t bd = B_MN ? make_sdesc(sb + k * 2048, 64 * BK * 2, 1024) : make_sdesc(sb + k * 32, 16, 1024);
+            umma_bf16_pair(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit_pair(&empty_bar[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_pair(&tfull_bar[buf]);
+      }
+    }
+  } else {
+    // ======================= epilogue warps (both CTAs) =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* stg = stg_all + (size_t)(warp - 2) * 32 * STG_PITCH;
+    int it = 0;
+    for (int w = w_begin; w < w_end; w += w_step, ++it) {
+      const int split = w % p.splits;
+      const int t = w / p.splits;
+      const int mt = p.raster ? t / n_tiles : t % m_tiles, nt = p.raster ? t % n_tiles : t / m_tiles;
+      const int buf = it & (NBUF - 1);
+      const uint32_t acc_phase = (uint32_t)(it / NBUF) & 1u;
+      mbar_wait(&tfull_bar[buf], acc_phase);
+      tc_fence_after();
+      const int m_base = mt * 2 * BM + (int)rank * BM + quad * 32;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * BN);
+      OutSel o{p.C, p.c_f32, p.mode, p.epi, p.beta};
+      if (p.splits > 1) {
+        o.C = p.ws + (long long)split * p.ws_slab; o.c_f32 = 1; o.mode = EM_NONE; o.epi = LR2_EPI_NONE; o.beta = 0.f;
+      }
+      drain_tile<BN, false>(p, o, taddr, m_base, nt, stg, lane, half);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[buf]), 0));
+    }
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  cluster_sync_all();      // neither CTA may exit (or free TMEM) while its pair still reads its smem / TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
 // Fold split-K slabs and apply the epilogue. One thread per 8 output columns.
-__global__ void splitk_reduce_kernel(GemmParams p, long long out_rows, int out_cols) {
+__global__ void splitk_reduce_kernel(const __grid_constant__ GemmParams p, long long out_rows, int out_cols) {
+  const OutSel o{p.C, p.c_f32, p.mode, p.epi, p.beta};
   const int cols8 = out_cols / 8;
   const long long total = out_rows * cols8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -572,7 +1032,7 @@ __global__ void splitk_reduce_kernel(GemmParams p, long long out_rows, int out_c
       v[0] += a.x; v[1] += a.y; v[2] += a.z; v[3] += a.w;
       v[4] += b.x; v[5] += b.y; v[6] += b.z; v[7] += b.w;
     }
-    epi_store8(p, v, r, c);
+    epi_store8(p, o, v, r, c);
   }
 }
 
@@ -657,6 +1117,41 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
   LR2_RETURN_LAUNCH();
 }
 
+// 2-CTA pair kernel: persistent over min(#tiles, resident clusters) CTA pairs.
+template <int BN, bool A_MN, bool B_MN>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using L = SmemLayout2<BN>;
+  static int max_pairs = 0;
+  if (max_pairs == 0) {
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    if (e != cudaSuccess) return LR2_ERR_CUDA;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(num_sms() & ~1); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = L::TOTAL;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    e = cudaOccupancyMaxActiveClusters(&n, gemm2_kernel<BN, A_MN, B_MN>, &cfg);
+    if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / 2; }
+    max_pairs = n < num_sms() / 2 ? n : num_sms() / 2;
+  }
+  const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = (p.N + BN - 1) / BN;
+  const int total = m_tiles * n_tiles * p.splits;
+  const int pairs = total < max_pairs ? total : max_pairs;
+  gemm2_kernel<BN, A_MN, B_MN><<<2 * pairs, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, p); LR2_LAUNCHED(1);
+  LR2_RETURN_LAUNCH();
+}
+
+template <int BN>
+static int launch2_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
+                         cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch2<BN, false, false>(ta, tb, p, s);
+  if (!a_mn && b_mn) return launch2<BN, false, true>(ta, tb, p, s);
+  if (a_mn && !b_mn) return launch2<BN, true, false>(ta, tb, p, s);
+  return launch2<BN, true, true>(ta, tb, p, s);
+}
+
 template <int BN>
 static int launch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                         cudaStream_t s) {
@@ -704,7 +1199,24 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     if ((ldc % 8) || (out_cols % 8)) return LR2_ERR_MISALIGNED;
   }
   int BN = block_n;
-  if (BN == 0) BN = (N <= 64) ? 64 : (N <= 128 ? 128 : ((N > 128 && N <= 256 && transposed_out) ? 256 : 128));
+  bool pair = false;          // block_n = 2000 + BN selects the cta_group::2 pair kernel (256 x BN tiles)
+  if (BN == 0) {
+    static int auto_pair = -1;
+    if (auto_pair < 0) { const char* e = getenv("LR2_GEMM_PAIR"); auto_pair = e ? atoi(e) : 1; }
+    // untransposed problems whose 256 x 256 pair tiles keep at least half of the 74 CTA pairs busy run on the
+    // cta_group::2 kernel (half the L2->SMEM bytes per FLOP); everything else on the single-CTA kernel.  Callers that
+    // want split-K to fill the pairs pick `splits` with the same rule (lr2ppo_b200/ops.py: plan_gemm).
+    const long long t256 = (long long)((M + 255) / 256) * ((N + 255) / 256) * splits;
+    if (auto_pair && !transposed_out && N % 256 == 0 && M >= 256 && K > 128 && t256 >= 37) {
+      pair = true;
+      BN = 256;
+    } else {
+      BN = (N <= 64) ? 64 : (N <= 128 ? 128 : ((N > 128 && N <= 256 && transposed_out) ? 256 : 128));
+    }
+  } else if (BN >= 2000) {
+    pair = true; BN -= 2000;
+    if (BN != 128 && BN != 256) return LR2_ERR_UNSUPPORTED;
+  }
   if (BN != 64 && BN != 128 && BN != 256) return LR2_ERR_UNSUPPORTED;
 
   CUtensorMap ta, tb;
@@ -712,7 +1224,7 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   // K-major operand [rows,K]: dims {K, rows}, box {64, tile_rows}; MN-major [K,rows]: dims {rows, K}, box {64, 64}.
   rc = a_mn_major ? get_tmap(A, M, K, lda, 64, BK, &ta) : get_tmap(A, K, M, lda, BK, BM, &ta);
   if (rc != LR2_OK) return rc;
-  rc = b_mn_major ? get_tmap(B, N, K, ldb, 64, BK, &tb) : get_tmap(B, K, N, ldb, BK, BN, &tb);
+  rc = b_mn_major ? get_tmap(B, N, K, ldb, 64, BK, &tb) : get_tmap(B, K, N, ldb, BK, pair ? BN / 2 : BN, &tb);
   if (rc != LR2_OK) return rc;
 
   GemmParams p;
@@ -724,13 +1236,16 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   p.bias = bias; p.aux = reinterpret_cast<const bf16*>(aux); p.ldaux = ldaux;
   p.beta = beta; p.drop_p = drop_p; p.seed = seed; p.site = site;
   p.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
-  p.drop_thresh = dropout_thresh(drop_p); p.drop_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  p.drop_thresh = dropout_thresh16(drop_p); p.drop_scale = dropout_scale16(drop_p);
+  p.mode = resolve_mode(epilogue, act, drop_p, bias, c_is_f32, beta);
   p.ws = reinterpret_cast<float*>(workspace);
   { static int r = -1; if (r < 0) { const char* e = getenv("LR2_GEMM_RASTER"); r = e ? atoi(e) : 0; } p.raster = r; }
   const long long out_rows = transposed_out ? N : M;
   p.ws_slab = out_rows * ldc;
 
-  if (BN == 64) rc = launch_major<64>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
+  if (pair && BN == 256) rc = launch2_major<256>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
+  else if (pair) rc = launch2_major<128>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
+  else if (BN == 64) rc = launch_major<64>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
   else if (BN == 128) rc = launch_major<128>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
   else rc = launch_major<256>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
   if (rc != LR2_OK) return rc;

@@ -401,16 +401,15 @@ __global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ ou
                                uint32_t thresh, unsigned long long seed_in, unsigned int site,
                                const unsigned long long* __restrict__ seed_dev) {
   const unsigned long long seed = seed_in + (seed_dev ? *seed_dev : 0ull);
-  const float sc = 1.f / (1.f - p);
+  const float sc = dropout_scale16(p);
   const long long n8 = n / 8;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
        i += (long long)gridDim.x * blockDim.x) {
-    float v[8];
+    float v[8], mult[8];
     ld8f(x + i * 8, v);
-    const uint32_t keep = dropout_keep4(seed, site, (unsigned long long)i * 2, thresh) |
-                          (dropout_keep4(seed, site, (unsigned long long)i * 2 + 1, thresh) << 4);
+    dropout_mult8(seed, site, (unsigned long long)i, thresh, sc, mult);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = ((keep >> k) & 1u) ? v[k] * sc : 0.f;
+    for (int k = 0; k < 8; ++k) v[k] *= mult[k];
     st8f(out + i * 8, v);
   }
 }
@@ -444,7 +443,7 @@ extern "C" int lr2_dropout_bf16(const void* x, void* out, long long n, float p, 
                                 unsigned int site, const void* seed_dev, void* stream) {
   if (n <= 0 || n % 8 || p < 0.f || p >= 1.f) return LR2_ERR_BAD_SHAPE;
   lr2::dropout_kernel<<<lr2::grid_for(n / 8, 256), 256, 0, S_(stream)>>>(
-      reinterpret_cast<const lr2::bf16*>(x), reinterpret_cast<lr2::bf16*>(out), n, p, lr2::dropout_thresh(p), seed, site,
+      reinterpret_cast<const lr2::bf16*>(x), reinterpret_cast<lr2::bf16*>(out), n, p, lr2::dropout_thresh16(p), seed, site,
       reinterpret_cast<const unsigned long long*>(seed_dev));
   LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();

@@ -107,8 +107,8 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
   for (int ch = 0; ch < LN_MAX_CHUNKS; ++ch)
 #pragma unroll
     for (int i = 0; i < 8; ++i) { dg[ch][i] = 0.f; db[ch][i] = 0.f; }
-  const uint32_t th = dropout_thresh(drop_p);
-  const float dscale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const uint32_t th = dropout_thresh16(drop_p);
+  const float dscale = dropout_scale16(drop_p);
 
   for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
     const bf16* xr = x + row * D;
@@ -159,16 +159,12 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
         }
         store8(dx + row * D + c, o);
         if (dxm != nullptr) {
-          uint32_t keep = 0xFFu;
-          if (drop_p > 0.f) {
-            const uint64_t lin = (uint64_t)(row * D + c);
-            keep = dropout_keep4(seed, site, lin >> 2, th) | (dropout_keep4(seed, site, (lin >> 2) + 1, th) << 4);
-          }
+          float mult[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+          if (drop_p > 0.f) dropout_mult8(seed, site, (uint64_t)(row * D + c) >> 3, th, dscale, mult);
           // mask the bf16-rounded dx so dxm == mask * dx exactly
           float m[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            m[i] = ((keep >> i) & 1u) ? __bfloat162float(__float2bfloat16(o[i])) * dscale : 0.f;
+          for (int i = 0; i < 8; ++i) m[i] = __bfloat162float(__float2bfloat16(o[i])) * mult[i];
           store8(dxm + row * D + c, m);
         }
       }

@@ -102,10 +102,11 @@ def _wgrad(sink, lin, dy, x, bias_from=None):
     gw, beta = sink.buf(lin.weight)
     m_out, k_in = lin.weight.shape
     rows = dy.shape[0]
-    # few output tiles and a long reduction -> split-K to fill the SMs
+    # few output tiles and a long reduction -> split-K to fill the SMs (CTA pairs when the pair kernel applies)
+    splits = ops.plan_gemm(m_out, k_in, rows) if beta == 0.0 else 1
     tiles = ((m_out + 127) // 128) * ((k_in + 127) // 128)
-    splits = 1
-    if beta == 0.0 and tiles < 120 and rows >= 1024:
+    if splits == 1 and beta == 0.0 and tiles < 120 and rows >= 1024 and \
+            not (k_in % 256 == 0 and m_out >= 256 and ((m_out + 255) // 256) * (k_in // 256) >= 37):
         splits = max(1, min(16, 148 // tiles, rows // 512))
     ops.gemm(dy, x, a_mn=True, b_mn=True, out=gw, beta=beta, splits=splits)
     sink.put_vec(lin.bias, ops.colsum(dy if bias_from is None else bias_from))
@@ -397,7 +398,8 @@ class FusionEngine:
             # data-parallel runs the two small wgrad operands are all-gathered (global-batch gradient, no all-reduce)
             dy_, x_ = (self.dp_gather(dy1p), self.dp_gather(ctx["cat"])) if self.dp_gather is not None \
                 else (dy1p, ctx["cat"])
-            ops.gemm(dy_, x_, a_mn=True, b_mn=True, out=self.fc1_grad_bf16)
+            # K = items (<= 256): epilogue-bound -> single-CTA 128-wide tiles with four TMEM accumulator buffers
+            ops.gemm(dy_, x_, a_mn=True, b_mn=True, out=self.fc1_grad_bf16, block_n=128)
             sink.put_vec(W["o1"].mod.bias, ops.colsum(dy1p))
         elif self.dp_gather is not None:
             # data parallel: gather the two (small) wgrad operands instead of all-reducing the 2 GB gradient

@@ -47,6 +47,19 @@ def _workspace(nbytes, device):
 
 
 # ------------------------------------------------------------------ GEMM --
+def plan_gemm(M, N, K, transposed_out=False):
+    """Split-K factor for an untransposed [M,N] problem, matching the kernel selection in lr2_gemm_bf16: problems whose
+    256 x 256 pair tiles would leave most of the 74 CTA pairs idle (weight gradients: few output tiles, long K) are
+    split along K until the pairs are filled; otherwise 1."""
+    if transposed_out or N % 256 or M < 256 or K <= 128:
+        return 1
+    t = ((M + 255) // 256) * (N // 256)
+    if t >= 74:
+        return 1
+    s = max(1, min(74 // t, ((K + 63) // 64) // 8, 16))
+    return s if t * s >= 37 else 1
+
+
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=bf16, transposed_out=False, epilogue=EPI_NONE,
          bias=None, aux=None, c2=None, beta=0.0, drop_p=0.0, seed=0, site=0, seed_dev=None, splits=1, block_n=0,
          M=None, N=None, K=None):

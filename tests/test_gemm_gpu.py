@@ -121,3 +121,84 @@ def test_gemm_dropout_consistent_and_unbiased():
     frac = 1.0 - kept.float().mean().item()
     assert abs(frac - p) < 0.01, frac
     assert _rel(o1.float()[kept], (ref / (1 - p))[kept]) < 1e-2
+
+
+# ---- cta_group::2 pair kernel (block_n = 2000 + BN: a two-CTA cluster computes 256 x BN tiles) ----
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K,bn", [(256, 256, 64, 2256), (256, 128, 64, 2128), (512, 512, 512, 2256),
+                                       (1000, 768, 768, 2256), (1000, 768, 768, 2128), (304, 384, 192, 2256),
+                                       (200, 136, 72, 2128), (4736, 1280, 320, 2256)])
+def test_gemm_pair_majors(M, N, K, bn, a_mn, b_mn):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N * 3 + K + bn)
+    a = _mk(M, K, a_mn, g)
+    b = _mk(N, K, b_mn, g)
+    out = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out_dtype=torch.float32, block_n=bn)
+    ref = _ref(a, b, a_mn, b_mn)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 2e-3, f"rel err {_rel(out, ref)}"
+
+
+@pytest.mark.parametrize("bn", [2128, 2256, 0])
+def test_gemm_pair_persistent_many_tiles_and_epilogues(bn):
+    g = torch.Generator(device="cuda").manual_seed(11)
+    a = _mk(9408, 768, False, g)
+    w = (_mk(3072, 768, False, g).float() * 0.05).to(torch.bfloat16)
+    bias = torch.randn(3072, generator=g, device="cuda") * 0.1
+    pre = torch.empty((9408, 3072), dtype=torch.bfloat16, device="cuda")
+    out = ops.gemm(a, w, epilogue=ops.EPI_BIAS_GELU, bias=bias, c2=pre, block_n=bn)
+    ref_pre = a.float() @ w.float().t() + bias
+    assert _rel(pre, ref_pre) < 1e-2
+    assert _rel(out, torch.nn.functional.gelu(ref_pre)) < 1e-2
+    # K = 3072 -> N = 768 with bias + residual, then the MN-major dgrad and the MN/MN wgrad of the same layer
+    w2 = (_mk(768, 3072, False, g).float() * 0.05).to(torch.bfloat16)
+    b2 = torch.randn(768, generator=g, device="cuda") * 0.1
+    res = _mk(9408, 768, False, g)
+    y = ops.gemm(out, w2, epilogue=ops.EPI_BIAS_DROP_RES, bias=b2, aux=res, block_n=bn)
+    assert _rel(y, out.float() @ w2.float().t() + b2 + res.float()) < 1e-2
+    dy = _mk(9408, 768, False, g)
+    dh = ops.gemm(dy, w2, b_mn=True, block_n=bn)
+    assert _rel(dh, dy.float() @ w2.float()) < 1e-2
+    gw = ops.gemm(dy, out, a_mn=True, b_mn=True, out_dtype=torch.float32, block_n=bn)
+    assert _rel(gw, dy.float().t() @ out.float()) < 2e-3
+
+
+@pytest.mark.parametrize("bn", [2128, 2256])
+def test_gemm_pair_splitk_and_beta(bn):
+    g = torch.Generator(device="cuda").manual_seed(12)
+    M, N, K = 768, 512, 4096
+    a = _mk(M, K, True, g)
+    b = _mk(N, K, True, g)
+    ref = a.float().t() @ b.float()
+    out = ops.gemm(a, b, a_mn=True, b_mn=True, out_dtype=torch.float32, splits=4, block_n=bn)
+    assert _rel(out, ref) < 2e-3
+    c0 = torch.randn(M, N, generator=g, device="cuda")
+    acc = c0.clone()
+    ops.gemm(a, b, a_mn=True, b_mn=True, out=acc, beta=1.0, block_n=bn)
+    assert _rel(acc, ref + c0) < 2e-3
+
+
+@pytest.mark.parametrize("bn", [128, 2256])
+def test_gemm_dropout_mask_shared_by_forward_and_backward_epilogues(bn):
+    """GELU+dropout (forward) and dGELU+dropout (dgrad) at the same (seed, site) drop the same elements, the mask does
+    not depend on the tile shape, and the survivors are scaled by 1/(1-p)."""
+    g = torch.Generator(device="cuda").manual_seed(13)
+    M, N, K, p = 2304, 1024, 256, 0.1
+    a = _mk(M, K, False, g)
+    w = _mk(N, K, False, g)
+    bias = torch.randn(N, generator=g, device="cuda")
+    pre = torch.empty((M, N), dtype=torch.bfloat16, device="cuda")
+    h = ops.gemm(a, w, epilogue=ops.EPI_BIAS_GELU, bias=bias, c2=pre, drop_p=p, seed=77, site=5, block_n=bn)
+    h0 = ops.gemm(a, w, epilogue=ops.EPI_BIAS_GELU, bias=bias, block_n=bn)
+    dy = _mk(M, K, False, g)
+    dh = ops.gemm(dy, w, epilogue=ops.EPI_DGELU, aux=pre, drop_p=p, seed=77, site=5, block_n=bn)
+    dh0 = ops.gemm(dy, w, epilogue=ops.EPI_DGELU, aux=pre, block_n=bn)
+    live = (h0 != 0) & (dh0 != 0)
+    keep_f = (h != 0)[live]
+    keep_b = (dh != 0)[live]
+    assert torch.equal(keep_f, keep_b)
+    frac = 1.0 - keep_f.float().mean().item()
+    assert abs(frac - p) < 0.005, frac
+    assert _rel(h.float()[live & (h != 0)], (h0.float() / (1 - p))[live & (h != 0)]) < 1e-2
+    # same mask from the single-CTA 128-wide kernel
+    h_ref = ops.gemm(a, w, epilogue=ops.EPI_BIAS_GELU, bias=bias, drop_p=p, seed=77, site=5, block_n=128)
+    assert torch.equal((h_ref != 0)[live], keep_f)

@@ -32,6 +32,7 @@ def main():
     wq = rnd(E, E); dy = rnd(Mt, E); dh = rnd(Mt, H)
     W = rnd(H, K1); cat = rnd(items, K1); dy1 = rnd(items, H); bh = torch.randn(H, device=dev)
     gW = torch.empty(H, K1, dtype=torch.float32, device=dev)
+    gWb = torch.empty(H, K1, dtype=bf, device=dev)
     gw1 = torch.empty(H, E, dtype=torch.float32, device=dev)
     y1 = torch.empty(items, H, dtype=bf, device=dev); dcat = torch.empty(items, K1, dtype=bf, device=dev)
     out1 = torch.empty(Mt, H, dtype=bf, device=dev); out2 = torch.empty(Mt, E, dtype=bf, device=dev)
@@ -63,19 +64,29 @@ def main():
         ("fc1 wgrad 3072x162816 K=48 f32", 2 * items * H * K1, H * K1 * 4 + items * K1 * 2,
          lambda: ops.gemm(dy1, cat, a_mn=True, b_mn=True, out=gW)),
     ]
-    bn = int(os.environ.get("BENCH_BN", "0"))
-    if bn:
+    for bn in [int(v) for v in os.environ.get("BENCH_BNS", "").split(",") if v]:
         cases += [
+            (f"fwd 9408x3072x768 plain BN={bn}", 2 * Mt * H * E, (Mt * E + H * E + Mt * H) * 2,
+             lambda bn=bn: ops.gemm(x, w1, out=out1, block_n=bn)),
             (f"fwd 9408x3072x768 gelu+pre BN={bn}", 2 * Mt * H * E, (Mt * E + H * E + 2 * Mt * H) * 2,
-             lambda: ops.gemm(x, w1, out=out1, epilogue=ops.EPI_BIAS_GELU, bias=b1, c2=pre, block_n=bn)),
+             lambda bn=bn: ops.gemm(x, w1, out=out1, epilogue=ops.EPI_BIAS_GELU, bias=b1, c2=pre, block_n=bn)),
+            (f"fwd 9408x3072x768 gelu+drop BN={bn}", 2 * Mt * H * E, (Mt * E + H * E + 2 * Mt * H) * 2,
+             lambda bn=bn: ops.gemm(x, w1, out=out1, epilogue=ops.EPI_BIAS_GELU, bias=b1, c2=pre, drop_p=0.1, seed=1,
+                                    site=2, block_n=bn)),
             (f"fwd 9408x768x3072 bias BN={bn}", 2 * Mt * H * E, (Mt * H + H * E + Mt * E) * 2,
-             lambda: ops.gemm(h, w2, out=out2, epilogue=ops.EPI_BIAS, bias=b2, block_n=bn)),
+             lambda bn=bn: ops.gemm(h, w2, out=out2, epilogue=ops.EPI_BIAS, bias=b2, block_n=bn)),
+            (f"fwd 9408x768x768 bias BN={bn}", 2 * Mt * E * E, (2 * Mt * E + E * E) * 2,
+             lambda bn=bn: ops.gemm(x, wq, out=out2, epilogue=ops.EPI_BIAS, bias=b2, block_n=bn)),
             (f"dgrad 9408x768x3072 (b_mn) BN={bn}", 2 * Mt * H * E, (Mt * H + H * E + Mt * E) * 2,
-             lambda: ops.gemm(dh, w1, b_mn=True, out=out2, block_n=bn)),
+             lambda bn=bn: ops.gemm(dh, w1, b_mn=True, out=out2, block_n=bn)),
+            (f"dgrad 9408x3072x768 dgelu (b_mn) BN={bn}", 2 * Mt * H * E, (Mt * E + H * E + 2 * Mt * H) * 2,
+             lambda bn=bn: ops.gemm(dy, w2, b_mn=True, out=out1, epilogue=ops.EPI_DGELU, aux=pre, block_n=bn)),
             (f"wgrad 3072x768 K=9408 f32 BN={bn}", 2 * Mt * H * E, (Mt * H + Mt * E) * 2 + H * E * 4,
-             lambda: ops.gemm(dh, x, a_mn=True, b_mn=True, out=gw1, block_n=bn)),
-            (f"fc1 wgrad 3072x162816 K=48 f32 BN={bn}", 2 * items * H * K1, H * K1 * 4 + items * K1 * 2,
-             lambda: ops.gemm(dy1, cat, a_mn=True, b_mn=True, out=gW, block_n=bn)),
+             lambda bn=bn: ops.gemm(dh, x, a_mn=True, b_mn=True, out=gw1, block_n=bn)),
+            (f"wgrad 3072x768 K=9408 f32 s2 BN={bn}", 2 * Mt * H * E, (Mt * H + Mt * E) * 2 + H * E * 4,
+             lambda bn=bn: ops.gemm(dh, x, a_mn=True, b_mn=True, out=gw1, block_n=bn, splits=2)),
+            (f"fc1 wgrad 3072x162816 K=48 bf16 BN={bn}", 2 * items * H * K1, H * K1 * 2 + items * K1 * 2,
+             lambda bn=bn: ops.gemm(dy1, cat, a_mn=True, b_mn=True, out=gWb, block_n=bn)),
         ]
     only = sys.argv[1] if len(sys.argv) > 1 else None
     for name, flops, byts, fn in cases:
