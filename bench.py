@@ -245,7 +245,6 @@ def main():
         pool.append((text, img, tgts))
     resident = [tuple(t.to(dev) for t in b) for b in pool]
     h2d_bytes = sum(t.numel() * t.element_size() for t in pool[0])
-    stats_host = torch.empty(10, dtype=torch.float32).pin_memory()
 
     def eager_step(batch):
         text, img, tgts = batch
@@ -310,16 +309,32 @@ def main():
     value = world * BS * args.steps / (ms / 1e3)
 
     # ---- (2) end-to-end: pinned host -> device every step, stats read back every step ---------------------
+    # lr2ppo_b200.feed: the H2D copy of batch i+1 runs on a copy stream while step i computes (double-buffered
+    # device slots, event-ordered), and the 10 statistics of every step are read back through pinned memory with a
+    # one-step lag -- what a training loop that logs every step does without stalling the GPU.
+    from lr2ppo_b200.feed import DeviceFeeder, StatsReader
+    feeder = DeviceFeeder(pool[0], dev)
+    reader = StatsReader(10)
+    dev_in = gstep.static_inputs() if use_graph else tuple(torch.empty_like(t) for t in resident[0])
+    feeder.stage(pool[0])
+    logged = []
+
     def e2e_step(i):
-        text, img, tgts = pool[i % len(pool)]
-        b = None if use_graph else (text.to(dev, non_blocking=True), img.to(dev, non_blocking=True),
-                                    tgts.to(dev, non_blocking=True))
-        stats = step(pool[i % len(pool)]) if use_graph else step(b)   # graph: H2D straight into its static buffers
-        stats_host.copy_(stats, non_blocking=False)                # D2H + host sync, as a training loop would log
+        feeder.next_into(dev_in)                         # waits (on the stream) for this batch's H2D copy
+        feeder.stage(pool[(i + 1) % len(pool)])          # prefetch the next batch during this step
+        if use_graph:
+            sch.step(); csch.step()
+            stats = gstep.replay()
+        else:
+            stats = step(dev_in)
+        prev = reader.push(stats)                        # async D2H; returns the previous step's statistics
+        if prev is not None:
+            logged.append(float(prev[0]))
 
     for i in range(2):
         e2e_step(i)
     ms_e2e, _ = timed(e2e_step, args.steps)
+    reader.flush()
     e2e = world * BS * args.steps / (ms_e2e / 1e3)
 
     # ---- (3) per-kernel CUDA-event pass for the roofline of the dominant kernel ----------------------------

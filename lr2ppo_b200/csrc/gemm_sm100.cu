@@ -31,7 +31,10 @@ namespace lr2 {
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int EPI_WARPS = 16;                      // four per TMEM lane quadrant
+#ifndef LR2_EPI_WARPS
+#define LR2_EPI_WARPS 16
+#endif
+constexpr int EPI_WARPS = LR2_EPI_WARPS;          // a multiple of 4: EPI_WARPS / 4 column parts per TMEM lane quadrant
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;   // warp0 TMA, warp1 MMA, warps2-17 epilogue
 constexpr int STG_PITCH = 36;                      // floats per staged row (32 + 4 pad)
 
@@ -60,6 +63,7 @@ struct GemmParams {
   int raster;          // 0: tiles strided over CTAs, m fastest; 1: contiguous chunk per CTA, n fastest
   int act;             // activation of the GELU epilogues: 0 = exact erf GELU, 1 = QuickGELU x*sigmoid(1.702x)
   int mode;            // EpiMode resolved on the host from (epi, act, drop_p, bias)
+  int dbg;             // LR2_GEMM_DBG (profiling experiments only): 1 = skip the accumulator drain, 2 = skip the MMAs
   // LR2_EPI_ADAMW (fused wgrad + AdamW): C = fp32 parameter (in/out)
   float* adam_m; float* adam_v; bf16* adam_shadow; const float* adam_hyper; float adam_wd;
 };
@@ -582,7 +586,8 @@ __device__ __noinline__ void chunk_transposed(const GemmParams& q, const OutSel 
 template <int BN, bool ADAMW>
 __device__ __forceinline__ void drain_tile(const GemmParams& q, const OutSel& o, uint32_t taddr, int m_base, int nt,
                                            float* stg, int lane, int half) {
-  constexpr int COLS_PER_WARP = (BN / 4 < 32) ? 32 : BN / 4;    // BN=64: only parts 0,1 have columns
+  constexpr int PARTS = EPI_WARPS / 4;
+  constexpr int COLS_PER_WARP = (BN / PARTS < 32) ? 32 : BN / PARTS;   // BN=64, 16 warps: only parts 0,1 have columns
   constexpr int CW = 32;                                        // chunk width
 #pragma unroll 1
   for (int c0 = half * COLS_PER_WARP; c0 < (half + 1) * COLS_PER_WARP && c0 < BN; c0 += CW) {
@@ -972,7 +977,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t ad = A_MN ? make_sdesc(sa + k * 2048, 64 * BK * 2, 1024) : make_sdesc(sa + k * 32, 16, 1024);
             const uint64_t bd = B_MN ? make_sdesc(sb + k * 2048, 64 * BK * 2, 1024) : make_sdesc(sb + k * 32, 16, 1024);
-            umma_bf16_pair(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (!(p.dbg & 2)) umma_bf16_pair(tmem_d, ad, bd, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit_pair(&empty_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -1000,7 +1005,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       if (p.splits > 1) {
         o.C = p.ws + (long long)split * p.ws_slab; o.c_f32 = 1; o.mode = EM_NONE; o.epi = LR2_EPI_NONE; o.beta = 0.f;
       }
-      drain_tile<BN, false>(p, o, taddr, m_base, nt, stg, lane, half);
+      if (!(p.dbg & 1)) drain_tile<BN, false>(p, o, taddr, m_base, nt, stg, lane, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[buf]), 0));
@@ -1238,6 +1243,7 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   p.seed_dev = reinterpret_cast<const unsigned long long*>(seed_dev);
   p.drop_thresh = dropout_thresh16(drop_p); p.drop_scale = dropout_scale16(drop_p);
   p.mode = resolve_mode(epilogue, act, drop_p, bias, c_is_f32, beta);
+  { static int d = -1; if (d < 0) { const char* e = getenv("LR2_GEMM_DBG"); d = e ? atoi(e) : 0; } p.dbg = d; }
   p.ws = reinterpret_cast<float*>(workspace);
   { static int r = -1; if (r < 0) { const char* e = getenv("LR2_GEMM_RASTER"); r = e ? atoi(e) : 0; } p.raster = r; }
   const long long out_rows = transposed_out ? N : M;

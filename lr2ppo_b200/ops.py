@@ -60,8 +60,19 @@ def plan_gemm(M, N, K, transposed_out=False):
     return s if t * s >= 37 else 1
 
 
+def plan_small_gemm(M, N, K):
+    """Split-K factor for problems with a handful of output tiles and a long reduction (out_layer.fc2 on <= 96 rows,
+    the xitt projections, K/V projections): a few CTAs walking K serially are DRAM-latency bound (25 us for
+    48x768x3072 on 6 CTAs), so K is spread over up to 148 CTAs and folded by lr2_splitk_reduce."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    kb = (K + 63) // 64
+    if tiles > 36 or kb < 16 or N % 8:
+        return 1
+    return max(1, min(16, 148 // tiles, kb // 4))
+
+
 def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=bf16, transposed_out=False, epilogue=EPI_NONE,
-         bias=None, aux=None, c2=None, beta=0.0, drop_p=0.0, seed=0, site=0, seed_dev=None, splits=1, block_n=0,
+         bias=None, aux=None, c2=None, beta=0.0, drop_p=0.0, seed=0, site=0, seed_dev=None, splits=None, block_n=0,
          M=None, N=None, K=None):
     """D[M,N] = A[M,K] @ B[N,K]^T  (bf16 in, fp32 accumulate).
 
@@ -87,6 +98,12 @@ def gemm(a, b, *, a_mn=False, b_mn=False, out=None, out_dtype=bf16, transposed_o
     if out.shape[-2:] != (rows, cols) or out.stride(-1) != 1:
         raise _lib.Lr2Error("gemm: bad output shape")
     ldc = out.stride(-2) if out.dim() >= 2 else cols
+    if splits is None:      # auto: fill the CTA pairs / SMs when the output has few tiles (same rule as the C side)
+        splits = 1
+        if not transposed_out and block_n == 0 and beta == 0.0:
+            splits = plan_gemm(M, N, K)
+            if splits == 1:
+                splits = plan_small_gemm(M, N, K)
     ws = None
     if splits > 1:
         nbytes = L.lr2_gemm_workspace_bytes(M, N, splits, int(transposed_out), ldc)

@@ -224,10 +224,17 @@ class GraphedStage3Step:
         self.model.eval()
         return stats
 
+    def static_inputs(self):
+        """The graph's input buffers (text, img, tgts); fill them (e.g. feed.DeviceFeeder.next_into) then replay()."""
+        return self.text, self.img, self.tgts
+
+    def replay(self):
+        self.opt.update_hyper(); self.copt.update_hyper()
+        self.graph.replay()
+        return self.stats
+
     def __call__(self, text, img, tgts):
         self.text.copy_(text, non_blocking=True)
         self.img.copy_(img, non_blocking=True)
         self.tgts.copy_(tgts, non_blocking=True)
-        self.opt.update_hyper(); self.copt.update_hyper()
-        self.graph.replay()
-        return self.stats
+        return self.replay()
