@@ -8,6 +8,7 @@
 // and D = rowsum(dO*O), phase B (per key row) produces dK and dV.  fp32 math, bf16 I/O.
 // 4*S*S*64 FLOP per head against 4*S*64*2 bytes: compute-bound on CUDA cores for S ~ 200; a tcgen05 version is
 // listed as next work in DESIGN.md.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace lr2 {
@@ -285,6 +286,20 @@ mha_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf1
 
 using namespace lr2;
 
+// tcgen05 kernels (mha_tc.cu); the CUDA-core kernels above remain as the LR2_MHA_LEGACY=1 cross-check
+int lr2_mha_tc_fwd(const void* q, const void* k, const void* v, long long ld, const float* key_bias, void* o,
+                   long long ldo, float* lse, int B, int S, int H, float scale, float drop_p, unsigned long long seed,
+                   const void* seed_dev, cudaStream_t stream);
+int lr2_mha_tc_bwd(const void* q, const void* k, const void* v, long long ld, const float* key_bias, const void* o,
+                   const void* d_o, long long ldo, const float* lse, void* dq, void* dk, void* dv, long long ldd, int B,
+                   int S, int H, float scale, float drop_p, unsigned long long seed, const void* seed_dev,
+                   cudaStream_t stream);
+static bool mha_legacy() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("LR2_MHA_LEGACY"); v = (e && atoi(e)) ? 1 : 0; }
+  return v == 1;
+}
+
 static int mha_check(int B, int S, int H, int dh, long long ld, long long ldo) {
   if (B <= 0 || S <= 0 || H <= 0) return LR2_ERR_BAD_SHAPE;
   if (dh != MHA_DH || S > MHA_MAX_S) return LR2_ERR_UNSUPPORTED;
@@ -297,6 +312,9 @@ extern "C" int lr2_mha_fwd(const void* q, const void* k, const void* v, long lon
                            unsigned long long seed, const void* seed_dev, void* stream) {
   int rc = mha_check(B, S, H, dh, ld, ldo);
   if (rc != LR2_OK) return rc;
+  if (!mha_legacy())
+    return lr2_mha_tc_fwd(q, k, v, ld, key_bias, o, ldo, lse, B, S, H, scale, drop_p, seed, seed_dev,
+                          reinterpret_cast<cudaStream_t>(stream));
   const size_t smem = ((size_t)2 * S * MHA_DH + S) * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
@@ -320,6 +338,9 @@ extern "C" int lr2_mha_bwd(const void* q, const void* k, const void* v, long lon
   int rc = mha_check(B, S, H, dh, ld, ldo);
   if (rc != LR2_OK) return rc;
   if ((ldd % 8) || lse == nullptr) return LR2_ERR_MISALIGNED;
+  if (!mha_legacy())
+    return lr2_mha_tc_bwd(q, k, v, ld, key_bias, o, d_o, ldo, lse, dq, dk, dv, ldd, B, S, H, scale, drop_p, seed,
+                          seed_dev, reinterpret_cast<cudaStream_t>(stream));
   const size_t smem = (size_t)4 * S * MHA_DH * 2 + (size_t)3 * S * sizeof(float);
   static size_t configured = 0;
   if (smem > configured) {
