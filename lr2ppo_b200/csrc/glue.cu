@@ -78,7 +78,18 @@ colsum_partial_kernel(const bf16* __restrict__ x, long long ldx, long long rows,
   const long long r1 = min(rows, r0 + rows_per);
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c < cols) {
-    for (long long r = r0 + warp; r < r1; r += 8) {
+    long long r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {              // four independent 16-byte loads in flight per lane
+      const uint4 u0 = *reinterpret_cast<const uint4*>(x + r * ldx + c);
+      const uint4 u1 = *reinterpret_cast<const uint4*>(x + (r + 8) * ldx + c);
+      const uint4 u2 = *reinterpret_cast<const uint4*>(x + (r + 16) * ldx + c);
+      const uint4 u3 = *reinterpret_cast<const uint4*>(x + (r + 24) * ldx + c);
+      float v0[8], v1[8], v2[8], v3[8];
+      unpack8(u0, v0); unpack8(u1, v1); unpack8(u2, v2); unpack8(u3, v3);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] += (v0[k] + v1[k]) + (v2[k] + v3[k]);
+    }
+    for (; r < r1; r += 8) {
       float v[8];
       ld8f(x + r * ldx + c, v);
 #pragma unroll

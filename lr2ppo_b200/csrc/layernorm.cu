@@ -92,7 +92,12 @@ ln_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ gamma, const
 // dx = rinv * (g - mean(g) - xhat * sum(g*xhat) * kfac), g = dy*gamma
 //   torch:   kfac = 1/D
 //   tencent: kfac = 1/((D-1) * (1 - eps*rinv))      (std = 1/rinv - eps)
-__global__ void __launch_bounds__(LN_WARPS * 32)
+// Register budget: the row is kept as the RAW 16-byte bf16 vectors (x and dy: 2 x NCH uint4) and xhat / g are
+// recomputed from them after the two row reductions, so that with the 2 x NCH x 8 dgamma / dbeta accumulators the
+// kernel stays under 128 registers and two 256-thread blocks (16 rows in flight) fit on an SM; the first version
+// (fp32 xhat / g arrays sized for D = 1024) needed 166 registers -> 8 warps per SM -> 5x above the HBM floor.
+template <int NCH>
+__global__ void __launch_bounds__(LN_WARPS * 32, 2)
 ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ gamma,
               const float* __restrict__ stats, const bf16* __restrict__ add, bf16* __restrict__ dx,
               bf16* __restrict__ dxm, float* __restrict__ partials, long long rows, int D, float eps, int mode,
@@ -102,9 +107,9 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int nch = D / 256 + ((D % 256) ? 1 : 0);
-  float dg[LN_MAX_CHUNKS][8], db[LN_MAX_CHUNKS][8];
+  float dg[NCH][8], db[NCH][8];
 #pragma unroll
-  for (int ch = 0; ch < LN_MAX_CHUNKS; ++ch)
+  for (int ch = 0; ch < NCH; ++ch)
 #pragma unroll
     for (int i = 0; i < 8; ++i) { dg[ch][i] = 0.f; db[ch][i] = 0.f; }
   const uint32_t th = dropout_thresh16(drop_p);
@@ -114,43 +119,61 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
     const bf16* xr = x + row * D;
     const bf16* dyr = dy + regroup(row, g_in, g_out, g_off) * D;
     const float mean = stats[2 * row], rinv = stats[2 * row + 1];
-    float xh[LN_MAX_CHUNKS][8], g[LN_MAX_CHUNKS][8];
+    uint4 xraw[NCH], draw[NCH];
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {           // all loads of the row first
+      const int c = ch * 256 + lane * 8;
+      if (ch < nch && c < D) {
+        xraw[ch] = *reinterpret_cast<const uint4*>(xr + c);
+        draw[ch] = *reinterpret_cast<const uint4*>(dyr + c);
+      } else {
+        xraw[ch] = make_uint4(0, 0, 0, 0); draw[ch] = make_uint4(0, 0, 0, 0);
+      }
+    }
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int ch = 0; ch < LN_MAX_CHUNKS; ++ch) {
+    for (int ch = 0; ch < NCH; ++ch) {
       const int c = ch * 256 + lane * 8;
       if (ch < nch && c < D) {
         float xv[8], dv[8];
-        load8(xr + c, xv);
-        load8(dyr + c, dv);
+        unpack8(xraw[ch], xv);
+        unpack8(draw[ch], dv);
         const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
         const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
         const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          xh[ch][i] = (xv[i] - mean) * rinv;
-          g[ch][i] = dv[i] * gm[i];
-          s1 += g[ch][i];
-          s2 += g[ch][i] * xh[ch][i];
-          dg[ch][i] += dv[i] * xh[ch][i];
+          const float xh = (xv[i] - mean) * rinv;
+          const float g = dv[i] * gm[i];
+          s1 += g;
+          s2 += g * xh;
+          dg[ch][i] += dv[i] * xh;
           db[ch][i] += dv[i];
         }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { xh[ch][i] = 0.f; g[ch][i] = 0.f; }
       }
     }
     s1 = warp_sum(s1);
     s2 = warp_sum(s2);
     const float mg = s1 / (float)D;
     const float kfac = (mode == 0) ? 1.f / (float)D : 1.f / ((float)(D - 1) * (1.f - eps * rinv));
+    const float s2k = s2 * kfac;
 #pragma unroll
-    for (int ch = 0; ch < LN_MAX_CHUNKS; ++ch) {
+    for (int ch = 0; ch < NCH; ++ch) {
       const int c = ch * 256 + lane * 8;
       if (ch < nch && c < D) {
+        float xv[8], dv[8];
+        unpack8(xraw[ch], xv);
+        unpack8(draw[ch], dv);
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
         float o[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = rinv * (g[ch][i] - mg - xh[ch][i] * s2 * kfac);
+        for (int i = 0; i < 8; ++i) {
+          const float xh = (xv[i] - mean) * rinv;          // same expressions as in the first pass
+          const float g = dv[i] * gm[i];
+          o[i] = rinv * (g - mg - xh * s2k);
+        }
         if (add != nullptr) {
           float a[8];
           load8(add + row * D + c, a);
@@ -175,7 +198,7 @@ ln_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const flo
   extern __shared__ float sred[];  // [LN_WARPS][2][D]
   float* mine = sred + (size_t)warp * 2 * D;
 #pragma unroll
-  for (int ch = 0; ch < LN_MAX_CHUNKS; ++ch) {
+  for (int ch = 0; ch < NCH; ++ch) {
     const int c = ch * 256 + lane * 8;
     if (ch < nch && c < D) {
 #pragma unroll
@@ -237,18 +260,28 @@ extern "C" int lr2_layernorm_bwd(const void* dy, const void* x, const float* gam
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const int nb = ln_blocks(rows, LN_BWD_BLOCKS);
   const size_t smem = (size_t)LN_WARPS * 2 * D * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    if (cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LN_WARPS * 2 * 1024 * 4) !=
-        cudaSuccess)
-      return LR2_ERR_CUDA;
-    configured = true;
-  }
-  ln_bwd_kernel<<<nb, LN_WARPS * 32, smem, s>>>(reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x),
-                                                gamma, stats, reinterpret_cast<const bf16*>(add),
-                                                reinterpret_cast<bf16*>(dx), reinterpret_cast<bf16*>(dxm), partials,
-                                                rows, D, eps, mode, g_in, g_out, g_off, drop_p, seed, site,
-                                                reinterpret_cast<const unsigned long long*>(seed_dev)); LR2_LAUNCHED(1);
+  const int nchunks = (D + 255) / 256;
+#define LR2_LN_BWD(NCH_)                                                                                             \
+  do {                                                                                                               \
+    static bool configured = false;                                                                                  \
+    if (!configured) {                                                                                               \
+      if (cudaFuncSetAttribute(ln_bwd_kernel<NCH_>, cudaFuncAttributeMaxDynamicSharedMemorySize,                     \
+                               LN_WARPS * 2 * 1024 * 4) != cudaSuccess)                                             \
+        return LR2_ERR_CUDA;                                                                                         \
+      configured = true;                                                                                             \
+    }                                                                                                                \
+    ln_bwd_kernel<NCH_><<<nb, LN_WARPS * 32, smem, s>>>(                                                            \
+        reinterpret_cast<const bf16*>(dy), reinterpret_cast<const bf16*>(x), gamma, stats,                           \
+        reinterpret_cast<const bf16*>(add), reinterpret_cast<bf16*>(dx), reinterpret_cast<bf16*>(dxm), partials,    \
+        rows, D, eps, mode, g_in, g_out, g_off, drop_p, seed, site,                                                  \
+        reinterpret_cast<const unsigned long long*>(seed_dev));                                                      \
+  } while (0)
+  if (nchunks <= 1) LR2_LN_BWD(1);
+  else if (nchunks == 2) LR2_LN_BWD(2);
+  else if (nchunks == 3) LR2_LN_BWD(3);
+  else LR2_LN_BWD(4);
+#undef LR2_LN_BWD
+  LR2_LAUNCHED(1);
   if (cudaGetLastError() != cudaSuccess) return LR2_ERR_CUDA;
   ln_bwd_reduce_kernel<<<(2 * D + 255) / 256, 256, 0, s>>>(partials, nb, D, dgamma, dbeta); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();

@@ -31,27 +31,35 @@ constexpr uint32_t TCA_SITE = 0x4D48u;
 __device__ __forceinline__ uint32_t sw_off(int r, int c) {          // byte offset of 16-byte chunk c of row r
   return (uint32_t)r * 128u + (uint32_t)((c ^ (r & 7)) << 4);
 }
-// [nrows_total][64] bf16 tile, rows >= nvalid zero-filled; src row pitch ld elements
+// [nrows_total][64] bf16 tile, rows >= nvalid zero-filled; src row pitch ld elements.  16-byte cp.async copies
+// (zero-fill through src-size 0) keep every chunk of the tile in flight at once; the caller waits with
+// cp_async_wait_all() before the proxy fence.
 __device__ __forceinline__ void load_tile(uint8_t* dst, const bf16* src, long long ld, int nvalid, int nrows_total,
                                           int tid, int nthreads) {
+  const uint32_t d0 = smem_u32(dst);
   for (int idx = tid; idx < nrows_total * 8; idx += nthreads) {
     const int r = idx >> 3, c = idx & 7;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (r < nvalid) v = *reinterpret_cast<const uint4*>(src + (long long)r * ld + c * 8);
-    *reinterpret_cast<uint4*>(dst + sw_off(r, c)) = v;
+    const bool ok = r < nvalid;
+    const bf16* g = src + (ok ? (long long)r * ld + c * 8 : 0);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d0 + sw_off(r, c)), "l"(g), "r"(ok ? 16 : 0)
+                 : "memory");
   }
 }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ uint64_t tca_idx8(long long bh, int i, int j) {
   return ((unsigned long long)bh * TCA_MAX_S + (unsigned long long)i) * (TCA_MAX_S / 8) + (unsigned long long)(j >> 3);
 }
 
 // ------------------------------------------------------------------ forward --
 struct FwdSmem {
-  static constexpr int Q = 0, K = 16384, V = K + 32768, P = V + 32768, B = P + 65536, BAR = B + 1024,
-                       TOTAL = BAR + 64 + 1024;
+  static constexpr int Q = 0, K = 16384, V = K + 32768, P = V + 32768, B = P + 65536, RED = B + 1024,
+                       BAR = RED + 2048, TOTAL = BAR + 64 + 1024;
 };
 
-__global__ void __launch_bounds__(128, 1)
+// 256 threads: warp w works on TMEM lane quadrant w & 3 (query rows) and on column part w >> 2 (one half of the keys
+// in the softmax passes, one half of the 64 output dims in the epilogue); the two partial row maxima / row sums meet
+// in shared memory.
+__global__ void __launch_bounds__(256, 1)
 mha_tc_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, long long ld,
                   const float* __restrict__ key_bias, bf16* __restrict__ o, long long ldo, float* __restrict__ lse,
                   int S, int H, float scale, float drop_p, uint32_t thresh16, float dscale,
@@ -63,16 +71,21 @@ mha_tc_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
   uint8_t* Vs = sm + FwdSmem::V;
   uint8_t* Ps = sm + FwdSmem::P;
   float* Bs = reinterpret_cast<float*>(sm + FwdSmem::B);
+  float* redm = reinterpret_cast<float*>(sm + FwdSmem::RED);          // [2][128] partial row maxima
+  float* redl = redm + 256;                                            // [2][128] partial row sums
   uint64_t* bar = reinterpret_cast<uint64_t*>(sm + FwdSmem::BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, part = warp >> 2;
   const long long bh = blockIdx.x;
   const int b = (int)(bh / H), h = (int)(bh % H);
   const unsigned long long seed = seed_in + (seed_dev ? *seed_dev : 0ull);
   const long long row0 = (long long)b * S;
   const int NKp = (S + 15) & ~15;                      // keys padded to the UMMA N / K granularity
   const int nqt = (S + 127) / 128;
+  const int csplit = (((NKp + 31) / 32 + 1) / 2) * 32; // part 0: columns [0, csplit), part 1: [csplit, NKp)
+  const int cbeg = part ? csplit : 0, cend = part ? NKp : min(csplit, NKp);
 
   if (warp == 0) {
     if (lane == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -81,22 +94,24 @@ mha_tc_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
                  "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  load_tile(Ks, k + row0 * ld + h * TCA_DH, ld, S, TCA_MAX_S, tid, 128);
-  load_tile(Vs, v + row0 * ld + h * TCA_DH, ld, S, TCA_MAX_S, tid, 128);
-  for (int j = tid; j < TCA_MAX_S; j += 128) Bs[j] = (key_bias && j < S) ? key_bias[row0 + j] : 0.f;
+  load_tile(Ks, k + row0 * ld + h * TCA_DH, ld, S, NKp, tid, 256);
+  load_tile(Vs, v + row0 * ld + h * TCA_DH, ld, S, NKp, tid, 256);
+  load_tile(Qs, q + row0 * ld + h * TCA_DH, ld, min(128, S), 128, tid, 256);       // first query tile
+  for (int j = tid; j < TCA_MAX_S; j += 256) Bs[j] = (key_bias && j < S) ? key_bias[row0 + j] * 1.4426950408889634f : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);     // this warp's TMEM lane quadrant
+  const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);     // this warp's TMEM lane quadrant
   const uint32_t idesc_s = make_idesc_m(128, NKp, false, false);
   const uint32_t idesc_o = make_idesc_m(128, TCA_DH, false, true);
   uint32_t phase = 0;
   const float sl2 = scale * 1.4426950408889634f;
+  const int r = quad * 32 + lane;                        // row of the tile; TMEM lane = r
 
   for (int t = 0; t < nqt; ++t) {
-    const int nq = min(128, S - t * 128);
-    load_tile(Qs, q + (row0 + t * 128) * ld + h * TCA_DH, ld, nq, 128, tid, 128);
+    if (t > 0) load_tile(Qs, q + (row0 + t * 128) * ld + h * TCA_DH, ld, min(128, S - t * 128), 128, tid, 256);
+    cp_async_wait_all();
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -111,24 +126,26 @@ mha_tc_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
     mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
 
-    const int r = tid;                                   // row of the tile; TMEM lane = r
     const int i = t * 128 + r;                           // query index
-    // pass 1: row maximum of s = acc*scale + bias  (log2 domain)
+    // pass 1: partial row maximum of s = acc*scale + bias (log2 domain) over this part's columns
     float mx = -INFINITY;
-    for (int c0 = 0; c0 < NKp; c0 += 32) {
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
       uint32_t a[32];
       tmem_ld32(trow + (uint32_t)c0, a);
       tmem_ld_wait();
 #pragma unroll
       for (int e = 0; e < 32; ++e) {
         const int j = c0 + e;
-        const float sv = fmaf(__uint_as_float(a[e]), sl2, Bs[j & (TCA_MAX_S - 1)] * 1.4426950408889634f);
+        const float sv = fmaf(__uint_as_float(a[e]), sl2, Bs[j & (TCA_MAX_S - 1)]);
         if (j < S) mx = fmaxf(mx, sv);
       }
     }
-    // pass 2: p = 2^(s - mx), row sum, dropout, bf16 P~ into the swizzled K-major tile (blocks of 64 keys)
+    redm[part * 128 + r] = mx;
+    __syncthreads();
+    mx = fmaxf(redm[r], redm[128 + r]);
+    // pass 2: p = 2^(s - mx), partial row sum, dropout, bf16 P~ into the swizzled K-major tile (blocks of 64 keys)
     float l = 0.f;
-    for (int c0 = 0; c0 < NKp; c0 += 32) {
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
       uint32_t a[32];
       tmem_ld32(trow + (uint32_t)c0, a);
       tmem_ld_wait();
@@ -140,7 +157,7 @@ mha_tc_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
 #pragma unroll
           for (int e = 0; e < 8; ++e) {
             const int j = j0 + e;
-            const float sv = fmaf(__uint_as_float(a[g * 8 + e]), sl2, Bs[j & (TCA_MAX_S - 1)] * 1.4426950408889634f);
+            const float sv = fmaf(__uint_as_float(a[g * 8 + e]), sl2, Bs[j & (TCA_MAX_S - 1)]);
             p[e] = (j < S) ? ex2_approx(sv - mx) : 0.f;
             l += p[e];
           }
@@ -157,6 +174,7 @@ mha_tc_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
         }
       }
     }
+    redl[part * 128 + r] = l;
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
@@ -167,16 +185,16 @@ mha_tc_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
                   make_sdesc(smem_u32(Vs) + ks * 2048, 8192, 1024), idesc_o, ks > 0 ? 1u : 0u);
       umma_commit(bar);
     }
+    l = redl[r] + redl[128 + r];
     mbar_wait(bar, phase); phase ^= 1;
     tc_fence_after();
     const float inv = 1.f / l;
-#pragma unroll
-    for (int c0 = 0; c0 < TCA_DH; c0 += 32) {
+    {
       uint32_t a[32];
-      tmem_ld32(trow + 256u + (uint32_t)c0, a);
+      tmem_ld32(trow + 256u + (uint32_t)part * 32u, a);
       tmem_ld_wait();
       if (i < S) {
-        bf16* orow = o + (row0 + i) * ldo + h * TCA_DH + c0;
+        bf16* orow = o + (row0 + i) * ldo + h * TCA_DH + part * 32;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 u;
@@ -188,7 +206,7 @@ mha_tc_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
         }
       }
     }
-    if (lse != nullptr && i < S) lse[bh * S + i] = (mx + __log2f(l)) * 0.6931471805599453f;   // natural-log lse
+    if (lse != nullptr && part == 0 && i < S) lse[bh * S + i] = (mx + __log2f(l)) * 0.6931471805599453f;   // natural log
     tc_fence_before();      // TMEM reads of this tile are complete before the next tile's MMAs overwrite it
   }
   __syncthreads();
@@ -239,10 +257,10 @@ mha_tc_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
                  "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  load_tile(Qs, q + row0 * ld + h * TCA_DH, ld, S, TCA_MAX_S, tid, 256);
-  load_tile(Ks, k + row0 * ld + h * TCA_DH, ld, S, TCA_MAX_S, tid, 256);
-  load_tile(Vs, v + row0 * ld + h * TCA_DH, ld, S, TCA_MAX_S, tid, 256);
-  load_tile(Gs, d_o + row0 * ldo + h * TCA_DH, ldo, S, TCA_MAX_S, tid, 256);
+  load_tile(Qs, q + row0 * ld + h * TCA_DH, ld, S, nt * 128, tid, 256);
+  load_tile(Ks, k + row0 * ld + h * TCA_DH, ld, S, nt * 128, tid, 256);
+  load_tile(Vs, v + row0 * ld + h * TCA_DH, ld, S, nt * 128, tid, 256);
+  load_tile(Gs, d_o + row0 * ldo + h * TCA_DH, ldo, S, nt * 128, tid, 256);
   {
     // D_i = rowsum(dO_i o O_i); thread = row
     const int i = tid;
@@ -263,6 +281,7 @@ mha_tc_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
     Ls[i] = (i < S) ? lse[bh * S + i] * 1.4426950408889634f : 0.f;      // log2 domain
     Bs[i] = (key_bias && i < S) ? key_bias[row0 + i] * 1.4426950408889634f : 0.f;
   }
+  cp_async_wait_all();
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -425,7 +444,7 @@ int lr2_mha_tc_fwd(const void* q, const void* k, const void* v, long long ld, co
       return LR2_ERR_CUDA;
     configured = true;
   }
-  mha_tc_fwd_kernel<<<B * H, 128, FwdSmem::TOTAL, stream>>>(
+  mha_tc_fwd_kernel<<<B * H, 256, FwdSmem::TOTAL, stream>>>(
       reinterpret_cast<const bf16*>(q), reinterpret_cast<const bf16*>(k), reinterpret_cast<const bf16*>(v), ld, key_bias,
       reinterpret_cast<bf16*>(o), ldo, lse, S, H, scale, drop_p, dropout_thresh16(drop_p), dropout_scale16(drop_p), seed,
       reinterpret_cast<const unsigned long long*>(seed_dev));
