@@ -66,7 +66,7 @@ __global__ void rows_copy_kernel(const bf16* __restrict__ src, long long src_gst
 
 // Column sums: grid (col tiles of 256, row slabs). Thread owns 8 columns... each warp covers 256 columns,
 // the block's warps stride over rows; deterministic two-stage reduction.
-constexpr int CS_SLABS = 64;
+constexpr int CS_SLABS = 128;   // row slabs (grid.y): enough CTAs to keep > 44 KB of loads in flight per SM
 __global__ void __launch_bounds__(256)
 colsum_partial_kernel(const bf16* __restrict__ x, long long ldx, long long rows, int cols,
                       float* __restrict__ partials) {
@@ -112,7 +112,15 @@ __global__ void colsum_final_kernel(const float* __restrict__ partials, int slab
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   float s = accumulate ? out[c] : 0.f;
-  for (int b = 0; b < slabs; ++b) s += partials[(size_t)b * cols + c];
+  int b = 0;
+  for (; b + 8 <= slabs; b += 8) {             // eight independent loads in flight; fixed summation order
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = partials[(size_t)(b + k) * cols + c];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += v[k];
+  }
+  for (; b < slabs; ++b) s += partials[(size_t)b * cols + c];
   out[c] = s;
 }
 
