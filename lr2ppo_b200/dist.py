@@ -40,18 +40,35 @@ class GradSync:
         dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
         return out
 
+    def gather_rows_async(self, t):
+        """Start the all-gather of [rows, D] on NCCL's own stream and return a handle; `handle()` makes the current
+        stream wait and yields the [world*rows, D] tensor.  Used to prefetch the out_layer.fc1 wgrad operand X (the
+        concat buffer, 15.6 MB per rank) during the forward pass, so the exchange overlaps the rest of forward and
+        backward instead of sitting in front of the wgrad GEMM."""
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        work = dist.all_gather_into_tensor(out, t.contiguous(), group=self.group, async_op=True)
+
+        def handle():
+            work.wait()
+            return out
+        return handle
+
     def attach(self, module, optimizer):
         """Enable the activation-gather path for the module's out_layer.fc1 and fold 1/world into AdamW."""
         for e in self._engines(module):
             e.dp_gather = self.gather_rows
+            e.dp_gather_async = self.gather_rows_async
             self._skip.add(id(e.m.out_layer.fc1.weight))
         optimizer.grad_scale = 1.0 / self.world
         optimizer._hyper.clear()
 
-    def __call__(self, module):
+    def start(self, module):
+        """Begin the SUM all-reduce of every gradient except out_layer.fc1 (whose gradient is already global) on
+        NCCL's own stream; returns `finish()`, which waits for it and scatters the bucket back into the .grad
+        tensors.  FusedAdamW.step(first={fc1}, between=finish) updates the 500 M fc1 parameters meanwhile."""
         grads = [p.grad for p in module.parameters() if p.grad is not None and id(p) not in self._skip]
         if not grads:
-            return
+            return lambda: None
         n = sum(g.numel() for g in grads)
         flat = self._flat.get(id(module))
         if flat is None or flat.numel() != n:
@@ -59,5 +76,16 @@ class GradSync:
             self._flat[id(module)] = flat
         views = list(flat.split([g.numel() for g in grads]))
         torch._foreach_copy_(views, [g.view(-1) for g in grads])
-        dist.all_reduce(flat, group=self.group)
-        torch._foreach_copy_([g.view(-1) for g in grads], views)
+        work = dist.all_reduce(flat, group=self.group, async_op=True)
+
+        def finish():
+            work.wait()
+            torch._foreach_copy_([g.view(-1) for g in grads], views)
+        return finish
+
+    def early_params(self, module):
+        """ids of the parameters whose gradients need no all-reduce (out_layer.fc1 of each engine)."""
+        return {i for i in self._skip if any(id(p) == i for p in module.parameters())}
+
+    def __call__(self, module):
+        self.start(module)()

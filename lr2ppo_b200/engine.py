@@ -251,6 +251,7 @@ class FusionEngine:
         self._written = set()
         self.fc1_stash = None      # list of (dY, X) when out_layer.fc1 is updated by the fused wgrad+AdamW kernel
         self.dp_gather = None      # optional callable(t) -> all-gathered rows (data-parallel fused mode)
+        self.dp_gather_async = None  # optional callable(t) -> handle; handle() waits and returns the gathered rows
         self.fc1_grad_bf16 = None  # bf16 [out, in] gradient buffer of out_layer.fc1.weight (see enable_bf16_fc1_grad)
 
     def begin_step(self):
@@ -324,6 +325,9 @@ class FusionEngine:
         _, c_x = xit_forward(W["xit"], tf, imf, items, S, I, train, seed, 0, save, out=cat_rows,
                              regroup=(S, S + I, 0), seed_dev=seed_dev)
         ops.rows_copy(imf, I, 0, cat_rows, S + I, S, items, I, E)
+        cat_all = None
+        if save and self.dp_gather_async is not None and self.fc1_grad_bf16 is not None:
+            cat_all = self.dp_gather_async(cat)      # wgrad operand X of out_layer.fc1, consumed in backward
         # out_layer.fc1: weight is the 128-row MMA operand, items are N; split-K streams the weight once
         o1 = W["o1"]
         hid = o1.w.shape[0]
@@ -351,7 +355,7 @@ class FusionEngine:
                 logits = _small_linear(feat, m.head, self.bank)
             if save:
                 ctx = dict(W=W, dims=(bs, T, S, I, E, items), c_tp=c_tp, c_ip=c_ip, c_x=c_x, cat=cat, pre3=pre3,
-                           y1=y1, feat=feat, imf=imf)
+                           y1=y1, feat=feat, imf=imf, cat_all=cat_all)
             return logits, ctx
         # critic / reward: + pos_emb, self-attention over the T items, head on the LAST token
         ops.add_pos_fwd(feat, m.pos_emb.weight.detach()[:T].contiguous(), bs, T)
@@ -359,7 +363,7 @@ class FusionEngine:
         logits = ops.rowdot_fwd(z, m.head.weight.detach().view(-1), m.head.bias.detach(), bs, T, T - 1)
         if save:
             ctx = dict(W=W, dims=(bs, T, S, I, E, items), c_tp=c_tp, c_ip=c_ip, c_x=c_x, cat=cat, pre3=pre3, y1=y1,
-                       feat=feat, imf=imf, c_t=c_t, z=z)
+                       feat=feat, imf=imf, c_t=c_t, z=z, cat_all=cat_all)
         return logits, ctx
 
     def backward(self, ctx, dlogits):
@@ -396,8 +400,11 @@ class FusionEngine:
         elif self.fc1_grad_bf16 is not None:
             # bf16 gradient side-buffer read directly by FusedAdamW (1 GB written + read instead of 2 GB); in
             # data-parallel runs the two small wgrad operands are all-gathered (global-batch gradient, no all-reduce)
-            dy_, x_ = (self.dp_gather(dy1p), self.dp_gather(ctx["cat"])) if self.dp_gather is not None \
-                else (dy1p, ctx["cat"])
+            if self.dp_gather is not None:
+                dy_ = self.dp_gather(dy1p)
+                x_ = ctx["cat_all"]() if ctx.get("cat_all") is not None else self.dp_gather(ctx["cat"])
+            else:
+                dy_, x_ = dy1p, ctx["cat"]
             # K = items (<= 256): epilogue-bound -> single-CTA 128-wide tiles with four TMEM accumulator buffers
             ops.gemm(dy_, x_, a_mn=True, b_mn=True, out=self.fc1_grad_bf16, block_n=128)
             sink.put_vec(W["o1"].mod.bias, ops.colsum(dy1p))

@@ -99,7 +99,11 @@ class FusedAdamW(Optimizer):
             offs = torch.arange(0, p.numel(), chunk, dtype=torch.int64)
             chunks.append(torch.stack([torch.full_like(offs, t), offs], dim=1))
         chunk_t = torch.cat(chunks, dim=0).contiguous()
-        tab = dict(params=ps, ids=[id(p) for p in ps], gptrs=gptrs, n_chunks=chunk_t.shape[0],
+        starts, acc = {}, 0
+        for t, p in enumerate(ps):          # chunk range of every tensor (two-phase step: see step(first=...))
+            starts[id(p)] = (acc, chunks[t].shape[0])
+            acc += chunks[t].shape[0]
+        tab = dict(params=ps, ids=[id(p) for p in ps], gptrs=gptrs, n_chunks=chunk_t.shape[0], ranges=starts,
                    ptrs=torch.tensor(ptrs, dtype=torch.int64, device=dev),
                    meta=torch.tensor(meta, dtype=torch.int64, device=dev),
                    chunks=chunk_t.to(dev))
@@ -168,12 +172,17 @@ class FusedAdamW(Optimizer):
                 ent["host"] = hv
 
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, first=None, between=None):
+        """first / between (data-parallel overlap): the chunks of the parameters whose ids are in `first` (the
+        out_layer.fc1 weight, whose gradient is already global) are launched before `between()` is called (it waits
+        for the asynchronous all-reduce of the remaining gradients), everything else after it.  Per-element
+        arithmetic and results are identical to a single launch."""
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
         L = _lib.load()
+        prepared = []
         for gi, group in enumerate(self.param_groups):
             live = [p for p in group["params"] if id(p) not in self._fused and self._grad_of(p) is not None]
             fused = [p for p in group["params"] if id(p) in self._fused]
@@ -188,11 +197,39 @@ class FusedAdamW(Optimizer):
             if tab is None and live:
                 tab = self._build(gi, group, live)
                 self._tables[gi] = tab
+            spans = []
             if live:
                 for p in live:
                     self.state[p]["step"] += 1
-                _lib.run(L.lr2_adamw_multi, tab["ptrs"].data_ptr(), tab["meta"].data_ptr(),
-                         tab["chunks"].data_ptr(), tab["n_chunks"], hyper.data_ptr(), _lib.stream())
+                spans = [(0, tab["n_chunks"])]
+            prepared.append((group, live, fused, hyper, tab, spans))
+
+        def launch(tab, hyper, a, n):
+            _lib.run(L.lr2_adamw_multi, tab["ptrs"].data_ptr(), tab["meta"].data_ptr(),
+                     tab["chunks"].data_ptr() + 16 * a, n, hyper.data_ptr(), _lib.stream())
+
+        if first and between is not None:
+            # phase 1: the early tensors of every group; phase 2 (after between()): all remaining chunk spans
+            for k, (group, live, fused, hyper, tab, spans) in enumerate(prepared):
+                if not live:
+                    continue
+                early = sorted(tab["ranges"][i] for i in first if i in tab["ranges"])
+                if not early:
+                    continue
+                rest, pos = [], 0
+                for a, n in early:
+                    launch(tab, hyper, a, n)
+                    if a > pos:
+                        rest.append((pos, a - pos))
+                    pos = a + n
+                if pos < tab["n_chunks"]:
+                    rest.append((pos, tab["n_chunks"] - pos))
+                prepared[k] = (group, live, fused, hyper, tab, rest)
+        if between is not None:
+            between()
+        for group, live, fused, hyper, tab, spans in prepared:
+            for a, n in spans:
+                launch(tab, hyper, a, n)
             for p in fused:
                 pairs = self._fused[id(p)]()
                 if not pairs:

@@ -92,6 +92,21 @@ def rollout(model, reward_model, text_emb_batch, img_emb_batch, tgts_batch, stat
     return [state, next_state, action_scores, rewards, value, text_emb_batch, img_emb_batch, tgts_batch]
 
 
+def _sync_and_step(grad_sync, module, optimizer):
+    """optimizer.step() (finetune/ppo.py:580,587); data-parallel: the all-reduce of the small gradients runs on NCCL's
+    stream while AdamW already updates out_layer.fc1 (97 % of the parameters; its gradient was built from all-gathered
+    operands and needs no reduction)."""
+    if grad_sync is None:
+        optimizer.step()
+        return
+    early = grad_sync.early_params(module)
+    if early and hasattr(optimizer, "register_shadow"):
+        optimizer.step(first=early, between=grad_sync.start(module))
+    else:
+        grad_sync(module)
+        optimizer.step()
+
+
 _STAT_NAMES = ["policy_loss", "value_loss", "kl_penalty", "old_value", "value", "rewards_ori", "rewards",
                "advantages", "rank_loss", "entropy"]
 
@@ -117,14 +132,10 @@ def update_batch(args, model, optimizer, critic_optim, memory, grad_sync=None):
         action_scores, old_action_prob, rewards, old_value, pair, args.kl_div_loss_weight, args.entropy_weight,
         0.01, -0.1)
     loss.backward()
-    if grad_sync is not None:
-        grad_sync(model.actor)
-    optimizer.step()
+    _sync_and_step(grad_sync, model.actor, optimizer)
     value_loss = clipped_value_loss(value, rewards_adj.detach(), old_value, args.value_clip)
     value_loss.backward()
-    if grad_sync is not None:
-        grad_sync(model.critic)
-    critic_optim.step()
+    _sync_and_step(grad_sync, model.critic, critic_optim)
     return torch.stack([loss.detach(), value_loss.detach(), kl.mean(), old_value.mean(), value.detach().mean(),
                         rewards.mean(), rewards_adj.mean(), adv.mean(), rank_loss, ent.mean()])
 

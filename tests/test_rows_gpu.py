@@ -201,3 +201,45 @@ def test_adamw_golden_and_large():
         np.testing.assert_allclose(p.detach().cpu().numpy(), rp.numpy(), rtol=1e-5, atol=1e-8)
         sh = opt.shadow_of(p)
         assert torch.equal(sh, p.detach().to(torch.bfloat16))
+
+
+def test_adamw_two_phase_step_is_bit_identical():
+    """step(first=..., between=...) (data-parallel overlap: the big tensor is updated while the all-reduce of the
+    rest is in flight) must give exactly the bits of a single-launch step, and must call `between` exactly once
+    before any other tensor is touched."""
+    from lr2ppo_b200.optim import FusedAdamW
+    g = torch.Generator().manual_seed(5)
+    shapes = [(768,), (64, 4099), (3072, 768), (5, 7), (9000,)]
+    ps = [torch.randn(s, generator=g) * 0.02 for s in shapes]
+    gs = [torch.randn(s, generator=g) * 0.01 for s in shapes]
+
+    def make():
+        params = [torch.nn.Parameter(p.clone().cuda()) for p in ps]
+        opt = FusedAdamW([{"params": [params[1], params[2], params[3]], "weight_decay": 0.01},
+                          {"params": [params[0], params[4]], "weight_decay": 0.0}], lr=1e-3, correct_bias=False,
+                         shadow_bf16=True)
+        return params, opt
+
+    pa, oa = make()
+    pb, ob = make()
+    calls = []
+    for step in range(3):
+        for p, q, gr in zip(pa, pb, gs):
+            p.grad = (gr * (step + 1)).cuda()
+            q.grad = (gr * (step + 1)).cuda()
+        oa.step()
+        snap = [q.detach().clone() for q in pb]
+
+        def between():
+            torch.cuda.synchronize()
+            calls.append(step)
+            # only the `first` tensor may have changed so far
+            for i, (q, s0) in enumerate(zip(pb, snap)):
+                assert torch.equal(q.detach(), s0) == (i != 2), i
+
+        ob.step(first={id(pb[2])}, between=between)
+    assert calls == [0, 1, 2]
+    for p, q in zip(pa, pb):
+        assert torch.equal(p.detach(), q.detach())
+        assert torch.equal(oa.state_for(p)["exp_avg_sq"], ob.state_for(q)["exp_avg_sq"])
+        assert torch.equal(oa.shadow_of(p), ob.shadow_of(q))
