@@ -203,6 +203,14 @@ static size_t xattn_bwd_smem(int Sq, int dh) {
 
 using namespace lr2;
 
+// tcgen05 kernels (xattn_tc.cu) for the stage shapes (heads of 96, <= 16 keys, 64..256 query rows)
+bool lr2_xattn_tc_applicable(int Sq, int Skv, int dh);
+int lr2_xattn_tc_fwd(const void* q, long long ldq, const void* k, const void* v, long long ldkv, void* o, long long ldo,
+                     int items, int Sq, int Skv, int H, float pre_scale, float post_scale, cudaStream_t stream);
+int lr2_xattn_tc_bwd(const void* q, long long ldq, const void* k, const void* v, long long ldkv, const void* d_o,
+                     long long ldo, void* dq, long long lddq, void* dk, void* dv, long long lddkv, int items, int Sq,
+                     int Skv, int H, float pre_scale, float post_scale, cudaStream_t stream);
+
 static int xattn_check(int items, int Sq, int Skv, int H, int dh, long long ldq, long long ldkv, long long ldo) {
   if (items <= 0 || Sq <= 0 || Skv <= 0 || H <= 0) return LR2_ERR_BAD_SHAPE;
   if (Skv > XA_MAX_KV || dh > XA_MAX_DH || dh % 8) return LR2_ERR_UNSUPPORTED;
@@ -215,6 +223,9 @@ extern "C" int lr2_xattn_fwd(const void* q, long long ldq, const void* k, const 
                              float post_scale, void* stream) {
   int rc = xattn_check(items, Sq, Skv, H, dh, ldq, ldkv, ldo);
   if (rc != LR2_OK) return rc;
+  if (lr2_xattn_tc_applicable(Sq, Skv, dh))
+    return lr2_xattn_tc_fwd(q, ldq, k, v, ldkv, o, ldo, items, Sq, Skv, H, pre_scale, post_scale,
+                            reinterpret_cast<cudaStream_t>(stream));
   int threads = ((Sq + 31) / 32) * 32;
   if (threads > 256) threads = 256;
   xattn_fwd_kernel<<<items * H, threads, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
@@ -230,6 +241,9 @@ extern "C" int lr2_xattn_bwd(const void* q, long long ldq, const void* k, const 
   int rc = xattn_check(items, Sq, Skv, H, dh, ldq, ldkv, ldo);
   if (rc != LR2_OK) return rc;
   if ((lddq % 8) || (lddkv % 8)) return LR2_ERR_MISALIGNED;
+  if (lr2_xattn_tc_applicable(Sq, Skv, dh))
+    return lr2_xattn_tc_bwd(q, ldq, k, v, ldkv, d_o, ldo, dq, lddq, dk, dv, lddkv, items, Sq, Skv, H, pre_scale,
+                            post_scale, reinterpret_cast<cudaStream_t>(stream));
   const size_t smem = xattn_bwd_smem(Sq, dh);
   if (smem > 200 * 1024) return LR2_ERR_UNSUPPORTED;
   static size_t configured = 0;

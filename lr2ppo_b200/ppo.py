@@ -172,11 +172,35 @@ def evaluate(args, val_loader, step, split="test", num_tasks=None):
     and ONE all_gather for the whole pass (the reference gathers once per clip)."""
     args.model.eval()
     scores_l, gold_l = [], []
+    # The reference scores one clip per forward (batch_size 1, finetune/ppo.py:697-698), i.e. it streams the whole
+    # 500 M-parameter out_layer weight once per clip.  Tags of different clips are independent for the actor, so the
+    # (clip, tag) items of consecutive clips are packed into one forward of up to `eval_items` items (SURVEY §8(f) 3).
+    cap = int(getattr(args, "eval_items", 192))
+    pend_t, pend_i, pend_n = [], [], []
+
+    def flush():
+        if not pend_t:
+            return
+        text = torch.cat(pend_t, dim=0)                     # [items, 1, S, E]
+        img = torch.cat(pend_i, dim=0)                      # [items, 1, I, E]
+        sc = evaluate_scores(args.model, text, img)
+        off = 0
+        for n_tags in pend_n:
+            scores_l.append(sc[off:off + n_tags])
+            off += n_tags
+        pend_t.clear(); pend_i.clear(); pend_n.clear()
+
     for text_emb, img_emb, tgts in val_loader:
-        text = text_emb.to(args.device)
-        img = img_emb.unsqueeze(1).repeat(1, text.shape[1], 1, 1).to(args.device)
-        scores_l.append(evaluate_scores(args.model, text, img))
+        n_tags = text_emb.shape[1]
+        if pend_n and sum(pend_n) + n_tags > cap:
+            flush()
+        text = text_emb.to(args.device)                     # [1, tags, S, E]
+        pend_t.append(text.view(n_tags, 1, *text.shape[2:]))
+        pend_i.append(img_emb.to(args.device).unsqueeze(1).expand(1, n_tags, *img_emb.shape[1:])
+                      .reshape(n_tags, 1, *img_emb.shape[1:]))
+        pend_n.append(n_tags)
         gold_l.append(tgts.to(args.device).view(-1))
+    flush()
     meter = AverageNDCGMeter()
     n = len(scores_l)
     nmax = max(s.numel() for s in scores_l)

@@ -79,7 +79,10 @@ def test_layernorm_regroup_and_dropout_mask_matches_gemm():
 
 
 @pytest.mark.parametrize("items,Sq,Skv,H,E", [(5, 196, 16, 8, 768), (24, 2, 2, 8, 768), (24, 4, 4, 8, 768),
-                                               (3, 50, 7, 4, 256)])
+                                               (3, 50, 7, 4, 256),
+                                               # tcgen05 path (heads of 96, <= 16 keys, 64..256 query rows)
+                                               (48, 196, 16, 8, 768), (3, 64, 5, 8, 768), (2, 256, 16, 8, 768),
+                                               (2, 130, 9, 8, 768), (1, 129, 1, 8, 768)])
 def test_xattn_fwd_bwd(items, Sq, Skv, H, E):
     g = torch.Generator(device="cuda").manual_seed(items * Sq)
     q = (torch.randn(items, Sq, E, generator=g, device="cuda") * 0.3).to(bf)
