@@ -37,7 +37,11 @@ constexpr int UMMA_K = 16;
 #endif
 constexpr int EPI_WARPS = LR2_EPI_WARPS;          // a multiple of 4: EPI_WARPS / 4 column parts per TMEM lane quadrant
 constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;   // warp0 TMA, warp1 MMA, warps2-17 epilogue
-constexpr int STG_PITCH = 36;                      // floats per staged row (32 + 4 pad)
+constexpr int STG_PITCH = 32;                      // floats per staged row: dense 128-byte rows, XOR-swizzled chunks
+// Per-warp epilogue staging tile: 32 rows x 32 fp32, 16-byte chunk c of row r stored at chunk (c ^ (r & 7)).  The
+// row-per-lane writes (one row per lane) and the 4-lanes-per-row reads are both bank-conflict free without padding,
+// which frees 9 KB per CTA: the 256 x 256 pair kernel gets a fifth smem stage.
+__device__ __forceinline__ int stg_chunk(int r, int c) { return r * STG_PITCH + ((c ^ (r & 7)) << 2); }
 
 struct GemmParams {
   int M, N, K;
@@ -332,8 +336,9 @@ __device__ __forceinline__ void chunk_rows(const GemmParams& q, const OutSel& o,
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const long long off = off0 + it * step;
-    const float4* sp = reinterpret_cast<const float4*>(stg + (it * RPI + r0) * STG_PITCH + cg);
-    const float4 x0 = sp[0], x1 = sp[1];
+    const int rs = it * RPI + r0;
+    const float4 x0 = *reinterpret_cast<const float4*>(stg + stg_chunk(rs, cg >> 2));
+    const float4 x1 = *reinterpret_cast<const float4*>(stg + stg_chunk(rs, (cg >> 2) + 1));
     float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
     float a[8];
     if constexpr (HAS_AUX) unpack8(*reinterpret_cast<const uint4*>(aux + it * astep), a);
@@ -410,7 +415,7 @@ struct SmemLayout {
   static constexpr int A_BYTES = BM * BK * 2;   // 16 KB
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 4 : 6);
+  static constexpr int STAGES = (BN == 256) ? 3 : (BN == 128 ? 5 : 6);
   static constexpr int BAR_BYTES = 256;
   static constexpr int STG_BYTES = EPI_WARPS * 32 * STG_PITCH * 4;      // epilogue staging (fp32), per warp 32 rows
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024;  // +1024 for manual alignment
@@ -433,9 +438,10 @@ __device__ __forceinline__ void chunk_checked_body(const GemmParams& q, const Ou
     const bool full = (n + 8 <= q.N);
     if (full && m1 < q.M) {
       // two independent 8-wide groups in flight (rows rl0 and rl1)
-      const float4* s0 = reinterpret_cast<const float4*>(stg + rl0 * STG_PITCH + cg);
-      const float4* s1 = reinterpret_cast<const float4*>(stg + rl1 * STG_PITCH + cg);
-      const float4 x0 = s0[0], x1 = s0[1], y0 = s1[0], y1 = s1[1];
+      const float4 x0 = *reinterpret_cast<const float4*>(stg + stg_chunk(rl0, cg >> 2));
+      const float4 x1 = *reinterpret_cast<const float4*>(stg + stg_chunk(rl0, (cg >> 2) + 1));
+      const float4 y0 = *reinterpret_cast<const float4*>(stg + stg_chunk(rl1, cg >> 2));
+      const float4 y1 = *reinterpret_cast<const float4*>(stg + stg_chunk(rl1, (cg >> 2) + 1));
       float v0[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
       float v1[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
       uint4 p0 = make_uint4(0, 0, 0, 0), p1 = make_uint4(0, 0, 0, 0);
@@ -456,8 +462,8 @@ __device__ __forceinline__ void chunk_checked_body(const GemmParams& q, const Ou
         const int row_l = h2 ? rl1 : rl0;
         const int m = m_base + row_l;
         if (m < q.M && n < q.N) {
-          const float4* src = reinterpret_cast<const float4*>(stg + row_l * STG_PITCH + cg);
-          const float4 x0 = src[0], x1 = src[1];
+          const float4 x0 = *reinterpret_cast<const float4*>(stg + stg_chunk(row_l, cg >> 2));
+          const float4 x1 = *reinterpret_cast<const float4*>(stg + stg_chunk(row_l, (cg >> 2) + 1));
           float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
           if (full) {
             if constexpr (ADAMW) {
@@ -516,11 +522,11 @@ __device__ __forceinline__ void drain_tile(const GemmParams& q, const OutSel& o,
       uint32_t r[32];
       tmem_ld32(taddr + (uint32_t)c0, r);
       tmem_ld_wait();
-      float4* dst = reinterpret_cast<float4*>(stg + lane * STG_PITCH);
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                             __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+        *reinterpret_cast<float4*>(stg + stg_chunk(lane, i)) =
+            make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                        __uint_as_float(r[4 * i + 3]));
     }
     __syncwarp();
     if constexpr (ADAMW) {
