@@ -59,7 +59,13 @@ void lr2_note_launches(int n);
  *                         = 1: operand stored row-major [K, rows].
  * transposed_out = 1 writes element (m, n) at C[n*ldc + m] (epilogue tensors follow the
  * written orientation).  splits > 1 = split-K through `workspace`
- * (lr2_gemm_workspace_bytes).  block_n in {0 (auto), 64, 128, 256}.
+ * (lr2_gemm_workspace_bytes).  block_n in {0 (auto), 64, 128, 256} selects the single-CTA kernel's N tile;
+ * 2128 / 2256 select the cta_group::2 pair kernel (a two-CTA cluster computes 256 x 128 / 256 x 256 tiles).  Auto uses the
+ * pair kernel for untransposed problems with N % 256 == 0, K > 128 and at least 37 pair tiles (x splits).
+ * Dropout (all epilogues, lr2_layernorm_bwd, lr2_dropout_bf16): ONE Philox4x32-7 call per aligned group of 8 output
+ * elements (linear index r*ldc + c), 16 random bits per element; p is quantised to round(p * 65536) / 65536 and the
+ * survivors are scaled by exactly 65536 / (65536 - round(p * 65536)), so the mask is a pure function of
+ * (seed [+ *seed_dev], site, element index) and is regenerated wherever backward needs it.
  * ref: every nn.Linear on the path — finetune/ppo.py:154-170 (Mlp), :207-208 (out_layer),
  *      finetune/xit.py:103-147 (FeedForwardBlock, MultiHeadAttention projections),
  *      tencentpretrain/layers/multi_headed_attn.py:27-76, position_ffn.py:12-15 — and their
