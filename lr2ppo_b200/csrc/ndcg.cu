@@ -84,19 +84,41 @@ __global__ void ndcg_kernel(const float* __restrict__ scores, const long long* _
   bitonic_sort(skey, npad);
   const bool fallback = out_of_range != 0;   // arbitrary int64 labels: sort them too
   if (fallback) bitonic_sort(lkey, npad);
-  // sorted cut positions (min(N, k), ascending) and their original slots
+  // sorted cut positions (min(N, k), ascending) and their original slots: rank counting, one thread per k
+  // (no serial insertion loop with dependent global loads), and the label histogram's descending exclusive scan by
+  // one warp (two bins per lane) instead of a 63-step serial loop
   __shared__ int cut_pos[NDCG_MAX_K], cut_slot[NDCG_MAX_K];
+  __shared__ int cut_raw[NDCG_MAX_K];
   __shared__ int hstart[64];      // first ideal position of label L
-  if (threadIdx.x == 0) {
-    for (int j = 0; j < nk; ++j) {
-      const long long c = ks[j] < (long long)n ? ks[j] : (long long)n;
-      int p = j;
-      while (p > 0 && cut_pos[p - 1] > (int)c) { cut_pos[p] = cut_pos[p - 1]; cut_slot[p] = cut_slot[p - 1]; --p; }
-      cut_pos[p] = (int)(c < 0 ? 0 : c); cut_slot[p] = j;
+  if (threadIdx.x < nk) {
+    const long long kv = ks[threadIdx.x];
+    const long long c = kv < (long long)n ? kv : (long long)n;
+    cut_raw[threadIdx.x] = (int)(c < 0 ? 0 : c);
+  }
+  if (threadIdx.x >= 32 && threadIdx.x < 64) {
+    const int lane = threadIdx.x - 32;
+    // bins in descending label order: position d = 62 - L; lane handles d = 2*lane, 2*lane + 1
+    const int d0 = 2 * lane, d1 = d0 + 1;
+    const int h0 = d0 <= 62 ? hist[62 - d0] : 0, h1 = d1 <= 62 ? hist[62 - d1] : 0;
+    int incl = h0 + h1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
     }
-  } else if (threadIdx.x == 32) {
-    int pos = 0;
-    for (int L = 62; L >= 0; --L) { hstart[L] = pos; pos += hist[L]; }
+    const int excl = incl - (h0 + h1);
+    if (d0 <= 62) hstart[62 - d0] = excl;
+    if (d1 <= 62) hstart[62 - d1] = excl + h0;
+  }
+  __syncthreads();
+  if (threadIdx.x < nk) {
+    const int mine = cut_raw[threadIdx.x];
+    int rank = 0;
+    for (int j = 0; j < nk; ++j) {
+      const int other = cut_raw[j];
+      rank += (other < mine || (other == mine && j < (int)threadIdx.x)) ? 1 : 0;
+    }
+    cut_pos[rank] = mine; cut_slot[rank] = threadIdx.x;
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
@@ -125,6 +147,15 @@ __global__ void ndcg_kernel(const float* __restrict__ scores, const long long* _
     int i = 0;
     for (int j = 0; j < nk; ++j) {
       const int c = cut_pos[j];
+      // the additions stay strictly left-to-right (bit-exactness); the shared-memory loads are batched so that
+      // their latency is paid once per 8 terms instead of once per term
+      for (; i + 8 <= c; i += 8) {
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = t[i + e];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc = acc + v[e];
+      }
       for (; i < c; ++i) acc = acc + t[i];
       outc[cut_slot[j]] = acc;
     }
