@@ -129,6 +129,20 @@ def cpu_stage3(steps, warmup, budget_s, threads=None):
                       f"model build {build_s:.0f}s not timed", "ms_per_step": dt / steps * 1e3, "bs": bs}
 
 
+def workload_config(world, bf16_fc1_grad=True):
+    """The `config` object of the JSON line: the same for the B200 arm and the reference arm."""
+    return {"workload": "configs[3]: stage-3 full LR2PPO step (label-ranking rollout, reward scoring, "
+                        "advantage, fused policy/value losses, 2x AdamW) on synthetic LRMovieNet-shaped "
+                        "data; per-GPU batch 24 queries x 2 tags, text [24,2,196,768], img [24,2,16,768], "
+                        "fusion models 519M (actor) + 526M (critic) + 526M (reward) params, bf16 compute "
+                        "/ fp32 master weights + fp32 Adam state"
+                        + ("; out_layer.fc1 weight gradient kept in bf16" if bf16_fc1_grad else ""),
+            "queries_per_step_per_gpu": BS, "parallelism": f"dp{world}",
+            "l2": "per-step working set (3 GB bf16 weights + 29 GB optimizer traffic) >> 126 MB L2; "
+                  "no explicit flush",
+            "tflop_per_step_per_gpu": FLOP_PER_QUERY * BS / 1e12}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -137,9 +151,9 @@ def run_reference(args, rank):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": "stage-3 LR2PPO step (rollout + update), LRMovieNet-shaped synthetic batch "
-                                   f"[{r['bs']},2,196,768]+[{r['bs']},2,16,768], CPU oracle port of the reference path",
-                       "queries_per_step": r["bs"]},
+            "config": dict(workload_config(max(1, args.gpus)),
+                           reference_arm=f"CPU oracle port of the reference path (fp32, torch CPU); each step is a "
+                                         f"sample of {r['bs']} of the 24 queries"),
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -402,16 +416,7 @@ def main():
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
-                "config": {"workload": "configs[3]: stage-3 full LR2PPO step (label-ranking rollout, reward scoring, "
-                                       "advantage, fused policy/value losses, 2x AdamW) on synthetic LRMovieNet-shaped "
-                                       "data; per-GPU batch 24 queries x 2 tags, text [24,2,196,768], img [24,2,16,768], "
-                                       "fusion models 519M (actor) + 526M (critic) + 526M (reward) params, bf16 compute "
-                                       "/ fp32 master weights + fp32 Adam state"
-                                       + ("" if args.fp32_fc1_grad else "; out_layer.fc1 weight gradient kept in bf16"),
-                           "queries_per_step_per_gpu": BS, "parallelism": f"dp{world}",
-                           "l2": "per-step working set (3 GB bf16 weights + 29 GB optimizer traffic) >> 126 MB L2; "
-                                 "no explicit flush",
-                           "tflop_per_step_per_gpu": FLOP_PER_QUERY * BS / 1e12},
+                "config": workload_config(world, not args.fp32_fc1_grad),
                 "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d_bytes * world,
                         "d2h_bytes_per_step": 40 * world, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches_per_step * args.steps if use_graph else launches),

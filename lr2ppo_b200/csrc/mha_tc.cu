@@ -51,29 +51,41 @@ __device__ __forceinline__ uint64_t tca_idx8(long long bh, int i, int j) {
 }
 
 // ------------------------------------------------------------------ forward --
-struct FwdSmem {
-  static constexpr int Q = 0, K = 16384, V = K + 32768, P = V + 32768, B = P + 65536, RED = B + 1024,
-                       BAR = RED + 2048, TOTAL = BAR + 64 + 1024;
+// Shared-memory layout of the forward kernel, sized at run time from the padded key count NKp so that short
+// sequences keep several CTAs resident per SM (S = 64: 50 KB; S = 197: 103 KB -> two CTAs): Q tile 16 KB | K | V
+// (NKp rows of 128 B each) | P~ (at most two 64-key blocks: 128 keys are written and multiplied at a time) |
+// key bias | reduction scratch | barrier.
+struct FwdLayout {
+  int k, v, p, b, red, bar, total;
+  __host__ __device__ explicit FwdLayout(int NKp) {
+    const int kb = ((NKp * 128 + 1023) / 1024) * 1024;
+    const int nblk = (NKp + 63) / 64;
+    k = 16384; v = k + kb; p = v + kb; b = p + (nblk < 2 ? nblk : 2) * 16384; red = b + 1024; bar = red + 2048;
+    total = bar + 64 + 1024;
+  }
 };
 
 // 256 threads: warp w works on TMEM lane quadrant w & 3 (query rows) and on column part w >> 2 (one half of the keys
 // in the softmax passes, one half of the 64 output dims in the epilogue); the two partial row maxima / row sums meet
-// in shared memory.
-__global__ void __launch_bounds__(256, 1)
+// in shared memory.  TMEM: the S accumulator occupies columns [0, NKp); once a 128-key half of S has been turned
+// into P~ the O accumulator is built in columns [0, 64) (already consumed), so 64 / 128 / 256 columns suffice.
+__global__ void __launch_bounds__(256, 2)
 mha_tc_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, long long ld,
                   const float* __restrict__ key_bias, bf16* __restrict__ o, long long ldo, float* __restrict__ lse,
                   int S, int H, float scale, float drop_p, uint32_t thresh16, float dscale,
                   unsigned long long seed_in, const unsigned long long* __restrict__ seed_dev) {
   extern __shared__ uint8_t tca_raw[];
   uint8_t* sm = tca_raw + ((1024u - (smem_u32(tca_raw) & 1023u)) & 1023u);
-  uint8_t* Qs = sm + FwdSmem::Q;
-  uint8_t* Ks = sm + FwdSmem::K;
-  uint8_t* Vs = sm + FwdSmem::V;
-  uint8_t* Ps = sm + FwdSmem::P;
-  float* Bs = reinterpret_cast<float*>(sm + FwdSmem::B);
-  float* redm = reinterpret_cast<float*>(sm + FwdSmem::RED);          // [2][128] partial row maxima
+  const int NKp = (S + 15) & ~15;                      // keys padded to the UMMA N / K granularity
+  const FwdLayout L(NKp);
+  uint8_t* Qs = sm;
+  uint8_t* Ks = sm + L.k;
+  uint8_t* Vs = sm + L.v;
+  uint8_t* Ps = sm + L.p;
+  float* Bs = reinterpret_cast<float*>(sm + L.b);
+  float* redm = reinterpret_cast<float*>(sm + L.red);                 // [2][128] partial row maxima
   float* redl = redm + 256;                                            // [2][128] partial row sums
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + FwdSmem::BAR);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -82,16 +94,17 @@ mha_tc_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
   const int b = (int)(bh / H), h = (int)(bh % H);
   const unsigned long long seed = seed_in + (seed_dev ? *seed_dev : 0ull);
   const long long row0 = (long long)b * S;
-  const int NKp = (S + 15) & ~15;                      // keys padded to the UMMA N / K granularity
   const int nqt = (S + 127) / 128;
-  const int csplit = (((NKp + 31) / 32 + 1) / 2) * 32; // part 0: columns [0, csplit), part 1: [csplit, NKp)
+  const int nh = (NKp + 127) / 128;                    // 128-key halves
+  const uint32_t tcols = NKp <= 64 ? 64u : (NKp <= 128 ? 128u : 256u);
+  const int csplit = (((NKp + 31) / 32 + 1) / 2) * 32; // pass 1: part 0 scans [0, csplit), part 1 [csplit, NKp)
   const int cbeg = part ? csplit : 0, cend = part ? NKp : min(csplit, NKp);
 
   if (warp == 0) {
     if (lane == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(512u) : "memory");
+                 "r"(tcols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   load_tile(Ks, k + row0 * ld + h * TCA_DH, ld, S, NKp, tid, 256);
@@ -143,55 +156,63 @@ mha_tc_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
     redm[part * 128 + r] = mx;
     __syncthreads();
     mx = fmaxf(redm[r], redm[128 + r]);
-    // pass 2: p = 2^(s - mx), partial row sum, dropout, bf16 P~ into the swizzled K-major tile (blocks of 64 keys)
+    // pass 2, one 128-key half at a time: p = 2^(s - mx), partial row sum, dropout, bf16 P~ into the swizzled
+    // K-major tile (two blocks of 64 keys), then O (+)= P~ V_half
     float l = 0.f;
-    for (int c0 = cbeg; c0 < cend; c0 += 32) {
-      uint32_t a[32];
-      tmem_ld32(trow + (uint32_t)c0, a);
-      tmem_ld_wait();
+    for (int hf = 0; hf < nh; ++hf) {
+      const int kbeg = hf * 128, kend = min(NKp, kbeg + 128);
+      const int pb = kbeg + part * 64, pe = min(kend, pb + 64);
+      for (int c0 = pb; c0 < pe; c0 += 32) {
+        uint32_t a[32];
+        tmem_ld32(trow + (uint32_t)c0, a);
+        tmem_ld_wait();
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int j0 = c0 + g * 8;
-        if (j0 < NKp) {
-          float p[8];
+        for (int g = 0; g < 4; ++g) {
+          const int j0 = c0 + g * 8;
+          if (j0 < pe) {
+            float p[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int j = j0 + e;
-            const float sv = fmaf(__uint_as_float(a[g * 8 + e]), sl2, Bs[j & (TCA_MAX_S - 1)]);
-            p[e] = (j < S) ? ex2_approx(sv - mx) : 0.f;
-            l += p[e];
+            for (int e = 0; e < 8; ++e) {
+              const int j = j0 + e;
+              const float sv = fmaf(__uint_as_float(a[g * 8 + e]), sl2, Bs[j & (TCA_MAX_S - 1)]);
+              p[e] = (j < S) ? ex2_approx(sv - mx) : 0.f;
+              l += p[e];
+            }
+            if (drop_p > 0.f) {
+              float m[8];
+              dropout_mult8(seed, TCA_SITE, tca_idx8(bh, i & (TCA_MAX_S - 1), j0), thresh16, dscale, m);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) p[e] *= m[e];
+            }
+            uint4 u;
+            u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
+            u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
+            const int jl = j0 - kbeg;
+            *reinterpret_cast<uint4*>(Ps + (jl >> 6) * 16384 + sw_off(r, (jl & 63) >> 3)) = u;
           }
-          if (drop_p > 0.f) {
-            float m[8];
-            dropout_mult8(seed, TCA_SITE, tca_idx8(bh, i & (TCA_MAX_S - 1), j0), thresh16, dscale, m);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) p[e] *= m[e];
-          }
-          uint4 u;
-          u.x = pack_bf16x2(p[0], p[1]); u.y = pack_bf16x2(p[2], p[3]);
-          u.z = pack_bf16x2(p[4], p[5]); u.w = pack_bf16x2(p[6], p[7]);
-          *reinterpret_cast<uint4*>(Ps + (j0 >> 6) * 16384 + sw_off(r, (j0 & 63) >> 3)) = u;
         }
       }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();           // every S column of this half has been read: O may overwrite columns [0, 64)
+      if (tid == 0) {
+        tc_fence_after();
+        for (int ks = 0; ks < (kend - kbeg) / 16; ++ks)
+          umma_bf16(tmem_base, make_sdesc(smem_u32(Ps) + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+                    make_sdesc(smem_u32(Vs) + (kbeg / 16 + ks) * 2048, 8192, 1024), idesc_o,
+                    (hf > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(bar);
+      }
+      mbar_wait(bar, phase); phase ^= 1;     // P~ buffer is free again, O holds this half's contribution
+      tc_fence_after();
     }
     redl[part * 128 + r] = l;
-    fence_proxy_async();
-    tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      for (int ks = 0; ks < NKp / 16; ++ks)
-        umma_bf16(tmem_base + 256, make_sdesc(smem_u32(Ps) + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
-                  make_sdesc(smem_u32(Vs) + ks * 2048, 8192, 1024), idesc_o, ks > 0 ? 1u : 0u);
-      umma_commit(bar);
-    }
     l = redl[r] + redl[128 + r];
-    mbar_wait(bar, phase); phase ^= 1;
-    tc_fence_after();
     const float inv = 1.f / l;
     {
       uint32_t a[32];
-      tmem_ld32(trow + 256u + (uint32_t)part * 32u, a);
+      tmem_ld32(trow + (uint32_t)part * 32u, a);
       tmem_ld_wait();
       if (i < S) {
         bf16* orow = o + (row0 + i) * ldo + h * TCA_DH + part * 32;
@@ -212,17 +233,33 @@ mha_tc_fwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tcols) : "memory");
   }
 }
 
 // ----------------------------------------------------------------- backward --
-struct BwdSmem {
-  static constexpr int Q = 0, K = 32768, V = 65536, G = 98304, P = 131072, DS = 163840, L = 196608, D = L + 1024,
-                       B = D + 1024, BAR = B + 1024, TOTAL = BAR + 64 + 1024;
+// Run-time layout of the backward kernel.  Order dS | P | Q | K | V | dO: the MN-major descriptors that read dS^T / P^T
+// as 128-"key" operands always cover two 64-key blocks; when only one block exists (S <= 64: "small" mode) the second
+// block is whatever follows in shared memory -- finite bf16 data that only feeds discarded accumulator rows.
+// small mode (S <= 64, e.g. RoBERTa at 64 tokens): 99 KB of smem and 256 TMEM columns (S/dQ 0..63, dP 64..127,
+// dK 128..191, dV 192..255; dQ reuses the consumed S columns) -> two CTAs per SM.
+// large mode: 512 columns (S 0..127, dP 128..255, dQ_t 256 + 64 t, dK 384, dV 448), one CTA per SM.
+struct BwdLayout {
+  int ds, p, q, k, v, g, l, d, b, bar, total;
+  bool small;
+  uint32_t c_dp, c_dq, c_dk, c_dv, tcols;
+  __host__ __device__ explicit BwdLayout(int S) {
+    const int nt = (S + 127) / 128;
+    small = S <= 64;
+    const int pb = small ? 16384 : 32768, tb = nt * 16384;
+    ds = 0; p = pb; q = 2 * pb; k = q + tb; v = k + tb; g = v + tb; l = g + tb; d = l + 1024; b = d + 1024;
+    bar = b + 1024; total = bar + 64 + 1024;
+    c_dp = small ? 64u : 128u; c_dq = small ? 0u : 256u; c_dk = small ? 128u : 384u; c_dv = small ? 192u : 448u;
+    tcols = small ? 256u : 512u;
+  }
 };
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(256, 2)
 mha_tc_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const bf16* __restrict__ v, long long ld,
                   const float* __restrict__ key_bias, const bf16* __restrict__ o, const bf16* __restrict__ d_o,
                   long long ldo, const float* __restrict__ lse, bf16* __restrict__ dq, bf16* __restrict__ dk,
@@ -230,16 +267,17 @@ mha_tc_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
                   float dscale, unsigned long long seed_in, const unsigned long long* __restrict__ seed_dev) {
   extern __shared__ uint8_t tca_raw[];
   uint8_t* sm = tca_raw + ((1024u - (smem_u32(tca_raw) & 1023u)) & 1023u);
-  uint8_t* Qs = sm + BwdSmem::Q;
-  uint8_t* Ks = sm + BwdSmem::K;
-  uint8_t* Vs = sm + BwdSmem::V;
-  uint8_t* Gs = sm + BwdSmem::G;
-  uint8_t* Ps = sm + BwdSmem::P;
-  uint8_t* dSs = sm + BwdSmem::DS;
-  float* Ls = reinterpret_cast<float*>(sm + BwdSmem::L);
-  float* Ds = reinterpret_cast<float*>(sm + BwdSmem::D);
-  float* Bs = reinterpret_cast<float*>(sm + BwdSmem::B);
-  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + BwdSmem::BAR);
+  const BwdLayout L(S);
+  uint8_t* Qs = sm + L.q;
+  uint8_t* Ks = sm + L.k;
+  uint8_t* Vs = sm + L.v;
+  uint8_t* Gs = sm + L.g;
+  uint8_t* Ps = sm + L.p;
+  uint8_t* dSs = sm + L.ds;
+  float* Ls = reinterpret_cast<float*>(sm + L.l);
+  float* Ds = reinterpret_cast<float*>(sm + L.d);
+  float* Bs = reinterpret_cast<float*>(sm + L.b);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sm + L.bar);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -254,7 +292,7 @@ mha_tc_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
     if (lane == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(512u) : "memory");
+                 "r"(L.tcols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   load_tile(Qs, q + row0 * ld + h * TCA_DH, ld, S, nt * 128, tid, 256);
@@ -307,7 +345,7 @@ mha_tc_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
                     make_sdesc(smem_u32(Ks) + kh * 16384 + ks * 32, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks)
-          umma_bf16(tmem_base + 128, make_sdesc(smem_u32(Gs) + t * 16384 + ks * 32, 16, 1024),
+          umma_bf16(tmem_base + L.c_dp, make_sdesc(smem_u32(Gs) + t * 16384 + ks * 32, 16, 1024),
                     make_sdesc(smem_u32(Vs) + kh * 16384 + ks * 32, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
         umma_commit(bar);
       }
@@ -323,7 +361,7 @@ mha_tc_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
         if (c0 >= NKp) break;                             // warp-uniform
         uint32_t sa[16], da[16];
         tmem_ld16(trow + (uint32_t)c0, sa);
-        tmem_ld16(trow + 128u + (uint32_t)c0, da);
+        tmem_ld16(trow + L.c_dp + (uint32_t)c0, da);
         tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -358,18 +396,18 @@ mha_tc_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
         tc_fence_after();
         // dQ_t (+)= dS K_kh : A = dS K-major (K = keys), B = K_kh MN-major
         for (int ks = 0; ks < NKp / 16; ++ks)
-          umma_bf16(tmem_base + 256 + t * 64, make_sdesc(smem_u32(dSs) + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
+          umma_bf16(tmem_base + L.c_dq + t * 64, make_sdesc(smem_u32(dSs) + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024),
                     make_sdesc(smem_u32(Ks) + kh * 16384 + ks * 2048, 8192, 1024), idesc_nn,
                     (kh > 0 || ks > 0) ? 1u : 0u);
         // dK_kh (+)= dS^T Q_t, dV_kh (+)= P^T dO_t : A = MN-major view of the [q][keys] tiles (K = the 128 query rows)
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
-          umma_bf16(tmem_base + 384, make_sdesc(smem_u32(dSs) + ks * 2048, 16384, 1024),
+          umma_bf16(tmem_base + L.c_dk, make_sdesc(smem_u32(dSs) + ks * 2048, 16384, 1024),
                     make_sdesc(smem_u32(Qs) + t * 16384 + ks * 2048, 8192, 1024), idesc_tt,
                     (t > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks)
-          umma_bf16(tmem_base + 448, make_sdesc(smem_u32(Ps) + ks * 2048, 16384, 1024),
+          umma_bf16(tmem_base + L.c_dv, make_sdesc(smem_u32(Ps) + ks * 2048, 16384, 1024),
                     make_sdesc(smem_u32(Gs) + t * 16384 + ks * 2048, 8192, 1024), idesc_tt,
                     (t > 0 || ks > 0) ? 1u : 0u);
         umma_commit(bar);
@@ -381,7 +419,7 @@ mha_tc_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
     {
       const int j = kh * 128 + r;
       bf16* dst = (part == 0 ? dk : dv) + (row0 + j) * ldd + h * TCA_DH;
-      const uint32_t col = 384u + (uint32_t)part * 64u;
+      const uint32_t col = part ? L.c_dv : L.c_dk;
 #pragma unroll
       for (int c0 = 0; c0 < TCA_DH; c0 += 32) {
         uint32_t a[32];
@@ -406,7 +444,7 @@ mha_tc_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
   for (int t = 0; t < nt; ++t) {
     const int i = t * 128 + r;
     uint32_t a[32];
-    tmem_ld32(trow + 256u + (uint32_t)t * 64u + (uint32_t)part * 32u, a);
+    tmem_ld32(trow + L.c_dq + (uint32_t)t * 64u + (uint32_t)part * 32u, a);
     tmem_ld_wait();
     if (i < S) {
       bf16* dst = dq + (row0 + i) * ldd + h * TCA_DH + part * 32;
@@ -425,7 +463,7 @@ mha_tc_bwd_kernel(const bf16* __restrict__ q, const bf16* __restrict__ k, const 
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(L.tcols) : "memory");
   }
 }
 
@@ -439,12 +477,13 @@ int lr2_mha_tc_fwd(const void* q, const void* k, const void* v, long long ld, co
                    const void* seed_dev, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(mha_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(mha_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             FwdLayout(TCA_MAX_S).total) != cudaSuccess)
       return LR2_ERR_CUDA;
     configured = true;
   }
-  mha_tc_fwd_kernel<<<B * H, 256, FwdSmem::TOTAL, stream>>>(
+  const int smem_fwd = FwdLayout((S + 15) & ~15).total;
+  mha_tc_fwd_kernel<<<B * H, 256, smem_fwd, stream>>>(
       reinterpret_cast<const bf16*>(q), reinterpret_cast<const bf16*>(k), reinterpret_cast<const bf16*>(v), ld, key_bias,
       reinterpret_cast<bf16*>(o), ldo, lse, S, H, scale, drop_p, dropout_thresh16(drop_p), dropout_scale16(drop_p), seed,
       reinterpret_cast<const unsigned long long*>(seed_dev));
@@ -458,12 +497,13 @@ int lr2_mha_tc_bwd(const void* q, const void* k, const void* v, long long ld, co
                    cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(mha_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BwdSmem::TOTAL) !=
-        cudaSuccess)
+    if (cudaFuncSetAttribute(mha_tc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             BwdLayout(TCA_MAX_S).total) != cudaSuccess)
       return LR2_ERR_CUDA;
     configured = true;
   }
-  mha_tc_bwd_kernel<<<B * H, 256, BwdSmem::TOTAL, stream>>>(
+  const int smem_bwd = BwdLayout(S).total;
+  mha_tc_bwd_kernel<<<B * H, 256, smem_bwd, stream>>>(
       reinterpret_cast<const bf16*>(q), reinterpret_cast<const bf16*>(k), reinterpret_cast<const bf16*>(v), ld, key_bias,
       reinterpret_cast<const bf16*>(o), reinterpret_cast<const bf16*>(d_o), ldo, lse, reinterpret_cast<bf16*>(dq),
       reinterpret_cast<bf16*>(dk), reinterpret_cast<bf16*>(dv), ldd, S, H, scale, drop_p, dropout_thresh16(drop_p),
