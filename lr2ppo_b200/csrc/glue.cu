@@ -107,21 +107,32 @@ colsum_partial_kernel(const bf16* __restrict__ x, long long ldx, long long rows,
     partials[(size_t)blockIdx.y * cols + cc] = s;
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ partials, int slabs, int cols, float* __restrict__ out,
-                                    int accumulate) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  float s = accumulate ? out[c] : 0.f;
-  int b = 0;
-  for (; b + 8 <= slabs; b += 8) {             // eight independent loads in flight; fixed summation order
-    float v[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = partials[(size_t)(b + k) * cols + c];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) s += v[k];
+// out[c] (+)= sum over slabs of partials[slab][c].  Block = 32 columns x 8 slab groups: each thread walks every 8th
+// slab (16 independent loads for 128 slabs instead of a 128-long dependent chain per column), the 8 group sums meet
+// in shared memory and are added in a fixed order (deterministic).
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ partials, int slabs, int cols, float* __restrict__ out, int accumulate) {
+  __shared__ float red[8][33];
+  const int cl = threadIdx.x & 31, sg = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float s = 0.f;
+  if (c < cols) {
+    int b = sg;
+    for (; b + 24 < slabs; b += 32) {
+      const float v0 = partials[(size_t)b * cols + c], v1 = partials[(size_t)(b + 8) * cols + c];
+      const float v2 = partials[(size_t)(b + 16) * cols + c], v3 = partials[(size_t)(b + 24) * cols + c];
+      s += v0; s += v1; s += v2; s += v3;
+    }
+    for (; b < slabs; b += 8) s += partials[(size_t)b * cols + c];
   }
-  for (; b < slabs; ++b) s += partials[(size_t)b * cols + c];
-  out[c] = s;
+  red[sg][cl] = s;
+  __syncthreads();
+  if (sg == 0 && c < cols) {
+    float t = accumulate ? out[c] : 0.f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][cl];
+    out[c] = t;
+  }
 }
 
 // head: warp per row.  ref: finetune/ppo.py:228 / :293-295
@@ -267,7 +278,7 @@ extern "C" int lr2_colsum_bf16(const void* x, long long ldx, long long rows, int
   dim3 grid((cols + 255) / 256, slabs);
   colsum_partial_kernel<<<grid, 256, 0, S_(stream)>>>(reinterpret_cast<const bf16*>(x), ldx, rows, cols, partials); LR2_LAUNCHED(1);
   if (cudaGetLastError() != cudaSuccess) return LR2_ERR_CUDA;
-  colsum_final_kernel<<<(cols + 255) / 256, 256, 0, S_(stream)>>>(partials, slabs, cols, out, accumulate); LR2_LAUNCHED(1);
+  colsum_final_kernel<<<(cols + 31) / 32, 256, 0, S_(stream)>>>(partials, slabs, cols, out, accumulate); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 
