@@ -64,23 +64,43 @@ class GradSync:
 
     def start(self, module):
         """Begin the SUM all-reduce of every gradient except out_layer.fc1 (whose gradient is already global) on
-        NCCL's own stream; returns `finish()`, which waits for it and scatters the bucket back into the .grad
-        tensors.  FusedAdamW.step(first={fc1}, between=finish) updates the 500 M fc1 parameters meanwhile."""
-        grads = [p.grad for p in module.parameters() if p.grad is not None and id(p) not in self._skip]
-        if not grads:
+        NCCL's own stream; returns `finish()`, which waits for it.  FusedAdamW.step(first={fc1}, between=finish)
+        updates the 500 M fc1 parameters meanwhile.
+
+        The gradients live in ONE flat fp32 bucket (16-byte aligned slots).  With persistent gradient buffers
+        (engine.persistent_grads, used by the CUDA-graph step) the `.grad` tensors are re-pointed to views of the
+        bucket on first use, so later steps all-reduce in place with no copy in or out; otherwise the values are
+        copied in before and back after the collective."""
+        params = [p for p in module.parameters() if p.grad is not None and id(p) not in self._skip]
+        if not params:
             return lambda: None
-        n = sum(g.numel() for g in grads)
-        flat = self._flat.get(id(module))
-        if flat is None or flat.numel() != n:
-            flat = torch.empty(n, dtype=torch.float32, device=grads[0].device)
-            self._flat[id(module)] = flat
-        views = list(flat.split([g.numel() for g in grads]))
-        torch._foreach_copy_(views, [g.view(-1) for g in grads])
+        grads = [p.grad for p in params]
+        ent = self._flat.get(id(module))
+        if ent is None or ent["shapes"] != [tuple(g.shape) for g in grads]:
+            offs, total = [], 0
+            for g in grads:
+                offs.append(total)
+                total += (g.numel() + 3) // 4 * 4
+            flat = torch.zeros(total, dtype=torch.float32, device=grads[0].device)
+            ent = {"flat": flat, "shapes": [tuple(g.shape) for g in grads],
+                   "views": [flat[o:o + g.numel()] for o, g in zip(offs, grads)]}
+            self._flat[id(module)] = ent
+        flat, views = ent["flat"], ent["views"]
+        inplace = all(g.data_ptr() == v.data_ptr() for g, v in zip(grads, views))
+        copy_back = False
+        if not inplace:
+            torch._foreach_copy_(views, [g.reshape(-1) for g in grads])
+            if all(getattr(e, "persistent_grads", False) for e in self._engines(module)):
+                for p, v in zip(params, views):
+                    p.grad = v.view(p.shape)             # from now on the backward writes straight into the bucket
+            else:
+                copy_back = True
         work = dist.all_reduce(flat, group=self.group, async_op=True)
 
         def finish():
             work.wait()
-            torch._foreach_copy_([g.view(-1) for g in grads], views)
+            if copy_back:
+                torch._foreach_copy_([g.view(-1) for g in grads], views)
         return finish
 
     def early_params(self, module):

@@ -61,6 +61,27 @@ def _worker(rank, world, path):
     assert torch.allclose(net.other.bias.grad, torch.full_like(net.other.bias, 10.0 * sum(range(1, world + 1))))
     bsum = dy.sum(0).clone(); dist.all_reduce(bsum)
     assert torch.allclose(net.out_layer.fc1.bias.grad, bsum, atol=1e-5)
+    # (3) persistent-gradient mode: the .grad tensors become views of the flat bucket (16-byte aligned slots) on the
+    # first call; afterwards start()/finish() all-reduce in place with no copies, and fc1.weight stays untouched
+    net._engine.persistent_grads = True
+    small = [p for n, p in net.named_parameters() if n != "out_layer.fc1.weight"]
+    for p in small:
+        p.grad = torch.full_like(p, float(rank + 1))
+    finish = sync.start(net)
+    finish()
+    ptrs = [p.grad.data_ptr() for p in small]
+    base = min(ptrs)
+    assert all((q - base) % 16 == 0 for q in ptrs)                          # aligned slots of one buffer
+    for p in small:
+        assert torch.allclose(p.grad, torch.full_like(p, float(sum(range(1, world + 1)))))
+    for p in small:                                                          # "next backward" writes in place
+        p.grad.fill_(float(2 * (rank + 1)))
+    sync.start(net)()
+    assert [p.grad.data_ptr() for p in small] == ptrs                        # still the same views: zero-copy
+    for p in small:
+        assert torch.allclose(p.grad, torch.full_like(p, float(2 * sum(range(1, world + 1)))))
+    assert torch.equal(net.out_layer.fc1.weight.grad, before)
+    assert sync.early_params(net) == {id(net.out_layer.fc1.weight)}
     dist.barrier()
     dist.destroy_process_group()
 
