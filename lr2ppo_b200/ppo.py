@@ -40,7 +40,10 @@ def build_optimizer(args, model):
                                         correct_bias=False)
     critic_optimizer = str2optimizer[opt_name](groups(model.critic.named_parameters()),
                                                lr=args.critic_learning_rate, correct_bias=False)
-    for eng, opt in ((model.actor._engine, optimizer), (model.critic._engine, critic_optimizer)):
+    for eng, opt in ((getattr(model.actor, "_engine", None), optimizer),
+                     (getattr(model.critic, "_engine", None), critic_optimizer)):
+        if eng is None:          # trad (MSLR) models: plain autograd Functions, no fusion engine / bf16 shadows
+            continue
         attach_shadows(eng, opt)
         # opt-in: correct but DRAM-page-locality bound today, so slower than wgrad + AdamW
         if getattr(args, "fused_fc1", False):

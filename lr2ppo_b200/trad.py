@@ -96,3 +96,54 @@ class ActorCritic(nn.Module):
         super().__init__()
         self.actor = Actor(args, vit_args)
         self.critic = Critic(args, vit_args)
+
+
+# ---- stage 3 on the trad models (BASELINE configs[0]: finetune/ppo_trad.py) ---------------------------------------
+@torch.no_grad()
+def rollout(model, reward_model, text_emb_batch, tgts_batch, state=None):
+    """One rollout timestep (finetune/ppo_trad.py:765-813).  Returns the 7-entry memory
+    [state, next_state, action_scores, rewards, value, text, tgts] that `train_model` consumes."""
+    bs, tags_num = text_emb_batch.shape[:2]
+    if state is None:
+        state = torch.arange(tags_num, device=text_emb_batch.device).unsqueeze(0).repeat(bs, 1)
+    was_training = model.training
+    model.eval()
+    reward_model.eval()
+    action_scores = model.actor(text_emb_batch, None, None).view(bs, tags_num)
+    value = model.critic(text_emb_batch, None, tgts_batch, state)
+    next_state = ops.ppo_rollout(action_scores.contiguous(), state.contiguous(), 2)
+    rewards = reward_model(text_emb_batch, None, tgts_batch, next_state)
+    if was_training:
+        model.train()
+    return [state, next_state, action_scores, rewards, value, text_emb_batch, tgts_batch]
+
+
+def train_model(args, model, optimizer, critic_optim, scheduler, critic_scheduler, memories, epoch):
+    """ref: finetune/ppo_trad.py:432-544 — same arguments and the same ten returned averages; the per-row Python
+    loop, the hinge-count sync and the ten per-batch all-reduces are replaced by the fused loss kernels."""
+    total = None
+    for state, next_state, old_action_prob, rewards, old_value, text, tgts in memories:
+        model.zero_grad()
+        bs, tags_num = old_action_prob.shape[:2]
+        action_scores = model.actor(text, None, None).view(bs, tags_num)
+        value = model.critic(text, None, tgts, state)
+        pair = next_state[:, -2:].contiguous()
+        loss, rank_loss, kl, ent, rewards_adj, adv = losses.ppo_policy_loss(
+            action_scores, old_action_prob, rewards, old_value, pair, args.kl_div_loss_weight, args.entropy_weight,
+            0.01, -0.1)
+        loss.backward()
+        optimizer.step()
+        value_loss = losses.clipped_value_loss(value, rewards_adj.detach(), old_value, args.value_clip)
+        value_loss.backward()
+        critic_optim.step()
+        stats = torch.stack([loss.detach(), value_loss.detach(), kl.mean(), old_value.mean(), value.detach().mean(),
+                             rewards.mean(), rewards_adj.mean(), adv.mean(), rank_loss, ent.mean()])
+        total = stats if total is None else total + stats
+    total = total / len(memories)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        total = total / dist.get_world_size()
+        dist.all_reduce(total)
+    scheduler.step()
+    critic_scheduler.step()
+    return list(total.unbind(0))

@@ -406,3 +406,63 @@ def gen_api():
 
 if __name__ == "__main__" and "api" in sys.argv[1:]:
     gen_api()
+
+
+def gen_trad_stage3():
+    """BASELINE configs[0]: one full stage-3 step of finetune/ppo_trad.py on the reference's own trad Actor / Critic /
+    Reward modules and its own `train_model` / `build_optimizer` (CPU, gloo world 1).  The rollout is inline in the
+    reference's main() (ppo_trad.py:765-813), so those lines are re-executed here against the reference modules.
+    Dropout is switched off (p = 0) so the step is deterministic; the linear schedule starts at lr = 0, so the first
+    step moves no weight and the gradients are pinned through Adam's first moments."""
+    import argparse
+    import torch.distributed as dist
+    pt = ref_loader.load("ppo_trad")
+    if not dist.is_initialized():
+        f = tempfile.NamedTemporaryFile(delete=False)
+        dist.init_process_group("gloo", init_method=f"file://{f.name}", rank=0, world_size=1)
+    margs = argparse.Namespace(mode="reg", labels_num=5)
+    model = pt.ActorCritic(margs, margs)
+    model.actor.load_state_dict(golden_util.make_trad_state_dict("actor"), strict=True)
+    model.critic.load_state_dict(golden_util.make_trad_state_dict("critic"), strict=True)
+    reward_model = pt.Reward(margs, margs)
+    reward_model.load_state_dict(golden_util.make_trad_state_dict("reward"), strict=True)
+    for m in list(model.modules()) + list(reward_model.modules()):
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    text, tgts, _ = golden_util.trad_inputs("actor")
+    args = argparse.Namespace(is_master=False, mode="reg", kl_div_loss_weight=0.001, entropy_weight=0.001,
+                              value_clip=0.5, learning_rate=1e-3, critic_learning_rate=1e-3, optimizer="adamw",
+                              scheduler="linear", train_steps=100, warmup=0.1, device=torch.device("cpu"))
+    opt, copt, sch, csch = pt.build_optimizer(args, model)
+    bs, tags_num = text.shape[:2]
+    # ---- rollout, ppo_trad.py:765-813 ----
+    model.eval(); reward_model.eval()
+    state = torch.tensor([i for i in range(tags_num)]).unsqueeze(0).repeat(bs, 1)
+    with torch.no_grad():
+        _, action_logits = model.actor(text, None, tgts)
+        value = model.critic(text, None, tgts, state)
+    action_scores = action_logits.view(bs, tags_num)
+    _, idx = torch.sort(action_scores, dim=-1, descending=True)
+    next_state = torch.stack([torch.index_select(state[i], 0, idx[i]) for i in range(bs)])
+    next_state = torch.cat([torch.arange(2).unsqueeze(0).repeat(bs, 1), next_state], dim=1)
+    with torch.no_grad():
+        rewards = reward_model(text, None, tgts, next_state)
+    memories = [[state.clone().detach(), next_state.clone().detach(), action_scores.clone().detach(),
+                 rewards.clone().detach(), value.clone().detach(), text.clone().detach(), tgts.clone().detach()]]
+    out = {"rollout": dict(action_scores=action_scores.clone(), value=value.clone(), next_state=next_state.clone(),
+                           rewards=rewards.clone())}
+    model.train()
+    stats = pt.train_model(args, model, opt, copt, sch, csch, memories, 0)
+    out["stats"] = [float(s) for s in stats]
+    for tag, module, o in (("actor", model.actor, opt), ("critic", model.critic, copt)):
+        for name, p in module.named_parameters():
+            m1 = o.state[p]["exp_avg"]
+            out[f"m/{tag}.{name}"] = m1.double().norm().float()
+            if m1.numel() <= 4096:
+                out[f"mfull/{tag}.{name}"] = m1.clone()
+    torch.save(out, os.path.join(GOLD, "trad_stage3.pt"))
+    print("trad_stage3.pt written; stats", out["stats"])
+
+
+if __name__ == "__main__" and "trad_stage3" in sys.argv[1:]:
+    gen_trad_stage3()
