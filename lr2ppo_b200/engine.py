@@ -393,21 +393,19 @@ class FusionEngine:
         # out_layer
         _wgrad(sink, W["o2"].mod, dfeat, ctx["y1"])
         dy1p = _dgrad(dfeat, W["o2"].w, epilogue=EPI_DGELU, aux=ctx["pre3"])
+        deferred_fc1 = None
         if self.fc1_stash is not None:
             # fused mode: the optimizer consumes (dY, X) in lr2_gemm_wgrad_adamw; no 2 GB gradient is written
             self.fc1_stash.append((dy1p, ctx["cat"]))
             sink.put_vec(W["o1"].mod.bias, ops.colsum(dy1p))
         elif self.fc1_grad_bf16 is not None:
             # bf16 gradient side-buffer read directly by FusedAdamW (1 GB written + read instead of 2 GB); in
-            # data-parallel runs the two small wgrad operands are all-gathered (global-batch gradient, no all-reduce)
-            if self.dp_gather is not None:
-                dy_ = self.dp_gather(dy1p)
-                x_ = ctx["cat_all"]() if ctx.get("cat_all") is not None else self.dp_gather(ctx["cat"])
-            else:
-                dy_, x_ = dy1p, ctx["cat"]
-            # K = world * items: epilogue-bound -> single-CTA tiles; 128-wide (four TMEM accumulator buffers) up to
-            # K = 256, 256-wide beyond (8 ranks: K = 384, operand traffic starts to matter: 460 vs 534 us)
-            ops.gemm(dy_, x_, a_mn=True, b_mn=True, out=self.fc1_grad_bf16, block_n=128 if dy_.shape[0] <= 256 else 256)
+            # data-parallel runs the two small wgrad operands are all-gathered (global-batch gradient, no all-reduce).
+            # The wgrad GEMM itself is deferred to the END of this backward (nothing downstream reads the weight
+            # gradient): the asynchronous gathers of dY (started here) and of X (started in forward) then have the
+            # whole backward to complete instead of sitting in front of it.
+            fc1_dy_handle = self.dp_gather_async(dy1p) if self.dp_gather_async is not None else None
+            deferred_fc1 = (dy1p, fc1_dy_handle)
             sink.put_vec(W["o1"].mod.bias, ops.colsum(dy1p))
         elif self.dp_gather is not None:
             # data parallel: gather the two (small) wgrad operands instead of all-reducing the 2 GB gradient
@@ -427,6 +425,18 @@ class FusionEngine:
         dtf, dimf = xit_backward(W["xit"], ctx["c_x"], dcat_rows, sink, dy_extra=dimf)
         mlp_backward(W["tp1"], W["tp2"], ctx["c_tp"], dtf, sink)
         mlp_backward(W["ip1"], W["ip2"], ctx["c_ip"], dimf, sink)
+        if deferred_fc1 is not None:
+            dy1p, handle = deferred_fc1
+            if handle is not None:
+                dy_ = handle()
+                x_ = ctx["cat_all"]() if ctx.get("cat_all") is not None else self.dp_gather(ctx["cat"])
+            elif self.dp_gather is not None:
+                dy_, x_ = self.dp_gather(dy1p), self.dp_gather(ctx["cat"])
+            else:
+                dy_, x_ = dy1p, ctx["cat"]
+            # K = world * items: epilogue-bound -> single-CTA tiles; 128-wide (four TMEM accumulator buffers) up to
+            # K = 256, 256-wide beyond (8 ranks: K = 384, operand traffic starts to matter: 460 vs 534 us)
+            ops.gemm(dy_, x_, a_mn=True, b_mn=True, out=self.fc1_grad_bf16, block_n=128 if dy_.shape[0] <= 256 else 256)
 
 
 def _add_bf16(a, b):
