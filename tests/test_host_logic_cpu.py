@@ -1,0 +1,74 @@
+"""Host-side logic that needs no GPU: GEMM planning rules (must agree with the kernel selection in
+lr2_gemm_bf16), bench.py's shared config object and reference-arm plumbing, the no-fallback guards."""
+import importlib
+import json
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_plan_gemm_fills_the_cta_pairs():
+    from lr2ppo_b200 import ops
+    # big activations x weight: already >= 74 pair tiles -> no split
+    assert ops.plan_gemm(9408, 3072, 768) == 1
+    assert ops.plan_gemm(9408, 768, 3072) == 1
+    # weight gradients: 12 x 3 = 36 pair tiles, K = 9408 -> 2 splits (72 of 74 pairs busy)
+    assert ops.plan_gemm(3072, 768, 9408) == 2
+    assert ops.plan_gemm(768, 3072, 9408) == 2
+    # 768 x 768: 9 tiles -> 8 splits
+    assert ops.plan_gemm(768, 768, 9408) == 8
+    # not eligible for the pair kernel: N % 256, tiny M, short K, transposed output
+    assert ops.plan_gemm(9408, 200, 768) == 1
+    assert ops.plan_gemm(48, 768, 3072) == 1
+    assert ops.plan_gemm(3072, 162816, 48) == 1
+    assert ops.plan_gemm(3072, 768, 9408, transposed_out=True) == 1
+    # never splits finer than 8 k-blocks per split, never more than 16
+    for M, N, K in [(256, 256, 512), (512, 256, 100000), (2048, 2048, 640)]:
+        s = ops.plan_gemm(M, N, K)
+        assert 1 <= s <= 16 and (s == 1 or (K + 63) // 64 // s >= 8 - 1)
+
+
+def test_plan_small_gemm():
+    from lr2ppo_b200 import ops
+    assert ops.plan_small_gemm(48, 768, 3072) == 12          # 6 tiles, 48 k-blocks
+    assert ops.plan_small_gemm(96, 3072, 768) == 1           # 12 k-blocks: too short to split
+    assert ops.plan_small_gemm(96, 3072, 2048) == 6          # 24 tiles, 32 k-blocks -> 148 // 24
+    assert ops.plan_small_gemm(9408, 768, 768) == 1          # many tiles
+    assert ops.plan_small_gemm(48, 768, 512) == 1            # short K
+    assert ops.plan_small_gemm(48, 770, 3072) == 1           # N % 8 (split-K reduce is 8-wide)
+
+
+def test_bench_config_is_shared_by_both_arms_and_reference_arm_needs_no_gpu(monkeypatch, capsys):
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    cfg = bench.workload_config(1)
+    assert cfg["workload"].startswith("configs[3]") and cfg["queries_per_step_per_gpu"] == 24
+    assert bench.workload_config(8)["parallelism"] == "dp8"
+    # reference arm: rank != 0 does nothing; rank 0 prints one JSON line built from cpu_stage3's result
+    fake = {"value": 3.0, "unit": "queries/s", "cores": 8, "kind": "port", "sample": "s", "ms_per_step": 8000.0,
+            "bs": 24}
+    monkeypatch.setattr(bench, "cpu_stage3", lambda steps, warmup, budget_s: dict(fake))
+    args = bench.argparse.Namespace(gpus=2, steps=3, warmup=1)
+    bench.run_reference(args, rank=1)
+    assert capsys.readouterr().out == ""
+    bench.run_reference(args, rank=0)
+    line = json.loads(capsys.readouterr().out)
+    assert line["impl"] == "reference" and line["metric"] == "LR2PPO stage-3 train queries/sec"
+    assert line["config"]["workload"] == bench.workload_config(2)["workload"]
+    assert line["e2e"] == {"value": 3.0, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == 8
+
+
+def test_no_cpu_fallback_guards():
+    from lr2ppo_b200 import _lib, ops
+    a = torch.zeros(8, 8, dtype=torch.bfloat16)
+    with pytest.raises(_lib.Lr2Error):
+        ops.gemm(a, a)                                       # CPU tensors are refused, never computed on the host
+    from lr2ppo_b200.feed import DeviceFeeder
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            DeviceFeeder((torch.zeros(4),), "cuda:0")
