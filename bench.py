@@ -400,6 +400,14 @@ def main():
         sampler.stop()
     value = world * BS * args.steps / (ms / 1e3)
 
+    if os.environ.get("LR2_BENCH_DEBUG") == "1":
+        # cross-check aid for the data-parallel modes: the same seeds must give the same statistics and weights
+        st = step(resident[0]).float().cpu().tolist()
+        w = model.actor.out_layer.fc1.weight
+        sh = model.actor._engine.bank.get(w)
+        print(f"[debug rank {rank}] stats {['%.6f' % v for v in st]} actor fc1 shadow sum {sh.float().sum().item():.6f} "
+              f"abs {sh.float().abs().sum().item():.4f}", file=sys.stderr, flush=True)
+
     # ---- (2) end-to-end: pinned host -> device every step, stats read back every step ---------------------
     # lr2ppo_b200.feed: the H2D copy of batch i+1 runs on a copy stream while step i computes (double-buffered
     # device slots, event-ordered), and the 10 statistics of every step are read back through pinned memory with a

@@ -21,6 +21,7 @@ class GradSync:
         self.group = group
         self._flat = {}
         self._skip = set()
+        self._sharded = {}
 
     def broadcast_params(self, module):
         """Replicas must start identical once gradients are averaged (rank 0's initialisation wins)."""
@@ -53,14 +54,61 @@ class GradSync:
             return out
         return handle
 
-    def attach(self, module, optimizer):
-        """Enable the activation-gather path for the module's out_layer.fc1 and fold 1/world into AdamW."""
+    def attach(self, module, optimizer, shard_fc1=None):
+        """Enable the activation-gather path for the module's out_layer.fc1 and fold 1/world into AdamW.
+
+        shard_fc1 (default on, LR2_DP_SHARD=0 disables): ZeRO-1 style row sharding of out_layer.fc1 (97 % of the
+        parameters).  Rank r computes the global-batch weight gradient only for its 1/world of the rows (K = world *
+        items GEMM on a row slice), runs AdamW only on those rows (fp32 master, moments and bf16 shadow slices), and the
+        updated bf16 shadow rows are all-gathered in place (`after_step`).  Every element is still updated exactly
+        once per step with the same global gradient, so the arithmetic is unchanged; per rank the 14.5 GB optimizer
+        pass and the redundant full-size wgrad shrink by world.  The fp32 master / moment rows of other ranks go
+        stale locally: call `consolidate(module, optimizer)` before saving a checkpoint."""
+        import os
+        if shard_fc1 is None:
+            shard_fc1 = os.environ.get("LR2_DP_SHARD", "1") == "1"
+        rank = dist.get_rank(self.group)
         for e in self._engines(module):
             e.dp_gather = self.gather_rows
             e.dp_gather_async = self.gather_rows_async
-            self._skip.add(id(e.m.out_layer.fc1.weight))
+            w = e.m.out_layer.fc1.weight
+            self._skip.add(id(w))
+            e.fc1_rows = None
+            rows = w.shape[0] // self.world
+            if shard_fc1 and self.world > 1 and w.shape[0] % self.world == 0 and (rows * w.shape[1]) % 4096 == 0 \
+                    and hasattr(optimizer, "set_window") and getattr(e, "fc1_grad_bf16", None) is not None:
+                e.fc1_rows = (rank * rows, (rank + 1) * rows)
+                optimizer.set_window(w, rank, self.world)
+                self._sharded[id(module)] = (e, w)
         optimizer.grad_scale = 1.0 / self.world
         optimizer._hyper.clear()
+
+    def after_step(self, module):
+        """After optimizer.step(): start the in-place all-gather of the updated bf16 shadow rows of a row-sharded
+        out_layer.fc1 on NCCL's stream.  Returns wait(); it must be called before the module's next forward."""
+        ent = self._sharded.get(id(module))
+        if ent is None:
+            return lambda: None
+        e, w = ent
+        shadow = e.bank.get(w)
+        r0, r1 = e.fc1_rows
+        work = dist.all_gather_into_tensor(shadow, shadow[r0:r1], group=self.group, async_op=True)
+        return work.wait
+
+    def consolidate(self, module, optimizer=None):
+        """Make the fp32 master weight (and, with `optimizer`, Adam's moments) of a row-sharded out_layer.fc1 complete
+        on every rank again (in-place all-gathers); call before state_dict() / checkpoint.save_*."""
+        ent = self._sharded.get(id(module))
+        if ent is None:
+            return
+        e, w = ent
+        r0, r1 = e.fc1_rows
+        tensors = [w.data]
+        if optimizer is not None:
+            st = optimizer.state_for(w)
+            tensors += [st["exp_avg"], st["exp_avg_sq"]]
+        for t in tensors:
+            dist.all_gather_into_tensor(t, t[r0:r1], group=self.group)
 
     def start(self, module):
         """Begin the SUM all-reduce of every gradient except out_layer.fc1 (whose gradient is already global) on

@@ -252,6 +252,7 @@ class FusionEngine:
         self.fc1_stash = None      # list of (dY, X) when out_layer.fc1 is updated by the fused wgrad+AdamW kernel
         self.dp_gather = None      # optional callable(t) -> all-gathered rows (data-parallel fused mode)
         self.dp_gather_async = None  # optional callable(t) -> handle; handle() waits and returns the gathered rows
+        self.fc1_rows = None         # (r0, r1): rows of out_layer.fc1 this rank owns (row-sharded optimizer)
         self.fc1_grad_bf16 = None  # bf16 [out, in] gradient buffer of out_layer.fc1.weight (see enable_bf16_fc1_grad)
 
     def begin_step(self):
@@ -436,7 +437,14 @@ class FusionEngine:
                 dy_, x_ = dy1p, ctx["cat"]
             # K = world * items: epilogue-bound -> single-CTA tiles; 128-wide (four TMEM accumulator buffers) up to
             # K = 256, 256-wide beyond (8 ranks: K = 384, operand traffic starts to matter: 460 vs 534 us)
-            ops.gemm(dy_, x_, a_mn=True, b_mn=True, out=self.fc1_grad_bf16, block_n=128 if dy_.shape[0] <= 256 else 256)
+            bn = 128 if dy_.shape[0] <= 256 else 256
+            rows = getattr(self, "fc1_rows", None)
+            if rows is not None and handle is not None:
+                # row-sharded fc1 (dist.GradSync): only this rank's rows of the global-batch gradient
+                r0, r1 = rows
+                ops.gemm(dy_[:, r0:r1], x_, a_mn=True, b_mn=True, out=self.fc1_grad_bf16[r0:r1], block_n=bn)
+            else:
+                ops.gemm(dy_, x_, a_mn=True, b_mn=True, out=self.fc1_grad_bf16, block_n=bn)
 
 
 def _add_bf16(a, b):

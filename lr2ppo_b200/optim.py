@@ -61,6 +61,25 @@ class FusedAdamW(Optimizer):
         self._fused[id(p)] = provider
         self._tables.clear()
 
+    def set_window(self, p, k, n):
+        """Data-parallel row sharding (dist.GradSync): this rank updates only the k-th of n equal chunk ranges of
+        parameter p (out_layer.fc1: 1/n of its rows); the other chunks are never launched here."""
+        if not hasattr(self, "_windows"):
+            self._windows = {}
+        self._windows[id(p)] = (int(k), int(n))
+        self._tables.clear()
+
+    def _owned(self, tab, i):
+        """Chunk range (start, count) of tensor id i that this rank updates."""
+        a, n = tab["ranges"][i]
+        w = getattr(self, "_windows", {}).get(i)
+        if w is None:
+            return a, n
+        k, parts = w
+        if n % parts:
+            raise _lib.Lr2Error("sharded parameter: chunk count is not divisible by the number of ranks")
+        return a + k * (n // parts), n // parts
+
     def shadow_of(self, p):
         return self._shadows.get(id(p))
 
@@ -208,23 +227,38 @@ class FusedAdamW(Optimizer):
             _lib.run(L.lr2_adamw_multi, tab["ptrs"].data_ptr(), tab["meta"].data_ptr(),
                      tab["chunks"].data_ptr() + 16 * a, n, hyper.data_ptr(), _lib.stream())
 
-        if first and between is not None:
-            # phase 1: the early tensors of every group; phase 2 (after between()): all remaining chunk spans
-            for k, (group, live, fused, hyper, tab, spans) in enumerate(prepared):
-                if not live:
+        def subtract(spans, cut):
+            """spans minus the interval cut = (a, n)."""
+            ca, cb = cut[0], cut[0] + cut[1]
+            out = []
+            for a, n in spans:
+                b = a + n
+                if cb <= a or ca >= b:
+                    out.append((a, n))
                     continue
-                early = sorted(tab["ranges"][i] for i in first if i in tab["ranges"])
-                if not early:
-                    continue
-                rest, pos = [], 0
+                if a < ca:
+                    out.append((a, ca - a))
+                if cb < b:
+                    out.append((cb, b - cb))
+            return out
+
+        windows = getattr(self, "_windows", {})
+        for k, (group, live, fused, hyper, tab, spans) in enumerate(prepared):
+            if not live:
+                continue
+            # chunks of row-sharded tensors that belong to other ranks are never launched
+            for i in windows:
+                if i in tab["ranges"]:
+                    full = tab["ranges"][i]
+                    own = self._owned(tab, i)
+                    spans = subtract(spans, full) + [own]
+            early = sorted(self._owned(tab, i) for i in (first or ()) if i in tab["ranges"])
+            if early and between is not None:
+                # phase 1: the early tensors of every group; phase 2 (after between()): all remaining chunk spans
                 for a, n in early:
                     launch(tab, hyper, a, n)
-                    if a > pos:
-                        rest.append((pos, a - pos))
-                    pos = a + n
-                if pos < tab["n_chunks"]:
-                    rest.append((pos, tab["n_chunks"] - pos))
-                prepared[k] = (group, live, fused, hyper, tab, rest)
+                    spans = subtract(spans, (a, n))
+            prepared[k] = (group, live, fused, hyper, tab, sorted(spans))
         if between is not None:
             between()
         for group, live, fused, hyper, tab, spans in prepared:

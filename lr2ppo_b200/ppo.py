@@ -98,16 +98,18 @@ def rollout(model, reward_model, text_emb_batch, img_emb_batch, tgts_batch, stat
 def _sync_and_step(grad_sync, module, optimizer):
     """optimizer.step() (finetune/ppo.py:580,587); data-parallel: the all-reduce of the small gradients runs on NCCL's
     stream while AdamW already updates out_layer.fc1 (97 % of the parameters; its gradient was built from all-gathered
-    operands and needs no reduction)."""
+    operands and needs no reduction).  Returns wait(): with a row-sharded fc1 it completes the all-gather of the
+    updated bf16 shadow rows and must be called before the module's next forward."""
     if grad_sync is None:
         optimizer.step()
-        return
+        return lambda: None
     early = grad_sync.early_params(module)
     if early and hasattr(optimizer, "register_shadow"):
         optimizer.step(first=early, between=grad_sync.start(module))
     else:
         grad_sync(module)
         optimizer.step()
+    return grad_sync.after_step(module)
 
 
 _STAT_NAMES = ["policy_loss", "value_loss", "kl_penalty", "old_value", "value", "rewards_ori", "rewards",
@@ -135,10 +137,11 @@ def update_batch(args, model, optimizer, critic_optim, memory, grad_sync=None):
         action_scores, old_action_prob, rewards, old_value, pair, args.kl_div_loss_weight, args.entropy_weight,
         0.01, -0.1)
     loss.backward()
-    _sync_and_step(grad_sync, model.actor, optimizer)
+    wait_actor = _sync_and_step(grad_sync, model.actor, optimizer)       # shadow gather overlaps the critic's work
     value_loss = clipped_value_loss(value, rewards_adj.detach(), old_value, args.value_clip)
     value_loss.backward()
-    _sync_and_step(grad_sync, model.critic, critic_optim)
+    wait_critic = _sync_and_step(grad_sync, model.critic, critic_optim)
+    wait_actor(); wait_critic()
     return torch.stack([loss.detach(), value_loss.detach(), kl.mean(), old_value.mean(), value.detach().mean(),
                         rewards.mean(), rewards_adj.mean(), adv.mean(), rank_loss, ent.mean()])
 

@@ -243,3 +243,41 @@ def test_adamw_two_phase_step_is_bit_identical():
         assert torch.equal(p.detach(), q.detach())
         assert torch.equal(oa.state_for(p)["exp_avg_sq"], ob.state_for(q)["exp_avg_sq"])
         assert torch.equal(oa.shadow_of(p), ob.shadow_of(q))
+
+
+def test_adamw_row_windows_partition_the_update():
+    """Row-sharded optimizer (dist.GradSync shard_fc1): two 'ranks' that each own half of the big tensor's chunks
+    together produce exactly the single-optimizer update; chunks of the other rank are left untouched."""
+    from lr2ppo_b200.optim import FusedAdamW
+    g = torch.Generator().manual_seed(8)
+    shapes = [(768,), (64, 8192), (5, 7)]          # the big one: 128 chunks of 4096
+    ps = [torch.randn(s, generator=g) * 0.02 for s in shapes]
+    gs = [torch.randn(s, generator=g) * 0.01 for s in shapes]
+
+    def make(window=None):
+        params = [torch.nn.Parameter(p.clone().cuda()) for p in ps]
+        opt = FusedAdamW([{"params": [params[1], params[2]], "weight_decay": 0.01},
+                          {"params": [params[0]], "weight_decay": 0.0}], lr=1e-3, correct_bias=False,
+                         shadow_bf16=True)
+        if window is not None:
+            opt.set_window(params[1], window, 2)
+        return params, opt
+
+    full, of = make()
+    r0, o0 = make(0)
+    r1, o1 = make(1)
+    for step in range(2):
+        for params in (full, r0, r1):
+            for p, gr in zip(params, gs):
+                p.grad = (gr * (step + 1)).cuda()
+        of.step()
+        o0.step(first={id(r0[1])}, between=lambda: None)
+        o1.step()
+    half = 32
+    assert torch.equal(r0[1].detach()[:half], full[1].detach()[:half])
+    assert torch.equal(r1[1].detach()[half:], full[1].detach()[half:])
+    assert torch.equal(r0[1].detach()[half:], ps[1].cuda()[half:])          # not owned: untouched
+    assert torch.equal(r1[1].detach()[:half], ps[1].cuda()[:half])
+    assert torch.equal(o0.shadow_of(r0[1])[:half], of.shadow_of(full[1])[:half])
+    for i in (0, 2):
+        assert torch.equal(r0[i].detach(), full[i].detach()) and torch.equal(r1[i].detach(), full[i].detach())

@@ -1,0 +1,99 @@
+"""2-GPU cross-check (torchrun --nproc-per-node 2): the row-sharded out_layer.fc1 optimizer (dist.GradSync shard_fc1)
+must reproduce the replicated data-parallel update bit for bit.  Dropout off, constant lr = 1e-3, three eager stage-3
+steps on identical models / batches in both modes; compares every parameter's bf16 shadow / fp32 value and, after
+consolidate(), the fp32 master and Adam moments of fc1."""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+
+from lr2ppo_b200 import ppo
+from lr2ppo_b200.dist import GradSync
+
+
+def build(seed, dev):
+    torch.manual_seed(seed)
+    margs = argparse.Namespace(mode="reg", labels_num=3, seq_length=196, max_imgs=16, visual_feat_dim=768)
+    with torch.device(dev):
+        model = ppo.ActorCritic(margs, margs)
+        reward = ppo.Reward(margs, margs)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    with torch.no_grad():
+        for m in (model, reward):
+            for n, p in m.named_parameters():
+                if "gamma" not in n and "beta" not in n:
+                    p.copy_(torch.randn(p.shape, generator=g, device=dev) * 0.02)
+            for mod in m.modules():
+                if isinstance(mod, torch.nn.LayerNorm):
+                    mod.weight.fill_(1.0)
+                if isinstance(mod, torch.nn.Dropout):
+                    mod.p = 0.0
+    model.eval(); reward.eval()
+    return model, reward
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+    dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+    dist.init_process_group("nccl", device_id=dev)
+    hp = argparse.Namespace(learning_rate=1e-3, critic_learning_rate=1e-3, optimizer="adamw", scheduler="constant",
+                            train_steps=100, warmup=0.1, kl_div_loss_weight=0.001, entropy_weight=0.001,
+                            value_clip=0.5, mode="reg", fc1_grad_bf16=True)
+    g = torch.Generator().manual_seed(100 + rank)
+    batches = [(torch.randn(24, 2, 196, 768, generator=g).to(dev),
+                torch.randn(24, 1, 16, 768, generator=g).repeat(1, 2, 1, 1).to(dev),
+                torch.randint(0, 3, (24, 2), generator=g).to(dev)) for _ in range(3)]
+    results = {}
+    for mode in (False, True):
+        model, reward = build(7, dev)
+        opt, copt, sch, csch = ppo.build_optimizer(hp, model)
+        sync = GradSync(world)
+        sync.broadcast_params(model); sync.broadcast_params(reward)
+        sync.attach(model.actor, opt, shard_fc1=mode)
+        sync.attach(model.critic, copt, shard_fc1=mode)
+        assert (model.actor._engine.fc1_rows is not None) == mode
+        stats = None
+        for text, img, tgts in batches:
+            mem = ppo.rollout(model, reward, text, img, tgts)
+            model.train()
+            stats = ppo.update_batch(hp, model, opt, copt, mem, sync)
+            model.eval()
+        torch.cuda.synchronize()
+        if mode:
+            sync.consolidate(model.actor, opt); sync.consolidate(model.critic, copt)
+        rec = {"stats": stats.float().cpu()}
+        for tag, mod, o in (("actor", model.actor, opt), ("critic", model.critic, copt)):
+            for n, p in mod.named_parameters():
+                rec[f"{tag}.{n}"] = p.detach().clone() if p.numel() < 50_000_000 else None
+            w = mod.out_layer.fc1.weight
+            rec[f"{tag}.fc1.shadow"] = mod._engine.bank.get(w).clone()
+            rec[f"{tag}.fc1.master"] = w.detach().clone()
+            rec[f"{tag}.fc1.m"] = o.state_for(w)["exp_avg"].clone()
+        results[mode] = rec
+        del model, reward, opt, copt, sync
+        torch.cuda.empty_cache()
+    a, b = results[False], results[True]
+    bad = []
+    for k in a:
+        if a[k] is None:
+            continue
+        if not torch.equal(a[k], b[k]):
+            d = (a[k].float() - b[k].float()).abs().max().item()
+            bad.append((k, d))
+    moved = (a["actor.fc1.master"] - build(7, dev)[0].actor.out_layer.fc1.weight.detach()).abs().max().item()
+    print(f"[rank {rank}] compared {len(a)} tensors, mismatches: {bad[:6]}; fc1 moved by {moved:.3e}; "
+          f"stats {a['stats'][:3].tolist()} vs {b['stats'][:3].tolist()}", flush=True)
+    dist.barrier()
+    ok = torch.tensor([0 if bad else 1], device=dev)
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("DP_SHARD_CHECK", "PASS" if ok.item() == 1 else "FAIL", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
