@@ -358,7 +358,11 @@ def main():
         for i in range(2):
             eager_step(resident[i])
         c0 = _lib.launch_count()
-        gstep = ppo.GraphedStage3Step(hp, model, reward, opt, copt, *resident[0], warmup=2, grad_sync=sync)
+        # N > 1: the pipelined cut of the same loop (update of the previous batch + rollout of the current one per
+        # replay) hides the all-gather of the critic's row-sharded weights under the next rollout
+        pipelined = world > 1 and os.environ.get("LR2_PIPELINE_STEP", "1") == "1"
+        cls = ppo.PipelinedStage3Step if pipelined else ppo.GraphedStage3Step
+        gstep = cls(hp, model, reward, opt, copt, *resident[0], warmup=2, grad_sync=sync)
         launches_per_step = (_lib.launch_count() - c0) // 3      # 2 warm-up passes + 1 captured pass
 
         def step(batch):
@@ -506,7 +510,8 @@ def main():
                 "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d_bytes * world,
                         "d2h_bytes_per_step": 40 * world, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches_per_step * args.steps if use_graph else launches),
-                "launch_mode": "cuda_graph_replay" if use_graph else "eager", "clocks": sampler.summary(),
+                "launch_mode": ("cuda_graph_replay_pipelined" if (use_graph and world > 1 and os.environ.get("LR2_PIPELINE_STEP", "1") == "1")
+                                else "cuda_graph_replay") if use_graph else "eager", "clocks": sampler.summary(),
                 "model_tflops_per_gpu": FLOP_PER_QUERY * BS * args.steps / (ms / 1e3) / 1e12}
         if roofline is not None:
             line["roofline"] = roofline

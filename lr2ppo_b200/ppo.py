@@ -72,9 +72,11 @@ def attach_shadows(engine, optimizer):
 
 
 @torch.no_grad()
-def rollout(model, reward_model, text_emb_batch, img_emb_batch, tgts_batch, state=None):
+def rollout(model, reward_model, text_emb_batch, img_emb_batch, tgts_batch, state=None, before_critic=None):
     """One rollout timestep (finetune/ppo.py:845-883).  Returns the memory entry
-    [state, next_state, action_scores, rewards, value, text, img, tgts] (no clones needed: nothing aliases)."""
+    [state, next_state, action_scores, rewards, value, text, img, tgts] (no clones needed: nothing aliases).
+    The critic's value does not depend on the actor / reward results, so it is evaluated last; `before_critic()` (the
+    pending all-gather of the critic's weights in the pipelined data-parallel step) is called right before it."""
     bs, tags_num = text_emb_batch.shape[:2]
     if state is None:
         state = torch.arange(tags_num, device=text_emb_batch.device).unsqueeze(0).repeat(bs, 1)
@@ -82,7 +84,6 @@ def rollout(model, reward_model, text_emb_batch, img_emb_batch, tgts_batch, stat
     model.eval()
     reward_model.eval()
     action_logits = model.actor.scores(text_emb_batch, img_emb_batch)
-    value = model.critic(text_emb_batch, img_emb_batch, tgts_batch, state)
     if model.actor.mode == "cls":
         pr = action_logits.view(bs, tags_num, 3).softmax(dim=-1)
         action_scores = pr[:, :, 1] + 2 * pr[:, :, 2]
@@ -90,6 +91,9 @@ def rollout(model, reward_model, text_emb_batch, img_emb_batch, tgts_batch, stat
         action_scores = action_logits.view(bs, tags_num)
     next_state = ops.ppo_rollout(action_scores.contiguous(), state.contiguous(), 2)
     rewards = reward_model(text_emb_batch, img_emb_batch, tgts_batch, next_state)
+    if before_critic is not None:
+        before_critic()
+    value = model.critic(text_emb_batch, img_emb_batch, tgts_batch, state)
     if was_training:
         model.train()
     return [state, next_state, action_scores, rewards, value, text_emb_batch, img_emb_batch, tgts_batch]
@@ -116,9 +120,11 @@ _STAT_NAMES = ["policy_loss", "value_loss", "kl_penalty", "old_value", "value", 
                "advantages", "rank_loss", "entropy"]
 
 
-def update_batch(args, model, optimizer, critic_optim, memory, grad_sync=None):
+def update_batch(args, model, optimizer, critic_optim, memory, grad_sync=None, defer_critic_wait=False):
     """One stored batch of the update loop (finetune/ppo.py:518-587).  Returns a [10] tensor of the
-    statistics the reference logs (means over the batch), still on the device."""
+    statistics the reference logs (means over the batch), still on the device.  defer_critic_wait: return
+    (stats, wait) instead, where wait() completes the critic's pending weight all-gather (row-sharded data parallel)
+    and must be called before the critic's next forward."""
     state, next_state, old_action_prob, rewards, old_value, text, img, tgts = memory
     if model.actor._engine.persistent_grads:
         model.actor._engine.begin_step(); model.critic._engine.begin_step()   # .grad buffers are reused
@@ -141,9 +147,13 @@ def update_batch(args, model, optimizer, critic_optim, memory, grad_sync=None):
     value_loss = clipped_value_loss(value, rewards_adj.detach(), old_value, args.value_clip)
     value_loss.backward()
     wait_critic = _sync_and_step(grad_sync, model.critic, critic_optim)
-    wait_actor(); wait_critic()
-    return torch.stack([loss.detach(), value_loss.detach(), kl.mean(), old_value.mean(), value.detach().mean(),
-                        rewards.mean(), rewards_adj.mean(), adv.mean(), rank_loss, ent.mean()])
+    wait_actor()
+    stats = torch.stack([loss.detach(), value_loss.detach(), kl.mean(), old_value.mean(), value.detach().mean(),
+                         rewards.mean(), rewards_adj.mean(), adv.mean(), rank_loss, ent.mean()])
+    if defer_critic_wait:
+        return stats, wait_critic
+    wait_critic()
+    return stats
 
 
 def train_model(args, model, optimizer, critic_optim, scheduler, critic_scheduler, memories, epoch, grad_sync=None):
@@ -279,3 +289,52 @@ class GraphedStage3Step:
         self.img.copy_(img, non_blocking=True)
         self.tgts.copy_(tgts, non_blocking=True)
         return self.replay()
+
+
+class PipelinedStage3Step(GraphedStage3Step):
+    """Same training loop, cut at a different point: one replay = update of the PREVIOUS batch followed by the rollout
+    of the current one (the sequence rollout 0, update 0, rollout 1, update 1, ... is unchanged, so are all results).
+    With the row-sharded data-parallel optimizer this lets the all-gather of the critic's updated weights -- the last
+    thing an update does -- run under the next rollout's actor and reward forwards inside the same CUDA graph instead
+    of being exposed at the end of the step.  `replay()` returns the statistics of the update it contained (i.e. of
+    the batch fed one call earlier); `flush()` runs the final pending update eagerly."""
+
+    def __init__(self, args, model, reward_model, optimizer, critic_optim, text, img, tgts, warmup=2, grad_sync=None):
+        self.args, self.model, self.reward, self.grad_sync = args, model, reward_model, grad_sync
+        self.opt, self.copt = optimizer, critic_optim
+        self.text, self.img, self.tgts = text.clone(), img.clone(), tgts.clone()
+        for e in (model.actor._engine, model.critic._engine):
+            e.persistent_grads = True
+        mem = rollout(model, reward_model, self.text, self.img, self.tgts)             # prologue: rollout of batch 0
+        self.mem = [t.clone() for t in mem]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.stats = self._eager()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.opt.frozen_hyper = self.copt.frozen_hyper = True
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.stats = self._eager()
+
+    def _eager(self):
+        self.model.train()
+        stats, wait_critic = update_batch(self.args, self.model, self.opt, self.copt, self.mem, self.grad_sync,
+                                          defer_critic_wait=True)
+        self.model.eval()
+        new = rollout(self.model, self.reward, self.text, self.img, self.tgts, before_critic=wait_critic)
+        for dst, src in zip(self.mem, new):
+            dst.copy_(src)
+        return stats
+
+    def flush(self):
+        """Run the update of the last rolled-out batch (eagerly) and return its statistics."""
+        frozen = self.opt.frozen_hyper
+        self.opt.frozen_hyper = self.copt.frozen_hyper = False
+        self.model.train()
+        stats = update_batch(self.args, self.model, self.opt, self.copt, self.mem, self.grad_sync)
+        self.model.eval()
+        self.opt.frozen_hyper = self.copt.frozen_hyper = frozen
+        return stats
