@@ -7,6 +7,7 @@
 // ndcg_k = ideal_k <= 1e-6f ? 1 : pred_k / ideal_k.  Only the sort is parallel.
 // Algorithmic HBM bytes: N*(4+8) in + 4*nk out per query (+8N when `order` is requested).
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace lr2 {
 
@@ -167,6 +168,298 @@ __global__ void ndcg_kernel(const float* __restrict__ scores, const long long* _
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-per-query path (N <= 1024): the whole query lives in one warp's registers, E = npad / 32 keys per lane.
+// The sort is the mirror ("flip") form of the bitonic network, in which every compare-exchange leaves the smaller
+// key at the lower position, so no direction flags exist: for block size kk = 2, 4, .., npad the first stage pairs
+// position p with p ^ (kk - 1) and the following stages pair p with p ^ j for j = kk/4 .. 1.  Positions are blocked
+// (p = lane * E + e): strides below E are register-to-register (static indices, fully unrolled), strides of E and
+// more are __shfl_xor exchanges with lane ^ (j / E) (flip: lane ^ (kk / E - 1), register E - 1 - e).  No
+// __syncthreads anywhere; 40 of the 55 stages of a 1024-key sort never leave the register file.
+//
+// Labels in [0, 62] (every realistic relevance scale) ride in the key's low byte, so the predicted gains need no
+// gather, and the ideal ordering comes from a label histogram (per-lane private byte counters in shared memory:
+// no atomics, reduced with dp4a).  Any other int64 label switches the query to the general path (gather + a second
+// register sort of the label keys).  Terms are produced position-striped (coalesced log2-table reads, conflict-free
+// shared-memory writes); lanes 0 / 1 then run the two strictly sequential fp32 sums cut to cut.
+// ---------------------------------------------------------------------------------------------------------------
+typedef unsigned long long u64;
+
+__device__ __forceinline__ void cex(u64& a, u64& b) {   // a <- min, b <- max
+  const bool sw = b < a;
+  const u64 lo = sw ? b : a, hi = sw ? a : b;
+  a = lo; b = hi;
+}
+__device__ __forceinline__ u64 pick(u64 mine, u64 other, bool lower) {   // lower position keeps the smaller key
+  const bool other_smaller = other < mine;
+  return (other_smaller == lower) ? other : mine;
+}
+template <int E, int J0>
+__device__ __forceinline__ void intra_strides(u64 (&k)[E]) {
+#pragma unroll
+  for (int j = J0; j > 0; j >>= 1) {
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+      if ((e & j) == 0) cex(k[e], k[e | j]);
+  }
+}
+template <int E>
+__device__ __forceinline__ void warp_sort(u64 (&k)[E], int lane) {
+  // blocks that fit in one lane
+#pragma unroll
+  for (int kk = 2; kk <= E; kk <<= 1) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int p = e ^ (kk - 1);
+      if (p > e) cex(k[e], k[p]);
+    }
+#pragma unroll
+    for (int j = kk >> 2; j > 0; j >>= 1) {
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+        if ((e & j) == 0) cex(k[e], k[e | j]);
+    }
+  }
+  // blocks of m = 2 .. 32 lanes
+#pragma unroll 1
+  for (int m = 2; m <= 32; m <<= 1) {
+    {
+      const int mask = m - 1;
+      const bool lower = (lane & (m >> 1)) == 0;
+      if (E == 1) {
+        const u64 o = __shfl_xor_sync(0xffffffffu, k[0], mask);
+        k[0] = pick(k[0], o, lower);
+      } else {
+#pragma unroll
+        for (int e = 0; e < E / 2; ++e) {
+          const u64 o1 = __shfl_xor_sync(0xffffffffu, k[E - 1 - e], mask);
+          const u64 o2 = __shfl_xor_sync(0xffffffffu, k[e], mask);
+          k[e] = pick(k[e], o1, lower);
+          k[E - 1 - e] = pick(k[E - 1 - e], o2, lower);
+        }
+      }
+    }
+#pragma unroll 1
+    for (int jl = m >> 2; jl > 0; jl >>= 1) {
+      const bool lower = (lane & jl) == 0;
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const u64 o = __shfl_xor_sync(0xffffffffu, k[e], jl);
+        k[e] = pick(k[e], o, lower);
+      }
+    }
+    intra_strides<E, E / 2>(k);
+  }
+}
+
+__host__ __device__ constexpr int ndcg_warp_smem(int E) {
+  // pay/ti: 33E words (padded), hist8/tp: max(2048, 128E) bytes, hist + hstart + 4 cut arrays: 1024 bytes
+  return ((33 * E * 4 + 15) / 16) * 16 + (128 * E > 2048 ? 128 * E : 2048) + 1024;
+}
+
+template <int E>
+__global__ void __launch_bounds__(128, 4) ndcg_warp_kernel(const float* __restrict__ scores,
+                                                        const long long* __restrict__ labels,
+                                                        const int* __restrict__ lens, int B, int N, long long ld,
+                                                        const long long* __restrict__ ks, int nk,
+                                                        const float* __restrict__ log2_table,
+                                                        float* __restrict__ ndcg, long long* __restrict__ order) {
+  extern __shared__ __align__(16) unsigned char nsm[];
+  constexpr int NPAD = 32 * E;
+  constexpr int A_BYTES = ((33 * E * 4 + 15) / 16) * 16;
+  constexpr int B_BYTES = 128 * E > 2048 ? 128 * E : 2048;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (q >= B) return;                                   // whole warps leave; nothing below is block-wide
+  unsigned char* base = nsm + (size_t)warp * ndcg_warp_smem(E);
+  unsigned int* pay = reinterpret_cast<unsigned int*>(base);            // [33E] sorted (idx << 8 | label), padded
+  float* ti = reinterpret_cast<float*>(base);                           // [32E] ideal terms (after pay is consumed)
+  unsigned char* hist8 = base + A_BYTES;                                // [64][32] per-lane label counters
+  float* tp = reinterpret_cast<float*>(base + A_BYTES);                 // [32E] predicted terms (after hist8)
+  int* hist = reinterpret_cast<int*>(base + A_BYTES + B_BYTES);         // [64]
+  int* hstart = hist + 64;                                              // [64]
+  int* cut_pos = hstart + 64;                                           // [32]
+  int* cut_slot = cut_pos + 32;                                         // [32]
+  float* cut_p = reinterpret_cast<float*>(cut_slot + 32);               // [32]
+  float* cut_i = cut_p + 32;                                            // [32]
+
+  const int n = lens ? min(lens[q], N) : N;
+  const float* sq = scores + (long long)q * ld;
+  const long long* lq = labels + (long long)q * ld;
+
+  {  // zero the private counters: 2048 bytes = 64 per lane
+    uint4* z = reinterpret_cast<uint4*>(hist8) + lane * 4;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    z[0] = zero; z[1] = zero; z[2] = zero; z[3] = zero;
+  }
+  __syncwarp();
+  u64 k[E];
+  bool oor = false;
+#pragma unroll
+  for (int e = 0; e < E; ++e) {                         // striped (coalesced) loads; the network does not care
+    const int i = e * 32 + lane;
+    if (i < n) {
+      const long long lab = lq[i];
+      const float s = sq[i] + 0.0f;                     // -0.0 -> +0.0: both zeros tie (torch.sort semantics)
+      unsigned int u = __float_as_uint(s);
+      u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+      u = ~u;                                           // ascending key = descending score
+      const bool in_range = lab >= 0 && lab <= 62;
+      const unsigned int lb = in_range ? (unsigned int)lab : 0xFFu;
+      oor |= !in_range;
+      k[e] = ((u64)u << 32) | ((unsigned int)i << 8) | lb;   // ties: lower index first (stable)
+      if (in_range) hist8[lb * 32 + lane] += 1;
+    } else {
+      k[e] = ~0ull;
+    }
+  }
+  const bool fallback = __any_sync(0xffffffffu, oor);
+  __syncwarp();
+  // counters -> hist[64]: lane handles bins lane and lane + 32 (32 bytes each)
+  int cnt0, cnt1;
+  {
+    const uint4* h = reinterpret_cast<const uint4*>(hist8);
+    const uint4 a0 = h[lane * 2], a1 = h[lane * 2 + 1], b0 = h[(lane + 32) * 2], b1 = h[(lane + 32) * 2 + 1];
+    cnt0 = __dp4a(a0.x, 0x01010101u, 0u) + __dp4a(a0.y, 0x01010101u, 0u) + __dp4a(a0.z, 0x01010101u, 0u) +
+           __dp4a(a0.w, 0x01010101u, 0u) + __dp4a(a1.x, 0x01010101u, 0u) + __dp4a(a1.y, 0x01010101u, 0u) +
+           __dp4a(a1.z, 0x01010101u, 0u) + __dp4a(a1.w, 0x01010101u, 0u);
+    cnt1 = __dp4a(b0.x, 0x01010101u, 0u) + __dp4a(b0.y, 0x01010101u, 0u) + __dp4a(b0.z, 0x01010101u, 0u) +
+           __dp4a(b0.w, 0x01010101u, 0u) + __dp4a(b1.x, 0x01010101u, 0u) + __dp4a(b1.y, 0x01010101u, 0u) +
+           __dp4a(b1.z, 0x01010101u, 0u) + __dp4a(b1.w, 0x01010101u, 0u);
+    hist[lane] = cnt0; hist[lane + 32] = cnt1;
+  }
+  __syncwarp();
+  {  // first ideal position of each label: descending exclusive scan, bins 62 - 2*lane and 61 - 2*lane per lane
+    const int d0 = 2 * lane, d1 = d0 + 1;
+    const int h0 = d0 <= 62 ? hist[62 - d0] : 0, h1 = d1 <= 62 ? hist[62 - d1] : 0;
+    int incl = h0 + h1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    const int excl = incl - (h0 + h1);
+    if (d0 <= 62) hstart[62 - d0] = excl;
+    if (d1 <= 62) hstart[62 - d1] = excl + h0;
+  }
+  // cuts min(n, k) ranked ascending (ties by slot), one lane per k
+  {
+    int mine = 0;
+    if (lane < nk) {
+      const long long kv = ks[lane];
+      const long long c = kv < (long long)n ? kv : (long long)n;
+      mine = (int)(c < 0 ? 0 : c);
+    }
+    int rank = 0;
+    for (int j = 0; j < nk; ++j) {
+      const int other = __shfl_sync(0xffffffffu, mine, j);
+      rank += (other < mine || (other == mine && j < lane)) ? 1 : 0;
+    }
+    if (lane < nk) { cut_pos[rank] = mine; cut_slot[rank] = lane; }
+  }
+
+  // One inlined copy of the network: pass 0 sorts the (score, index, label) keys; pass 1 (only when a label is outside
+  // [0, 62]) sorts the raw int64 label keys for the ideal ordering.
+  const int passes = fallback ? 2 : 1;
+#pragma unroll 1
+  for (int pass = 0; pass < passes; ++pass) {
+    if (pass == 1) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int i = e * 32 + lane;
+        k[e] = i < n ? label_key(lq[i]) : ~0ull;
+      }
+    }
+    warp_sort<E>(k, lane);
+    if (pass == 1) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const int p = lane * E + e;
+        if (p < n) ti[p] = gain_of(label_from_key(k[e])) / log2_table[p];
+      }
+      break;
+    }
+    // sorted payloads -> shared memory (blocked positions, one pad word per 32 keeps the banks distinct)
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int p = lane * E + e;
+      pay[p + (p >> 5)] = (unsigned int)(k[e] & 0xFFFFFFFFull);
+    }
+    __syncwarp();
+    // predicted terms, position-striped.  tp overwrites the byte counters (already reduced).
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = e * 32 + lane;
+      if (i < n) {
+        const unsigned int w = pay[i + (i >> 5)];
+        const unsigned int idx = w >> 8;
+        if (order != nullptr) order[(long long)q * ld + i] = (long long)idx;
+        const long long lab = fallback ? lq[idx] : (long long)(w & 0xFFu);
+        tp[i] = gain_of(lab) / log2_table[i];
+      }
+    }
+    __syncwarp();                                          // pay fully consumed: ti may overwrite it
+    if (!fallback) {
+      // ideal order = labels descending: label L fills positions [hstart[L], hstart[L] + hist[L])
+      const unsigned int ne_lo = __ballot_sync(0xffffffffu, cnt0 > 0), ne_hi = __ballot_sync(0xffffffffu, cnt1 > 0);
+      u64 present = ((u64)ne_hi << 32) | ne_lo;
+      while (present) {
+        const int L = 63 - __clzll((long long)present);
+        present &= ~(1ull << L);
+        const int s0 = hstart[L], c = hist[L];
+        const float g = gain_of((long long)L);
+        for (int i = s0 + lane; i < s0 + c; i += 32) ti[i] = g / log2_table[i];
+      }
+    }
+  }
+  __syncwarp();
+  // strictly sequential fp32 sums, walked cut to cut: lane 0 predicted, lane 1 ideal
+  if (lane < 2) {
+    const float* t = lane == 0 ? tp : ti;
+    float* outc = lane == 0 ? cut_p : cut_i;
+    float acc = 0.f;
+    int i = 0;
+    for (int j = 0; j < nk; ++j) {
+      const int c = cut_pos[j];
+      for (; i < c && (i & 3) != 0; ++i) acc = acc + t[i];
+      for (; i + 8 <= c; i += 8) {
+        const float4 v0 = *reinterpret_cast<const float4*>(t + i), v1 = *reinterpret_cast<const float4*>(t + i + 4);
+        acc = acc + v0.x; acc = acc + v0.y; acc = acc + v0.z; acc = acc + v0.w;
+        acc = acc + v1.x; acc = acc + v1.y; acc = acc + v1.z; acc = acc + v1.w;
+      }
+      for (; i < c; ++i) acc = acc + t[i];
+      outc[cut_slot[j]] = acc;
+    }
+  }
+  __syncwarp();
+  if (lane < nk) {
+    const float p = cut_p[lane], t = cut_i[lane];
+    ndcg[(long long)q * nk + lane] = (t <= 1e-6f) ? 1.0f : p / t;
+  }
+  (void)NPAD;
+}
+
+template <int E>
+static int launch_ndcg_warp(const float* scores, const long long* labels, const int* lens, int B, int N, long long ld,
+                            const long long* ks, int nk, const float* log2_table, float* ndcg, long long* order,
+                            cudaStream_t s) {
+  int wpb = B / 148;                      // fill the 148 SMs first, then stack warps per block
+  wpb = wpb < 1 ? 1 : (wpb > 4 ? 4 : wpb);
+  if (wpb == 3) wpb = 2;
+  const size_t smem = (size_t)wpb * ndcg_warp_smem(E);
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(ndcg_warp_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+      return LR2_ERR_CUDA;
+    configured = smem;
+  }
+  ndcg_warp_kernel<E><<<(B + wpb - 1) / wpb, wpb * 32, smem, s>>>(scores, labels, lens, B, N, ld, ks, nk, log2_table,
+                                                                 ndcg, order); LR2_LAUNCHED(1);
+  LR2_RETURN_LAUNCH();
+}
+
 }  // namespace lr2
 
 using namespace lr2;
@@ -176,6 +469,22 @@ extern "C" int lr2_ndcg_at_k(const float* scores, const long long* labels, const
                              void* stream) {
   if (B <= 0 || N <= 0 || nk <= 0 || ld < N) return LR2_ERR_BAD_SHAPE;
   if (N > 4096 || nk > lr2::NDCG_MAX_K) return LR2_ERR_UNSUPPORTED;
+  {
+    static const int legacy = [] { const char* e = getenv("LR2_NDCG_LEGACY"); return e && e[0] == '1' ? 1 : 0; }();
+    // one warp per query wins whenever there are enough queries to fill the SMs (or the query is short); a few long
+    // queries are latency-bound in a single warp and keep the block-per-query kernel (profiles/r01_ndcg_sweep.md)
+    if (!legacy && N <= 1024 && (N <= 256 || B >= 1024)) {
+      cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+#define LR2_NDCG_WARP(E_) return launch_ndcg_warp<E_>(scores, labels, lens, B, N, ld, ks, nk, log2_table, ndcg, order, s)
+      if (N <= 32) LR2_NDCG_WARP(1);
+      if (N <= 64) LR2_NDCG_WARP(2);
+      if (N <= 128) LR2_NDCG_WARP(4);
+      if (N <= 256) LR2_NDCG_WARP(8);
+      if (N <= 512) LR2_NDCG_WARP(16);
+      LR2_NDCG_WARP(32);
+#undef LR2_NDCG_WARP
+    }
+  }
   int npad = 2;
   while (npad < N) npad <<= 1;
   const size_t smem = (size_t)npad * (8 + 8 + 4 + 4);

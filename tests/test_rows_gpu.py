@@ -57,6 +57,26 @@ def test_ndcg_ties_ragged_and_all_zero():
     assert (out == 1).all()
 
 
+@pytest.mark.parametrize("N", [48, 300, 1024])
+def test_ndcg_general_labels_ragged_unsorted_cuts(N):
+    # labels outside [0, 62] in every other query (second register sort of the int64 label keys) next to
+    # histogram-path queries in the same launch; ragged lengths; cuts unsorted, duplicated, zero and oversized
+    rng = np.random.default_rng(N)
+    B = 16
+    scores = rng.standard_normal((B, N)).astype(np.float32)
+    scores[:, : N // 3] = np.round(scores[:, : N // 3])          # ties
+    labels = rng.integers(0, 63, (B, N))
+    for q in range(0, B, 2):
+        labels[q, rng.integers(0, N, 4)] = [63, -2, 70, 2 ** 40]
+    lens = rng.integers(1, N + 1, B).astype(np.int32)
+    lens[0] = N
+    ks = [7, 1, 100000000, 7, 0, 3]
+    ref, ref_order = restate.ndcg_at_k(scores, labels, ks, lens=lens, want_order=True)
+    out, order = ops.ndcg_at_k(cu(scores), cu(labels, torch.int64), ks, lens=cu(lens, torch.int32), want_order=True)
+    assert np.array_equal(order.cpu().numpy(), ref_order)
+    assert out.cpu().numpy().tobytes() == ref.tobytes()
+
+
 def test_ndcg_full_size_properties():
     # config-5 extreme (B=4096, N=1024): size-independent properties
     g = torch.Generator(device="cuda").manual_seed(0)
