@@ -296,22 +296,40 @@ __global__ void __launch_bounds__(128, 4) ndcg_warp_kernel(const float* __restri
   __syncwarp();
   u64 k[E];
   bool oor = false;
+  {
+    // striped (coalesced) loads; the network does not care where an element starts.  All score loads are issued
+    // first, then all label loads, and only then is anything consumed: one memory latency covers the whole query
+    // (written element by element the label range check serialises the loads: 21 % of the stall samples in
+    // profiles/r01_ndcg_full.md)
+    float sc[E];
+    long long labv[E];
 #pragma unroll
-  for (int e = 0; e < E; ++e) {                         // striped (coalesced) loads; the network does not care
-    const int i = e * 32 + lane;
-    if (i < n) {
-      const long long lab = lq[i];
-      const float s = sq[i] + 0.0f;                     // -0.0 -> +0.0: both zeros tie (torch.sort semantics)
-      unsigned int u = __float_as_uint(s);
-      u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-      u = ~u;                                           // ascending key = descending score
-      const bool in_range = lab >= 0 && lab <= 62;
-      const unsigned int lb = in_range ? (unsigned int)lab : 0xFFu;
-      oor |= !in_range;
-      k[e] = ((u64)u << 32) | ((unsigned int)i << 8) | lb;   // ties: lower index first (stable)
-      if (in_range) hist8[lb * 32 + lane] += 1;
-    } else {
-      k[e] = ~0ull;
+    for (int e = 0; e < E; ++e) {
+      const int i = e * 32 + lane;
+      sc[e] = i < n ? sq[i] : 0.f;
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = e * 32 + lane;
+      labv[e] = i < n ? lq[i] : 0ll;
+    }
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const int i = e * 32 + lane;
+      if (i < n) {
+        const long long lab = labv[e];
+        const float s = sc[e] + 0.0f;                     // -0.0 -> +0.0: both zeros tie (torch.sort semantics)
+        unsigned int u = __float_as_uint(s);
+        u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+        u = ~u;                                           // ascending key = descending score
+        const bool in_range = lab >= 0 && lab <= 62;
+        const unsigned int lb = in_range ? (unsigned int)lab : 0xFFu;
+        oor |= !in_range;
+        k[e] = ((u64)u << 32) | ((unsigned int)i << 8) | lb;   // ties: lower index first (stable)
+        if (in_range) hist8[lb * 32 + lane] += 1;
+      } else {
+        k[e] = ~0ull;
+      }
     }
   }
   const bool fallback = __any_sync(0xffffffffu, oor);
@@ -396,7 +414,10 @@ __global__ void __launch_bounds__(128, 4) ndcg_warp_kernel(const float* __restri
         const unsigned int idx = w >> 8;
         if (order != nullptr) order[(long long)q * ld + i] = (long long)idx;
         const long long lab = fallback ? lq[idx] : (long long)(w & 0xFFu);
-        tp[i] = gain_of(lab) / log2_table[i];
+        // a zero numerator sends the IEEE division to its slow path (FCHK); 0 / x is +0 for every x in the table
+        const float g = gain_of(lab);
+        const float t = (g == 0.f ? 1.0f : g) / log2_table[i];
+        tp[i] = g == 0.f ? 0.f : t;
       }
     }
     __syncwarp();                                          // pay fully consumed: ti may overwrite it
@@ -409,7 +430,12 @@ __global__ void __launch_bounds__(128, 4) ndcg_warp_kernel(const float* __restri
         present &= ~(1ull << L);
         const int s0 = hstart[L], c = hist[L];
         const float g = gain_of((long long)L);
-        for (int i = s0 + lane; i < s0 + c; i += 32) ti[i] = g / log2_table[i];
+        if (g == 0.f) {
+          for (int i = s0 + lane; i < s0 + c; i += 32) ti[i] = 0.f;
+        } else {
+#pragma unroll 4
+          for (int i = s0 + lane; i < s0 + c; i += 32) ti[i] = g / log2_table[i];
+        }
       }
     }
   }
@@ -473,7 +499,8 @@ extern "C" int lr2_ndcg_at_k(const float* scores, const long long* labels, const
     static const int legacy = [] { const char* e = getenv("LR2_NDCG_LEGACY"); return e && e[0] == '1' ? 1 : 0; }();
     // one warp per query wins whenever there are enough queries to fill the SMs (or the query is short); a few long
     // queries are latency-bound in a single warp and keep the block-per-query kernel (profiles/r01_ndcg_sweep.md)
-    if (!legacy && N <= 1024 && (N <= 256 || B >= 1024)) {
+    static const int force_warp = [] { const char* e = getenv("LR2_NDCG_WARP"); return e && e[0] == '1' ? 1 : 0; }();
+    if (!legacy && N <= 1024 && (force_warp || N <= 256 || B >= 1024)) {
       cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
 #define LR2_NDCG_WARP(E_) return launch_ndcg_warp<E_>(scores, labels, lens, B, N, ld, ks, nk, log2_table, ndcg, order, s)
       if (N <= 32) LR2_NDCG_WARP(1);
