@@ -10,7 +10,9 @@
 // One CTA = 16 warps.  Tile = 128 rows x tile_w bytes.  Warp w handles rows (w%4)*32..+32 and the (w/4)-th quarter of
 // the tile width (mirrors the GEMM epilogue's TMEM quadrant / column-part split).  seg = contiguous bytes per row per
 // warp store instruction (16 B per lane).
-template <int MODE>  // 0 = write only, 1 = read + write (same address), 2 = read only
+template <int MODE, int U>  // MODE 0 = write only, 1 = read + write (same address), 2 = read only; U = independent
+                             // 16-byte accesses a lane keeps in flight (U = 1 reproduces the round-1 table, whose
+                             // read / rmw rows were limited by loads in flight, not by the access pattern)
 __global__ void __launch_bounds__(512, 1)
 tile_kernel(char* base, long long pitch, int m_tiles, int n_tiles, int tile_w, int seg, int raster, int esz_shift,
             unsigned long long* sink) {
@@ -25,27 +27,48 @@ tile_kernel(char* base, long long pitch, int m_tiles, int n_tiles, int tile_w, i
   }
   const int lanes_per_row = seg / 16, rows_per_inst = 32 / lanes_per_row;
   const int part_w = tile_w / 4;
+  const int insts_per_c = 32 / rows_per_inst;            // store instructions per seg-wide column step
+  const int n_inst = (part_w / seg) * insts_per_c;       // per tile and warp
   uint4 acc = make_uint4(0, 0, 0, 0);
   for (int w = w_begin; w < w_end; w += w_step) {
     const int mt = raster ? w / n_tiles : w % m_tiles, nt = raster ? w % n_tiles : w / m_tiles;
     char* tile = base + (long long)(mt * 128 + quad * 32) * pitch + (long long)nt * tile_w + part * part_w;
-    for (int c = 0; c < part_w; c += seg) {
-      for (int r = 0; r < 32; r += rows_per_inst) {
-        char* p = tile + (long long)(r + lane / lanes_per_row) * pitch + c + (lane % lanes_per_row) * 16;
+    for (int i0 = 0; i0 < n_inst; i0 += U) {
+      char* p[U];
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = min(i0 + u, n_inst - 1);
+        const int c = (i / insts_per_c) * seg, r = (i % insts_per_c) * rows_per_inst;
+        p[u] = tile + (long long)(r + lane / lanes_per_row) * pitch + c + (lane % lanes_per_row) * 16;
+      }
+      if (MODE != 0) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = *reinterpret_cast<const uint4*>(p[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (i0 + u >= n_inst) break;
         if (MODE == 0) {
-          *reinterpret_cast<uint4*>(p) = make_uint4(w, r, c, lane);
+          *reinterpret_cast<uint4*>(p[u]) = make_uint4(w, i0, u, lane);
         } else if (MODE == 1) {
-          uint4 v = *reinterpret_cast<const uint4*>(p);
-          v.x += 1;
-          *reinterpret_cast<uint4*>(p) = v;
+          v[u].x += 1;
+          *reinterpret_cast<uint4*>(p[u]) = v[u];
         } else {
-          uint4 v = *reinterpret_cast<const uint4*>(p);
-          acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+          acc.x ^= v[u].x; acc.y ^= v[u].y; acc.z ^= v[u].z; acc.w ^= v[u].w;
         }
       }
     }
   }
   if (MODE == 2 && (acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345678u) *sink = 1;
+}
+
+template <int U>
+static void launch(int mode, char* buf, long long pitch, int m_tiles, int n_tiles, int tw, int seg, int raster,
+                   unsigned long long* sink) {
+  if (mode == 0) tile_kernel<0, U><<<148, 512>>>(buf, pitch, m_tiles, n_tiles, tw, seg, raster, 0, sink);
+  else if (mode == 1) tile_kernel<1, U><<<148, 512>>>(buf, pitch, m_tiles, n_tiles, tw, seg, raster, 0, sink);
+  else tile_kernel<2, U><<<148, 512>>>(buf, pitch, m_tiles, n_tiles, tw, seg, raster, 0, sink);
 }
 
 int main() {
@@ -57,22 +80,24 @@ int main() {
   cudaMemset(buf, 0, rows * cols_bytes);
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
-  printf("%-6s %-7s %-6s %-6s %10s %10s\n", "mode", "tile_w", "seg", "raster", "us", "GB/s");
+  printf("%-6s %-7s %-6s %-6s %-4s %10s %10s\n", "mode", "tile_w", "seg", "raster", "U", "us", "GB/s");
   const int tws[] = {256, 512, 1024, 2048, 4096, 8192};
   for (int mode = 0; mode < 3; ++mode)
     for (int ti = 0; ti < 6; ++ti)
       for (int raster = 0; raster < 2; ++raster)
-        for (int seg = 64; seg <= 512; seg *= 2) {
+        for (int seg = 64; seg <= 512; seg *= 2)
+         for (int U = 1; U <= 16; U *= 4) {
           const int tw = tws[ti];
+          if (mode == 0 && U != 1) continue;
           if (seg > tw / 4) continue;
           if (seg != 128 && !(tw == 512 || tw == 2048)) continue;   // sweep seg only at two widths
           const int m_tiles = rows / 128, n_tiles = (int)(cols_bytes / tw);
           float best = 1e30f;
           for (int it = 0; it < 3; ++it) {
             cudaEventRecord(e0);
-            if (mode == 0) tile_kernel<0><<<148, 512>>>(buf, cols_bytes, m_tiles, n_tiles, tw, seg, raster, 0, sink);
-            else if (mode == 1) tile_kernel<1><<<148, 512>>>(buf, cols_bytes, m_tiles, n_tiles, tw, seg, raster, 0, sink);
-            else tile_kernel<2><<<148, 512>>>(buf, cols_bytes, m_tiles, n_tiles, tw, seg, raster, 0, sink);
+            if (U == 1) launch<1>(mode, buf, cols_bytes, m_tiles, n_tiles, tw, seg, raster, sink);
+            else if (U == 4) launch<4>(mode, buf, cols_bytes, m_tiles, n_tiles, tw, seg, raster, sink);
+            else launch<16>(mode, buf, cols_bytes, m_tiles, n_tiles, tw, seg, raster, sink);
             cudaEventRecord(e1);
             cudaEventSynchronize(e1);
             float ms;
@@ -80,8 +105,8 @@ int main() {
             if (ms < best) best = ms;
           }
           const double bytes = (double)m_tiles * 128 * n_tiles * tw * (mode == 1 ? 2 : 1);
-          printf("%-6s %-7d %-6d %-6d %10.1f %10.1f\n", mode == 0 ? "write" : (mode == 1 ? "rmw" : "read"), tw, seg,
-                 raster, best * 1e3, bytes / best / 1e6);
+          printf("%-6s %-7d %-6d %-6d %-4d %10.1f %10.1f\n", mode == 0 ? "write" : (mode == 1 ? "rmw" : "read"), tw,
+                 seg, raster, U, best * 1e3, bytes / best / 1e6);
           fflush(stdout);
         }
   cudaError_t e = cudaDeviceSynchronize();
