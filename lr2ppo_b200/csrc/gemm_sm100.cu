@@ -1184,6 +1184,10 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   return LR2_OK;
 }
 
+int lr2_adamw_wgrad_mma(const void* dY, long long lddy, const void* X, long long ldx, int rows, int out_f, int in_f,
+                        float* param, float* exp_avg, float* exp_avg_sq, void* shadow_bf16, const float* hyper,
+                        float weight_decay, cudaStream_t stream);   // adamw_wgrad.cu
+
 // Fused out_layer.fc1 weight gradient + AdamW: the [out, in] fp32 parameter is updated tile by tile from the
 // TMEM accumulator of dY^T X, so the 500 M-element gradient is never written to or read from HBM.
 // HBM bytes per parameter: read p, m, v (12) + write p, m, v (12) + bf16 shadow (2) = 26 (28+2 unfused, plus
@@ -1199,6 +1203,15 @@ extern "C" int lr2_gemm_wgrad_adamw(const void* dY, long long lddy, const void* 
        reinterpret_cast<uintptr_t>(shadow_bf16)) & 15)
     return LR2_ERR_MISALIGNED;
   if (hyper == nullptr) return LR2_ERR_BAD_SHAPE;
+  {
+    // opt-in linear-pass implementation for short reductions (adamw_wgrad.cu; not GPU-validated yet)
+    static const int impl_mma = [] { const char* e = getenv("LR2_WGRAD_ADAMW_IMPL"); return e && !strcmp(e, "mma") ? 1 : 0; }();
+    if (impl_mma) {
+      const int rc_mma = lr2_adamw_wgrad_mma(dY, lddy, X, ldx, rows, out_f, in_f, param, exp_avg, exp_avg_sq, shadow_bf16,
+                                             hyper, weight_decay, stream);
+      if (rc_mma != LR2_ERR_UNSUPPORTED) return rc_mma;
+    }
+  }
   static int BN_sel = 0;
   if (BN_sel == 0) { const char* e = getenv("LR2_ADAMW_BN"); BN_sel = e ? atoi(e) : 128; }
   CUtensorMap ta, tb;
