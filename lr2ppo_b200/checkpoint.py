@@ -54,6 +54,10 @@ class AsyncCheckpointer:
 
     def save(self, obj, path):
         """obj: a state_dict or any nested dict / list of tensors and plain Python values."""
+        self.save_many([(obj, path)])
+
+    def save_many(self, items):
+        """items: [(obj, path)] snapshotted together and written in order by one background thread."""
         self.wait()
         event = None
         if torch.cuda.is_available():
@@ -61,19 +65,21 @@ class AsyncCheckpointer:
                 self._stream = torch.cuda.Stream()
             self._stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._stream):
-                snap = self._snapshot(obj)
+                snaps = [self._snapshot(obj, f"#{i}") for i, (obj, _) in enumerate(items)]
                 event = torch.cuda.Event()
                 event.record(self._stream)
         else:
-            snap = self._snapshot(obj)
+            snaps = [self._snapshot(obj, f"#{i}") for i, (obj, _) in enumerate(items)]
+        paths = [path for _, path in items]
 
         def write():
             try:
                 if event is not None:
                     event.synchronize()
-                tmp = f"{path}.tmp.{os.getpid()}"
-                torch.save(snap, tmp)
-                os.replace(tmp, path)         # a reader never sees a half-written file
+                for snap, path in zip(snaps, paths):
+                    tmp = f"{path}.tmp.{os.getpid()}"
+                    torch.save(snap, tmp)
+                    os.replace(tmp, path)     # a reader never sees a half-written file
             except Exception as e:            # surfaced by the next wait()
                 self.error = e
 
@@ -130,3 +136,160 @@ def load_training_state(path, models, optimizers, schedulers, map_location="cpu"
     if torch.cuda.is_available() and state["rng"]["cuda"]:
         torch.cuda.set_rng_state_all(state["rng"]["cuda"])
     return state["step"], state.get("extra")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Sharded training state (data-parallel runs with the row-sharded out_layer.fc1 optimizer).
+#
+# With dist.GradSync's row sharding each rank holds the authoritative fp32 master rows and Adam moments of only its
+# 1/world of out_layer.fc1 (6 GB of state per model in total); the other rows are stale locally.  A consolidated save
+# would first all-gather those 6 GB and then have rank 0 write everything.  Here every rank writes its own rows
+# (world writers in parallel, no collective), rank 0 adds the replicated remainder, and the loader reassembles
+# complete tensors, so a run can be resumed on ANY number of ranks.  `export_model` turns a sharded directory back
+# into the reference's single fp32 state_dict file (tencentpretrain/model_saver.py:4-11 format).
+#
+#   dir/common.pt                    rank 0: step, world, replicated model / optimizer / scheduler state, RNG
+#   dir/shard-00001-of-00004.pt      rank 1: {"rows": {model: {param: (r0, r1)}}, "param" / "exp_avg" / "exp_avg_sq"}
+# ---------------------------------------------------------------------------------------------------------------
+def _unwrap(m):
+    return m.module if hasattr(m, "module") else m
+
+
+def _state_index(optimizer, param):
+    """Index of `param` in optimizer.state_dict()['state'] (torch numbers the parameters group by group)."""
+    i = 0
+    for group in optimizer.param_groups:
+        for p in group["params"]:
+            if p is param:
+                return i
+            i += 1
+    raise KeyError("parameter is not managed by this optimizer")
+
+
+def _shard_name(rank, world):
+    return f"shard-{rank:05d}-of-{world:05d}.pt"
+
+
+def save_sharded(dirpath, models, optimizers, schedulers, step, rank, world, row_shards, checkpointer=None,
+                 extra=None):
+    """models / optimizers / schedulers: dicts keyed alike (e.g. "actor", "critic").  row_shards:
+    {model_key: {param_name: (r0, r1)}} = the rows of each row-sharded parameter that THIS rank owns
+    (`dist.GradSync.row_shards(module)`; {} for a replicated model).  Every rank calls this; no collective is issued.
+    Returns the checkpointer (call .wait() before reading the files back)."""
+    ck = checkpointer or _DEFAULT
+    os.makedirs(dirpath, exist_ok=True)
+    shard = {"step": int(step), "rank": int(rank), "world": int(world), "rows": {}, "param": {}, "exp_avg": {},
+             "exp_avg_sq": {}}
+    common = {"step": int(step), "world": int(world), "models": {}, "optimizers": {}, "schedulers": {},
+              "sharded": {}, "extra": extra,
+              "rng": {"cpu": torch.get_rng_state(),
+                      "cuda": torch.cuda.get_rng_state_all() if torch.cuda.is_available() else []}}
+    for key, model in models.items():
+        target = _unwrap(model)
+        named = dict(target.named_parameters())
+        mine = (row_shards or {}).get(key, {})
+        sd = target.state_dict()
+        opt = optimizers.get(key)
+        osd = opt.state_dict() if opt is not None else None
+        for name, (r0, r1) in mine.items():
+            p = named[name]
+            shard["rows"].setdefault(key, {})[name] = (int(r0), int(r1))
+            shard["param"].setdefault(key, {})[name] = p.detach()[r0:r1]
+            common["sharded"].setdefault(key, {})[name] = list(p.shape)
+            sd.pop(name)
+            if opt is not None:
+                idx = _state_index(opt, p)
+                st = osd["state"].get(idx)
+                if st is not None:
+                    shard["exp_avg"].setdefault(key, {})[name] = st["exp_avg"][r0:r1]
+                    shard["exp_avg_sq"].setdefault(key, {})[name] = st["exp_avg_sq"][r0:r1]
+                    osd["state"][idx] = {k: v for k, v in st.items() if k not in ("exp_avg", "exp_avg_sq")}
+        if rank == 0:
+            common["models"][key] = sd
+            if osd is not None:
+                common["optimizers"][key] = osd
+    if rank == 0:
+        common["schedulers"] = {k: s.state_dict() for k, s in schedulers.items()}
+        # common.pt is written last: its presence marks rank 0's part complete
+        ck.save_many([(shard, os.path.join(dirpath, _shard_name(0, world))),
+                      (common, os.path.join(dirpath, "common.pt"))])
+    else:
+        ck.save(shard, os.path.join(dirpath, _shard_name(rank, world)))
+    return ck
+
+
+def _read_sharded(dirpath, map_location="cpu"):
+    common_path = os.path.join(dirpath, "common.pt")
+    if not os.path.exists(common_path):
+        raise FileNotFoundError(f"{dirpath}: no common.pt (incomplete or not a sharded checkpoint)")
+    common = torch.load(common_path, map_location=map_location, weights_only=False)
+    world, step = common["world"], common["step"]
+    shards = []
+    for r in range(world):
+        path = os.path.join(dirpath, _shard_name(r, world))
+        if not os.path.exists(path):
+            raise FileNotFoundError(f"{dirpath}: shard {r} of {world} is missing")
+        s = torch.load(path, map_location=map_location, weights_only=False)
+        if s["step"] != step or s["world"] != world or s["rank"] != r:
+            raise RuntimeError(f"{path}: belongs to step {s['step']} / world {s['world']}, expected {step} / {world}")
+        shards.append(s)
+    return common, shards
+
+
+def _assemble(shape, pieces):
+    """pieces: [((r0, r1), rows tensor)] -> complete tensor; the row ranges must tile [0, shape[0]) exactly."""
+    pieces = sorted(pieces, key=lambda x: x[0][0])
+    at = 0
+    for (r0, r1), t in pieces:
+        if r0 != at or r1 <= r0 or t.shape[0] != r1 - r0:
+            raise RuntimeError(f"row shards do not tile the parameter: expected a piece starting at row {at}, "
+                               f"got rows [{r0}, {r1}) with {t.shape[0]} rows")
+        at = r1
+    if at != shape[0]:
+        raise RuntimeError(f"row shards cover {at} of {shape[0]} rows")
+    return torch.cat([t for _, t in pieces], dim=0).reshape(shape)
+
+
+def load_sharded(dirpath, models, optimizers, schedulers, map_location="cpu"):
+    """Inverse of save_sharded for any current world size: every rank reads common.pt and all shard files and gets
+    COMPLETE parameters and moments (re-attach dist.GradSync afterwards to shard again).  Returns (step, extra)."""
+    common, shards = _read_sharded(dirpath, map_location)
+    for key, model in models.items():
+        target = _unwrap(model)
+        sd = dict(common["models"][key])
+        named = dict(target.named_parameters())
+        opt = optimizers.get(key)
+        osd = common["optimizers"].get(key)
+        for name, shape in common["sharded"].get(key, {}).items():
+            sd[name] = _assemble(shape, [(s["rows"][key][name], s["param"][key][name]) for s in shards
+                                         if name in s["rows"].get(key, {})])
+            if opt is not None and osd is not None:
+                idx = _state_index(opt, named[name])
+                if any(name in s["exp_avg"].get(key, {}) for s in shards):
+                    st = dict(osd["state"].get(idx, {}))
+                    for mom in ("exp_avg", "exp_avg_sq"):
+                        st[mom] = _assemble(shape, [(s["rows"][key][name], s[mom][key][name]) for s in shards])
+                    osd["state"][idx] = st
+        target.load_state_dict(sd, strict=True)
+        if opt is not None and osd is not None:
+            opt.load_state_dict(osd)
+            for attr in ("_tables", "_hyper"):
+                if hasattr(opt, attr):
+                    getattr(opt, attr).clear()
+    for k, s in schedulers.items():
+        s.load_state_dict(common["schedulers"][k])
+    torch.set_rng_state(common["rng"]["cpu"])
+    if torch.cuda.is_available() and common["rng"]["cuda"]:
+        torch.cuda.set_rng_state_all(common["rng"]["cuda"])
+    return common["step"], common.get("extra")
+
+
+def export_model(dirpath, key, model_path):
+    """Sharded directory -> the reference's single-file fp32 state_dict of model `key`
+    (tencentpretrain/model_saver.py:4-11; loadable with load_state_dict(strict=True))."""
+    common, shards = _read_sharded(dirpath, "cpu")
+    sd = dict(common["models"][key])
+    for name, shape in common["sharded"].get(key, {}).items():
+        sd[name] = _assemble(shape, [(s["rows"][key][name], s["param"][key][name]) for s in shards])
+    torch.save(sd, model_path)
+    return sd

@@ -95,6 +95,19 @@ class GradSync:
         work = dist.all_gather_into_tensor(shadow, shadow[r0:r1], group=self.group, async_op=True)
         return work.wait
 
+    def row_shards(self, module):
+        """{parameter name: (r0, r1)} of the rows of `module`'s row-sharded parameters that this rank owns
+        ({} when nothing is sharded): the `row_shards` argument of checkpoint.save_sharded, which then needs no
+        consolidate()."""
+        ent = self._sharded.get(id(module))
+        if ent is None:
+            return {}
+        e, w = ent
+        for name, p in module.named_parameters():
+            if p is w:
+                return {name: tuple(e.fc1_rows)}
+        return {}
+
     def consolidate(self, module, optimizer=None):
         """Make the fp32 master weight (and, with `optimizer`, Adam's moments) of a row-sharded out_layer.fc1 complete
         on every rank again (in-place all-gathers); call before state_dict() / checkpoint.save_*."""
