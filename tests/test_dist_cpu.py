@@ -89,3 +89,109 @@ def _worker(rank, world, path):
 def test_gradsync_world2_gloo():
     with tempfile.TemporaryDirectory() as d:
         mp.spawn(_worker, args=(2, os.path.join(d, "rdzv")), nprocs=2, join=True)
+
+
+# ---- row-sharded out_layer.fc1 optimizer: attach -> step on own rows -> shadow all-gather -> sharded checkpoint ----
+class _Bank:
+    def __init__(self):
+        self.d = {}
+
+    def get(self, w):
+        if id(w) not in self.d:
+            self.d[id(w)] = w.detach().to(torch.bfloat16)
+        return self.d[id(w)]
+
+
+class _Net2(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.out_layer = torch.nn.Module()
+        self.out_layer.fc1 = torch.nn.Linear(1024, 8)          # rows/world * cols is a multiple of the 4096-element chunk
+        self.other = torch.nn.Linear(8, 4)
+        self._engine = _Eng(self)
+        self._engine.bank = _Bank()
+        self._engine.fc1_grad_bf16 = torch.zeros(8, 1024, dtype=torch.bfloat16)
+        self._engine.dp_gather_async = None
+
+
+class _RowAdam(torch.optim.Optimizer):
+    """Host stand-in for FusedAdamW with the attributes GradSync uses (set_window / state_for / grad_scale)."""
+
+    def __init__(self, params):
+        super().__init__(params, dict(lr=0.1))
+        self.grad_scale, self._hyper, self.windows = 1.0, {}, {}
+        for p in self.param_groups[0]["params"]:
+            self.state[p] = {"step": 0, "exp_avg": torch.zeros_like(p), "exp_avg_sq": torch.zeros_like(p)}
+
+    def set_window(self, p, k, n):
+        self.windows[id(p)] = (k, n)
+
+    def state_for(self, p):
+        return self.state[p]
+
+    @torch.no_grad()
+    def step(self, grads, shadows):
+        for p in self.param_groups[0]["params"]:
+            g = grads[id(p)] * self.grad_scale
+            rows = slice(None)
+            if id(p) in self.windows:
+                k, n = self.windows[id(p)]
+                per = p.shape[0] // n
+                rows = slice(k * per, (k + 1) * per)
+            st = self.state[p]
+            st["step"] += 1
+            st["exp_avg"][rows] = 0.9 * st["exp_avg"][rows] + 0.1 * g[rows]
+            st["exp_avg_sq"][rows] = 0.999 * st["exp_avg_sq"][rows] + 0.001 * g[rows] ** 2
+            p[rows] -= 0.1 * g[rows]
+            if id(p) in shadows:
+                shadows[id(p)][rows] = p[rows].to(torch.bfloat16)
+
+
+def _shard_worker(rank, world, path, ckdir):
+    from lr2ppo_b200 import checkpoint
+    from lr2ppo_b200.dist import GradSync
+    dist.init_process_group("gloo", init_method=f"file://{path}", rank=rank, world_size=world)
+    torch.manual_seed(7 + rank)
+    net = _Net2()
+    sync = GradSync(world)
+    sync.broadcast_params(net)
+    opt = _RowAdam(net.parameters())
+    sync.attach(net, opt, shard_fc1=True)
+    w = net.out_layer.fc1.weight
+    per = w.shape[0] // world
+    assert net._engine.fc1_rows == (rank * per, (rank + 1) * per) and opt.windows[id(w)] == (rank, world)
+    assert sync.row_shards(net) == {"out_layer.fc1.weight": (rank * per, (rank + 1) * per)}
+    w0 = w.detach().clone()
+    shadow = net._engine.bank.get(w)
+    torch.manual_seed(99)                                         # the global-batch gradients: same on every rank
+    grads = {id(p): torch.randn_like(p) * world for p in net.parameters()}       # (grad_scale = 1/world undoes it)
+    opt.step(grads, {id(w): shadow})
+    sync.after_step(net)()                                        # in-place all-gather of the updated bf16 rows
+    full = w0 - 0.1 * grads[id(w)] / world
+    assert torch.equal(shadow, full.to(torch.bfloat16))           # every rank's GEMMs see the complete new weight
+    own = slice(rank * per, (rank + 1) * per)
+    stale = torch.ones(w.shape[0], dtype=torch.bool); stale[own] = False
+    assert torch.equal(w.detach()[own], full[own]) and torch.equal(w.detach()[stale], w0[stale])   # master: own rows only
+    # sharded checkpoint: no consolidate; every rank writes its rows, rank 0 the rest
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0)
+    checkpoint.save_sharded(ckdir, {"actor": net}, {"actor": opt}, {"actor": sched}, step=1, rank=rank, world=world,
+                            row_shards={"actor": sync.row_shards(net)},
+                            checkpointer=checkpoint.AsyncCheckpointer()).wait()
+    dist.barrier()
+    net2 = _Net2(); opt2 = _RowAdam(net2.parameters())
+    sched2 = torch.optim.lr_scheduler.LambdaLR(opt2, lambda s: 1.0)
+    assert checkpoint.load_sharded(ckdir, {"actor": net2}, {"actor": opt2}, {"actor": sched2})[0] == 1
+    assert torch.equal(net2.out_layer.fc1.weight.detach(), full)  # complete fp32 master on every rank
+    assert torch.equal(opt2.state[net2.out_layer.fc1.weight]["exp_avg"], 0.1 * grads[id(w)] / world)
+    assert torch.equal(net2.other.weight.detach(), net.other.weight.detach())
+    # consolidate(): the in-memory alternative (all-gathers master + moments in place)
+    sync.consolidate(net, opt)
+    assert torch.equal(w.detach(), full)
+    assert torch.equal(opt.state[w]["exp_avg"], 0.1 * grads[id(w)] / world)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_row_sharded_optimizer_and_sharded_checkpoint_world2_gloo():
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_shard_worker, args=(2, os.path.join(d, "rdzv"), os.path.join(d, "ck")), nprocs=2, join=True)
