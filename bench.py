@@ -38,6 +38,10 @@ def parse():
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--fp32-fc1-grad", action="store_true",
                     help="materialise the out_layer.fc1 weight gradient in fp32 (.grad) instead of the bf16 side buffer")
+    ap.add_argument("--fused-fc1", action="store_true",
+                    help="experimental: out_layer.fc1 through the fused wgrad+AdamW kernel (no gradient tensor); "
+                         "LR2_WGRAD_ADAMW_IMPL=mma selects the linear-pass implementation.  Not the default: slower "
+                         "than wgrad + AdamW today (DESIGN.md 6.3)")
     ap.add_argument("--no-graph", action="store_true", help="run the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--ndcg-sweep", default=None, metavar="OUT.md",
                     help="run the BASELINE configs[4] NDCG@k sweep (GPU vs CPU oracle) and write a markdown table")
@@ -318,7 +322,8 @@ def main():
     model, reward = build_models(torch, dev)
     hp = argparse.Namespace(learning_rate=LR, critic_learning_rate=CRITIC_LR, optimizer="adamw", scheduler="linear",
                             train_steps=TRAIN_STEPS, warmup=0.1, kl_div_loss_weight=0.001, entropy_weight=0.001,
-                            value_clip=0.5, mode="reg", fc1_grad_bf16=not args.fp32_fc1_grad)
+                            value_clip=0.5, mode="reg", fc1_grad_bf16=not args.fp32_fc1_grad,
+                            fused_fc1=args.fused_fc1)
     opt, copt, sch, csch = ppo.build_optimizer(hp, model)
     sync = GradSync(world) if world > 1 else None
     if sync is not None:
@@ -506,7 +511,8 @@ def main():
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
-                "config": workload_config(world, not args.fp32_fc1_grad),
+                "config": dict(workload_config(world, not args.fp32_fc1_grad and not args.fused_fc1),
+                               **({"fused_fc1": os.environ.get("LR2_WGRAD_ADAMW_IMPL", "tcgen05")} if args.fused_fc1 else {})),
                 "e2e": {"value": e2e, "unit": "queries/s", "h2d_bytes_per_step": h2d_bytes * world,
                         "d2h_bytes_per_step": 40 * world, "ms_per_step": ms_e2e / args.steps},
                 "gpu_launches": int(launches_per_step * args.steps if use_graph else launches),

@@ -45,7 +45,8 @@ def build_optimizer(args, model):
         if eng is None:          # trad (MSLR) models: plain autograd Functions, no fusion engine / bf16 shadows
             continue
         attach_shadows(eng, opt)
-        # opt-in: correct but DRAM-page-locality bound today, so slower than wgrad + AdamW
+        # opt-in: correct, but its drain keeps too few loads in flight today (3.2 TB/s), so it is slower
+        # than wgrad + AdamW; LR2_WGRAD_ADAMW_IMPL=mma selects the linear-pass variant (adamw_wgrad.cu)
         if getattr(args, "fused_fc1", False):
             eng.enable_fused_fc1(opt)
         elif getattr(args, "fc1_grad_bf16", False):
