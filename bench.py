@@ -63,7 +63,7 @@ class ClockSampler:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
-        except Exception:
+        except OSError:                       # no nvidia-smi on this box: the clocks object says so
             self.proc = None
 
     def stop(self):
@@ -72,7 +72,7 @@ class ClockSampler:
         self.proc.terminate()
         try:
             out, _ = self.proc.communicate(timeout=5)
-        except Exception:
+        except subprocess.TimeoutExpired:
             self.proc.kill()
             out = ""
         for line in out.strip().splitlines():
@@ -209,7 +209,7 @@ def ndcg_sweep(out):
     peak = 6536.0
     try:
         peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
-    except Exception:
+    except (OSError, ValueError, KeyError):   # driver file absent: the profiling recipe's fallback above
         pass
     rows = []
     rng = np.random.default_rng(0)
@@ -274,7 +274,7 @@ def ncu_traffic(name):
                 if rd is not None:
                     best = max(best or 0.0, rd + wr)
         return best
-    except Exception:
+    except (OSError, ValueError, IndexError):
         return None
 
 
@@ -462,7 +462,7 @@ def main():
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
+        except (OSError, ValueError):
             pass
         hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
         tf_peak, tf_src = (peaks["bf16_tflops_sustained"], "measured sustained") if "bf16_tflops_sustained" in peaks \
