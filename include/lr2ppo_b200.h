@@ -222,6 +222,7 @@ int lr2_gae_scan(const float* rewards, const float* values, const float* notdone
  * N <= 4096, nk <= 32.  gain = float(int64(2**label - 1)); labels outside [0, 63] give 2**label == 0 (gain -1).
  * N <= 1024 runs one warp per query (register/shuffle bitonic network) unless few long queries are given;
  * LR2_NDCG_LEGACY=1 forces the block-per-query kernel, LR2_NDCG_WARP=1 the warp kernel (both bit-identical).
+ * LR2_NDCG_BLOCK_PAIRS=1 (opt-in) lets the block kernel index compare-exchange pairs directly (no idle threads).
  */
 int lr2_ndcg_at_k(const float* scores, const long long* labels, const int* lens, int B, int N, long long ld,
                   const long long* ks, int nk, const float* log2_table, float* ndcg, long long* order,

@@ -36,16 +36,29 @@ __device__ __forceinline__ float gain_of(long long rel) {
 
 constexpr int NDCG_MAX_K = 32;
 
+// pair_index != 0 (LR2_NDCG_BLOCK_PAIRS=1, opt-in until it has run on a GPU): thread t takes the t-th compare-exchange
+// pair directly, i = ((t & ~(j-1)) << 1) | (t & (j-1)), so no thread idles; otherwise every thread visits an element
+// and the upper partner of each pair skips (half of the threads idle in every stage).
 template <typename K>
-__device__ __forceinline__ void bitonic_sort(K* keys, int npad) {
+__device__ __forceinline__ void bitonic_sort(K* keys, int npad, int pair_index) {
   for (int k = 2; k <= npad; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < npad; i += blockDim.x) {
-        const int ixj = i ^ j;
-        if (ixj > i) {
+      if (pair_index) {
+        for (int t = threadIdx.x; t < (npad >> 1); t += blockDim.x) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+          const int ixj = i | j;
           const K a = keys[i], b = keys[ixj];
           const bool up = ((i & k) == 0);
           if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+        }
+      } else {
+        for (int i = threadIdx.x; i < npad; i += blockDim.x) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const K a = keys[i], b = keys[ixj];
+            const bool up = ((i & k) == 0);
+            if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+          }
         }
       }
       __syncthreads();
@@ -56,7 +69,7 @@ __device__ __forceinline__ void bitonic_sort(K* keys, int npad) {
 __global__ void ndcg_kernel(const float* __restrict__ scores, const long long* __restrict__ labels,
                             const int* __restrict__ lens, int N, long long ld, const long long* __restrict__ ks,
                             int nk, const float* __restrict__ log2_table, float* __restrict__ ndcg,
-                            long long* __restrict__ order, int npad) {
+                            long long* __restrict__ order, int npad, int pair_index) {
   extern __shared__ __align__(16) unsigned char nsm[];
   unsigned long long* skey = reinterpret_cast<unsigned long long*>(nsm);  // [npad] (score,idx) keys
   unsigned long long* lkey = skey + npad;                                  // [npad] label keys
@@ -82,9 +95,9 @@ __global__ void ndcg_kernel(const float* __restrict__ scores, const long long* _
     } else { skey[i] = ~0ull; lkey[i] = ~0ull; }
   }
   __syncthreads();
-  bitonic_sort(skey, npad);
+  bitonic_sort(skey, npad, pair_index);
   const bool fallback = out_of_range != 0;   // arbitrary int64 labels: sort them too
-  if (fallback) bitonic_sort(lkey, npad);
+  if (fallback) bitonic_sort(lkey, npad, pair_index);
   // sorted cut positions (min(N, k), ascending) and their original slots: rank counting, one thread per k
   // (no serial insertion loop with dependent global loads), and the label histogram's descending exclusive scan by
   // one warp (two bins per lane) instead of a 63-step serial loop
@@ -521,12 +534,13 @@ extern "C" int lr2_ndcg_at_k(const float* scores, const long long* labels, const
       return LR2_ERR_CUDA;
     configured = smem;
   }
+  static const int pair_index = [] { const char* e = getenv("LR2_NDCG_BLOCK_PAIRS"); return e && e[0] == '1' ? 1 : 0; }();
   int threads = npad / 2;
   if (threads < 32) threads = 64;
   if (threads > 512) threads = 512;
   if (threads < 64) threads = 64;
   ndcg_kernel<<<B, threads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(scores, labels, lens, N, ld, ks, nk,
-                                                                            log2_table, ndcg, order, npad); LR2_LAUNCHED(1);
+                                                                            log2_table, ndcg, order, npad, pair_index); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 
