@@ -21,6 +21,23 @@ def _f2i(x):
     return struct.unpack("<i", struct.pack("<f", float(x)))[0]
 
 
+def subtract_span(spans, cut):
+    """Chunk-index bookkeeping of the two-phase / row-sharded step: `spans` (list of (start, count)) minus the
+    interval cut = (start, count)."""
+    ca, cb = cut[0], cut[0] + cut[1]
+    out = []
+    for a, n in spans:
+        b = a + n
+        if cb <= a or ca >= b:
+            out.append((a, n))
+            continue
+        if a < ca:
+            out.append((a, ca - a))
+        if cb < b:
+            out.append((cb, b - cb))
+    return out
+
+
 class FusedAdamW(Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, correct_bias=True,
                  shadow_bf16=False, grad_scale=1.0):
@@ -227,20 +244,7 @@ class FusedAdamW(Optimizer):
             _lib.run(L.lr2_adamw_multi, tab["ptrs"].data_ptr(), tab["meta"].data_ptr(),
                      tab["chunks"].data_ptr() + 16 * a, n, hyper.data_ptr(), _lib.stream())
 
-        def subtract(spans, cut):
-            """spans minus the interval cut = (a, n)."""
-            ca, cb = cut[0], cut[0] + cut[1]
-            out = []
-            for a, n in spans:
-                b = a + n
-                if cb <= a or ca >= b:
-                    out.append((a, n))
-                    continue
-                if a < ca:
-                    out.append((a, ca - a))
-                if cb < b:
-                    out.append((cb, b - cb))
-            return out
+        subtract = subtract_span
 
         windows = getattr(self, "_windows", {})
         for k, (group, live, fused, hyper, tab, spans) in enumerate(prepared):

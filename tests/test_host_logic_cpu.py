@@ -72,3 +72,22 @@ def test_no_cpu_fallback_guards():
     if not torch.cuda.is_available():
         with pytest.raises(Exception):
             DeviceFeeder((torch.zeros(4),), "cuda:0")
+
+
+def test_adamw_chunk_span_arithmetic():
+    """FusedAdamW launches chunk spans; the two-phase (data-parallel) and row-sharded steps cut intervals out of them.
+    Every chunk must be launched exactly once by phase 1 + phase 2, and foreign rows never."""
+    from lr2ppo_b200.optim import subtract_span
+    assert subtract_span([(0, 10)], (3, 4)) == [(0, 3), (7, 3)]
+    assert subtract_span([(0, 10)], (0, 10)) == []
+    assert subtract_span([(0, 10)], (0, 4)) == [(4, 6)]
+    assert subtract_span([(0, 10)], (6, 4)) == [(0, 6)]
+    assert subtract_span([(0, 3), (7, 3)], (2, 6)) == [(0, 2), (8, 2)]
+    assert subtract_span([(0, 10)], (12, 5)) == [(0, 10)]
+    # a 100-chunk table whose tensor [20, 60) is row-sharded 4 ways (this rank owns the 3rd quarter) and launched early
+    spans = subtract_span([(0, 100)], (20, 40)) + [(40, 10)]
+    early = (40, 10)
+    late = sorted(subtract_span(spans, early))
+    launched = sorted([early] + late)
+    covered = [c for a, n in launched for c in range(a, a + n)]
+    assert covered == list(range(0, 20)) + list(range(40, 50)) + list(range(60, 100))     # once each, foreign rows never
