@@ -209,6 +209,22 @@ int lr2_ppo_rollout(const float* scores, const long long* state, int B, int n, i
  * Outputs perm [B, n] i64 and logprob [B] f32.  north_star extension; oracle: oracle/ppo_rows.c. */
 int lr2_rank_sample(const float* scores, const float* u, int B, int n, int greedy, long long* perm, float* logprob,
                     void* stream);
+/* Plackett-Luce log-probability of a given ranking perm [B,n] under scores [B,n] (north_star extension, the
+ * counterpart of lr2_rank_sample: same arithmetic step by step, so evaluating the sampler's own ranking under the same
+ * scores reproduces its logprob bit for bit).  logprob [B] and/or dscores [B,n] = dlogprob[b] * d lp_b / d scores
+ * (dlogprob NULL = 1).  inv_scratch: caller-owned int [B,n].  No reference implementation exists: the reference ranks
+ * greedily (finetune/ppo.py:865-874); log / masked helpers it keeps as dead code: finetune/ppo.py:431-491. */
+int lr2_rank_logprob(const float* scores, const long long* perm, int B, int n, const float* dlogprob, float* logprob,
+                     float* dscores, int* inv_scratch, void* stream);
+
+/* Ratio-clipped PPO surrogate, forward + gradient in one launch (north_star extension; --eps_clip is parsed but never
+ * read by the reference, finetune/ppo.py:730, and masked_normalize is dead code at finetune/ppo.py:485-491):
+ * A' = normalize ? (A - mean A) * rsqrt(max(var A, norm_eps)) : A;  ratio = exp(logp - logp_old);
+ * out[0] = -mean min(ratio A', clamp(ratio, 1 - eps, 1 + eps) A'), out[1] = clipped fraction;
+ * dlogp [B] (or NULL), adv_used [B] (or NULL) = A'. */
+int lr2_ppo_clip_surrogate(const float* logp, const float* logp_old, const float* adv, int B, float eps_clip,
+                           int normalize, float norm_eps, float* out, float* dlogp, float* adv_used, void* stream);
+
 /* GAE(gamma, lambda) reverse scan: delta_t = r_t + gamma*V_{t+1}*nd_t - V_t; A_t = delta_t + gamma*lambda*nd_t*A_{t+1}.
  * rewards [B,T], values [B,T+1], notdone [B,T] or NULL; adv, ret [B,T].  T=1, V_1=0 -> r - V (ref: finetune/ppo.py:560). */
 int lr2_gae_scan(const float* rewards, const float* values, const float* notdone, int B, int T, float gamma,

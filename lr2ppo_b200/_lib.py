@@ -60,6 +60,8 @@ SIGNATURES = {
     "lr2_ppo_rollout": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
     "lr2_rank_sample": (i32, [vp, vp, i32, i32, i32, vp, vp, vp]),
     "lr2_gae_scan": (i32, [vp, vp, vp, i32, i32, f32, f32, vp, vp, vp]),
+    "lr2_rank_logprob": (i32, [vp, vp, i32, i32, vp, vp, vp, vp, vp]),
+    "lr2_ppo_clip_surrogate": (i32, [vp, vp, vp, i32, f32, i32, f32, vp, vp, vp, vp]),
     "lr2_ndcg_at_k": (i32, [vp, vp, vp, i32, i32, i64, vp, i32, vp, vp, vp, vp]),
     "lr2_ndcg_presorted": (i32, [vp, vp, vp, i32, i32, vp, i32, vp, vp, vp, vp]),
     "lr2_adamw_chunk_elems": (i32, []),

@@ -261,6 +261,92 @@ __global__ void rank_sample_kernel(const float* __restrict__ scores, const float
   if (logprob != nullptr) logprob[b] = lp;
 }
 
+// Plackett-Luce log-probability of a GIVEN ranking under (new) scores, with the gradient: the quantity a PPO ratio
+// needs.  Same arithmetic as rank_sample_kernel, step by step (max over the not-yet-placed labels, sum of det_exp in
+// label-index order, det_log(e_pick) - det_log(total)), so rank_logprob(scores, rank_sample(scores).perm) reproduces the
+// sampler's own logprob bit for bit and the ratio of an unchanged policy is exactly 1.
+//   lp = sum_t [ (s[pi_t] - mx_t) - log sum_{j not placed before t} exp(s_j - mx_t) ]
+//   d lp / d s_j = [j placed at k] - sum_{t <= k} exp(s_j - mx_t) / total_t          (k = position of j in pi)
+// inv [B, n] (caller-owned scratch) receives the inverse permutation (position of each label).
+__global__ void rank_logprob_kernel(const float* __restrict__ scores, const long long* __restrict__ perm, int B, int n,
+                                    const float* __restrict__ dlp, float* __restrict__ logprob,
+                                    float* __restrict__ dscores, int* __restrict__ inv) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* sb = scores + (long long)b * n;
+  const long long* pb = perm + (long long)b * n;
+  int* ib = inv + (long long)b * n;
+  for (int t = 0; t < n; ++t) ib[(int)pb[t]] = t;
+  float* db = dscores != nullptr ? dscores + (long long)b * n : nullptr;
+  const float up = dlp != nullptr ? dlp[b] : 1.0f;
+  if (db != nullptr)
+    for (int j = 0; j < n; ++j) db[j] = up;            // the "+1" of every label (each is placed exactly once)
+  float lp = 0.f;
+  for (int t = 0; t < n; ++t) {
+    float mx = -INFINITY;
+    for (int j = 0; j < n; ++j)
+      if (ib[j] >= t) mx = fmaxf(mx, sb[j]);
+    float total = 0.f;
+    for (int j = 0; j < n; ++j)
+      if (ib[j] >= t) total = __fadd_rn(total, lr2_det_expf(__fsub_rn(sb[j], mx)));
+    const float pick_e = lr2_det_expf(__fsub_rn(sb[(int)pb[t]], mx));
+    lp = __fadd_rn(lp, __fsub_rn(lr2_det_logf(pick_e), lr2_det_logf(total)));
+    if (db != nullptr) {
+      const float inv_total = 1.0f / total;
+      for (int j = 0; j < n; ++j)
+        if (ib[j] >= t) db[j] -= up * (lr2_det_expf(__fsub_rn(sb[j], mx)) * inv_total);
+    }
+  }
+  if (logprob != nullptr) logprob[b] = lp;
+}
+
+// Ratio-clipped PPO surrogate (north_star extension; the reference parses --eps_clip but never reads it, and keeps the
+// PaLM-rlhf helper it would use, masked_normalize, as dead code: finetune/ppo.py:485-491):
+//   A' = normalize ? (A - mean(A)) * rsqrt(max(mean((A - mean)^2), norm_eps)) : A                     (:485-491)
+//   ratio = exp(logp - logp_old);  loss = -mean_b min(ratio * A', clamp(ratio, 1 - eps, 1 + eps) * A')
+// out[0] = loss, out[1] = fraction of rows with |ratio - 1| > eps.  dlogp = d loss / d logp (advantages are constants).
+// Ties of the two branches split the gradient evenly, as torch.min does (inside the clip range both are identical).
+__global__ void __launch_bounds__(PL_THREADS)
+ppo_clip_surrogate_kernel(const float* __restrict__ logp, const float* __restrict__ logp_old,
+                          const float* __restrict__ adv, int B, float eps_clip, int normalize, float norm_eps,
+                          float* __restrict__ out, float* __restrict__ dlogp, float* __restrict__ adv_used) {
+  __shared__ float sm[2 * (PL_THREADS / 32)];
+  const float invB = 1.f / (float)B;
+  float mean = 0.f, scale = 1.f;
+  if (normalize) {
+    float a1[1] = {0.f};
+    for (int b = threadIdx.x; b < B; b += PL_THREADS) a1[0] += adv[b];
+    block_sum<1>(a1, sm);
+    mean = a1[0] * invB;
+    float a2[1] = {0.f};
+    for (int b = threadIdx.x; b < B; b += PL_THREADS) { const float c = adv[b] - mean; a2[0] += c * c; }
+    block_sum<1>(a2, sm);
+    scale = 1.0f / sqrtf(fmaxf(a2[0] * invB, norm_eps));
+  }
+  float acc[2] = {0.f, 0.f};
+  for (int b = threadIdx.x; b < B; b += PL_THREADS) {
+    const float A = (adv[b] - mean) * scale;
+    const float ratio = expf(logp[b] - logp_old[b]);
+    const float lo = 1.f - eps_clip, hi = 1.f + eps_clip;
+    const float rc = fminf(fmaxf(ratio, lo), hi);
+    const float s1 = ratio * A, s2 = rc * A;
+    acc[0] += fminf(s1, s2);
+    acc[1] += (ratio < lo || ratio > hi) ? 1.f : 0.f;
+    if (adv_used != nullptr) adv_used[b] = A;
+    if (dlogp != nullptr) {
+      const float g1 = A * ratio;                                        // d s1 / d logp
+      const float g2 = (ratio >= lo && ratio <= hi) ? A * ratio : 0.f;   // d s2 / d logp (clamp passes inside only)
+      float g;
+      if (s1 < s2) g = g1;
+      else if (s1 > s2) g = g2;
+      else g = 0.5f * g1 + 0.5f * g2;
+      dlogp[b] = -g * invB;
+    }
+  }
+  block_sum<2>(acc, sm);
+  if (threadIdx.x == 0) { out[0] = -acc[0] * invB; out[1] = acc[1] * invB; }
+}
+
 // GAE as a warp-shuffle reverse scan over affine maps A_t = d_t + c_t * A_{t+1}.
 __global__ void gae_scan_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
                                 const float* __restrict__ notdone, int B, int T, float gamma, float lam,
@@ -339,6 +425,23 @@ extern "C" int lr2_rank_sample(const float* scores, const float* u, int B, int n
   if (B <= 0 || n <= 0) return LR2_ERR_BAD_SHAPE;
   if (!greedy && u == nullptr) return LR2_ERR_BAD_SHAPE;
   rank_sample_kernel<<<(B + 127) / 128, 128, 0, S_(stream)>>>(scores, u, B, n, greedy, perm, logprob); LR2_LAUNCHED(1);
+  LR2_RETURN_LAUNCH();
+}
+extern "C" int lr2_rank_logprob(const float* scores, const long long* perm, int B, int n, const float* dlogprob,
+                                float* logprob, float* dscores, int* inv_scratch, void* stream) {
+  if (B <= 0 || n <= 0) return LR2_ERR_BAD_SHAPE;
+  if (scores == nullptr || perm == nullptr || inv_scratch == nullptr) return LR2_ERR_BAD_SHAPE;
+  rank_logprob_kernel<<<(B + 127) / 128, 128, 0, S_(stream)>>>(scores, perm, B, n, dlogprob, logprob, dscores,
+                                                               inv_scratch); LR2_LAUNCHED(1);
+  LR2_RETURN_LAUNCH();
+}
+extern "C" int lr2_ppo_clip_surrogate(const float* logp, const float* logp_old, const float* adv, int B, float eps_clip,
+                                      int normalize, float norm_eps, float* out, float* dlogp, float* adv_used,
+                                      void* stream) {
+  if (B <= 0 || eps_clip < 0.f) return LR2_ERR_BAD_SHAPE;
+  if (logp == nullptr || logp_old == nullptr || adv == nullptr || out == nullptr) return LR2_ERR_BAD_SHAPE;
+  ppo_clip_surrogate_kernel<<<1, PL_THREADS, 0, S_(stream)>>>(logp, logp_old, adv, B, eps_clip, normalize, norm_eps, out,
+                                                              dlogp, adv_used); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 extern "C" int lr2_gae_scan(const float* rewards, const float* values, const float* notdone, int B, int T,

@@ -105,3 +105,49 @@ class RankLoss(torch.nn.Module):
         # loss = rank_loss * mean|A| with A = 1 - 0 = 1  ->  equals the rank loss, gradients included
         loss, _, _, _, _, _ = ppo_policy_loss(scores, scores.detach(), one, zero, indices, 0.0, 0.0, self.margin, -0.1)
         return loss
+
+
+# ---- north_star extensions (no counterpart in the reference's configuration: it ranks greedily and never reads
+# --eps_clip; they complete the sampled-ranking PPO update the north_star names) ------------------------------------
+class _RankLogProbFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scores, perm):
+        s = scores.detach().float().contiguous()
+        ctx.save_for_backward(s, perm.contiguous())
+        return ops.rank_logprob(s, perm.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        s, perm = ctx.saved_tensors
+        _, ds = ops.rank_logprob(s, perm, dlogprob=g.float().contiguous(), want_grad=True)
+        return ds, None
+
+
+def rank_logprob(scores, perm):
+    """Plackett-Luce log-probability [B] of the rankings `perm` [B,n] (e.g. from ops.rank_sample) under `scores`
+    [B,n]; differentiable in scores.  Evaluated on the scores that produced the sample it equals the sampler's own
+    logprob bit for bit."""
+    return _RankLogProbFn.apply(scores, perm)
+
+
+class _ClipSurrogateFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logp, logp_old, adv, eps_clip, normalize, norm_eps):
+        r = ops.ppo_clip_surrogate(logp.detach().float().contiguous().view(-1), logp_old.float().contiguous().view(-1),
+                                   adv.float().contiguous().view(-1), eps_clip, normalize, norm_eps)
+        ctx.save_for_backward(r["dlogp"])
+        ctx.shape = logp.shape
+        ctx.mark_non_differentiable(r["clip_frac"])
+        return r["loss"], r["clip_frac"]
+
+    @staticmethod
+    def backward(ctx, g, _):
+        (dl,) = ctx.saved_tensors
+        return (dl * g).view(ctx.shape), None, None, None, None, None
+
+
+def ppo_clip_surrogate(logp, logp_old, advantages, eps_clip=0.2, normalize=False, norm_eps=1e-5):
+    """-mean(min(ratio * A, clamp(ratio, 1 - eps, 1 + eps) * A)), ratio = exp(logp - logp_old); returns
+    (loss, clipped fraction).  normalize applies the reference's (unused) masked_normalize to the advantages
+    (finetune/ppo.py:485-491).  Gradient flows to logp only."""
+    return _ClipSurrogateFn.apply(logp, logp_old, advantages, eps_clip, normalize, norm_eps)

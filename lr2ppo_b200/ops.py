@@ -355,6 +355,37 @@ def rank_sample(scores, u=None, greedy=False):
     return perm, lp
 
 
+def rank_logprob(scores, perm, dlogprob=None, want_grad=False):
+    """Plackett-Luce log-probability of the rankings perm i64 [B,n] under scores f32 [B,n] -> lp f32 [B]
+    (+ dscores f32 [B,n] = dlogprob * d lp / d scores when want_grad)."""
+    L = _L()
+    _cuda(scores, f32, "scores"); _cuda(perm, i64, "perm"); _cuda(dlogprob, f32, "dlogprob")
+    B, n = scores.shape
+    if perm.shape != (B, n):
+        raise _lib.Lr2Error("perm must have the shape of scores")
+    lp = torch.empty(B, dtype=f32, device=scores.device)
+    ds = torch.empty((B, n), dtype=f32, device=scores.device) if want_grad else None
+    inv = torch.empty((B, n), dtype=torch.int32, device=scores.device)
+    _lib.run(L.lr2_rank_logprob, ptr(scores), ptr(perm), B, n, ptr(dlogprob), ptr(lp), ptr(ds), ptr(inv), _lib.stream())
+    return (lp, ds) if want_grad else lp
+
+
+def ppo_clip_surrogate(logp, logp_old, adv, eps_clip=0.2, normalize=False, norm_eps=1e-5, want_grad=True):
+    """-> dict(loss, clip_frac, dlogp [B] | None, adv [B] as used)."""
+    L = _L()
+    for t, nm in ((logp, "logp"), (logp_old, "logp_old"), (adv, "adv")):
+        _cuda(t, f32, nm)
+    B = logp.numel()
+    if logp_old.numel() != B or adv.numel() != B:
+        raise _lib.Lr2Error("logp, logp_old and adv must have the same number of rows")
+    out = torch.empty(2, dtype=f32, device=logp.device)
+    dl = torch.empty(B, dtype=f32, device=logp.device) if want_grad else None
+    used = torch.empty(B, dtype=f32, device=logp.device)
+    _lib.run(L.lr2_ppo_clip_surrogate, ptr(logp), ptr(logp_old), ptr(adv), B, float(eps_clip), int(bool(normalize)),
+                                   float(norm_eps), ptr(out), ptr(dl), ptr(used), _lib.stream())
+    return dict(loss=out[0], clip_frac=out[1], dlogp=dl, adv=used)
+
+
 def gae_scan(rewards, values, gamma, lam, notdone=None):
     L = _L()
     _cuda(rewards, f32); _cuda(values, f32); _cuda(notdone, f32)

@@ -466,3 +466,44 @@ def gen_trad_stage3():
 
 if __name__ == "__main__" and "trad_stage3" in sys.argv[1:]:
     gen_trad_stage3()
+
+
+def gen_ppo_helpers():
+    """The PaLM-rlhf-style helpers the reference keeps next to its update (finetune/ppo.py:431-491: log, log_prob,
+    masked_entropy, masked_kl_div, masked_normalize) run on seeded inputs: they pin the pieces from which the
+    north_star's ratio-clipped surrogate and sampled-ranking log-probability are restated (oracle/restate.py), since the
+    reference has no implementation of either.  Also pins a torch.autograd value of the clipped surrogate composed
+    from those helpers exactly as PaLM-rlhf composes them."""
+    ppo = ref_loader.load("ppo")
+    g = torch.Generator().manual_seed(4321)
+    out = {"normalize": [], "log_prob": [], "kl": [], "entropy": [], "surrogate": []}
+    for B in (1, 2, 24, 200):
+        t = torch.randn(B, generator=g) * 3 + 1
+        out["normalize"].append(dict(t=tl(t), out=tl(ppo.masked_normalize(t))))
+    out["normalize"].append(dict(t=[0.5, 0.5, 0.5], out=tl(ppo.masked_normalize(torch.tensor([0.5, 0.5, 0.5])))))
+    for B, n in ((3, 2), (5, 7)):
+        s = torch.randn(B, n, generator=g)
+        p = torch.softmax(s, -1)
+        q = torch.softmax(torch.randn(B, n, generator=g), -1)
+        out["log_prob"].append(dict(p=tl(p), out=tl(ppo.log_prob(p))))
+        out["kl"].append(dict(p=tl(p), q=tl(q), out=tl(ppo.masked_kl_div(p, q))))
+        out["entropy"].append(dict(p=tl(p), out=tl(ppo.masked_entropy(p))))
+    for B, eps, normalize in ((24, 0.2, True), (24, 0.2, False), (7, 0.05, True), (1, 0.2, False)):
+        logp = (torch.randn(B, generator=g) * 0.3).requires_grad_(True)
+        logp_old = torch.randn(B, generator=g) * 0.3
+        adv = torch.randn(B, generator=g)
+        a = ppo.masked_normalize(adv) if normalize else adv
+        ratios = (logp - logp_old).exp()
+        surr1 = ratios * a
+        surr2 = ratios.clamp(1 - eps, 1 + eps) * a
+        loss = (-torch.min(surr1, surr2)).mean()
+        loss.backward()
+        out["surrogate"].append(dict(logp=tl(logp), logp_old=tl(logp_old), adv=tl(adv), eps=eps, normalize=normalize,
+                                     loss=float(loss), dlogp=tl(logp.grad)))
+    with open(os.path.join(GOLD, "ppo_helpers.json"), "w") as f:
+        json.dump(out, f)
+    print("ppo_helpers.json written")
+
+
+if __name__ == "__main__" and "ppo_helpers" in sys.argv[1:]:
+    gen_ppo_helpers()

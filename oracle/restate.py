@@ -191,3 +191,36 @@ def tencent_layernorm(x, gamma, beta, eps=1e-6):
     mean = x.mean(-1, keepdim=True)
     std = x.std(-1, keepdim=True)
     return gamma * (x - mean) / (std + eps) + beta
+
+
+# ---- north_star extensions: Plackett-Luce log-probability of a ranking and the ratio-clipped surrogate ------------
+def masked_normalize(t, eps=1e-5):
+    """ref: finetune/ppo.py:485-491 (dead code in the reference; mask / dim are ignored there too)."""
+    mean = t.mean()
+    c = t - mean
+    var = (c ** 2).mean()
+    return c * var.clamp(min=eps).rsqrt()
+
+
+def rank_logprob(scores, perm):
+    """log P(perm | scores) under the sequential masked-softmax (Plackett-Luce) model of oracle_rank_sample, as a
+    differentiable torch expression (fp32): sum_t [ s[pi_t] - logsumexp_{j >= t} s[pi_j] ]."""
+    s = torch.gather(scores, 1, perm)                       # scores in ranking order
+    n = s.shape[1]
+    lp = torch.zeros(s.shape[0], dtype=s.dtype)
+    for t in range(n):
+        lp = lp + s[:, t] - torch.logsumexp(s[:, t:], dim=1)
+    return lp
+
+
+def ppo_clip_surrogate(logp, logp_old, adv, eps_clip=0.2, normalize=False, norm_eps=1e-5):
+    """PaLM-rlhf-style clipped surrogate built from the reference's helpers (log: finetune/ppo.py:431-432,
+    masked_normalize: :485-491); the reference itself never reads --eps_clip (finetune/ppo.py:730).
+    Returns (loss, clipped fraction); differentiable in logp."""
+    a = masked_normalize(adv, norm_eps) if normalize else adv
+    ratio = (logp - logp_old).exp()
+    s1 = ratio * a
+    s2 = ratio.clamp(1 - eps_clip, 1 + eps_clip) * a
+    loss = -torch.min(s1, s2).mean()
+    frac = ((ratio < 1 - eps_clip) | (ratio > 1 + eps_clip)).float().mean()
+    return loss, frac

@@ -1,0 +1,87 @@
+"""GPU parity of the north_star extensions lr2_rank_logprob / lr2_ppo_clip_surrogate against the oracle restatements
+(tests/test_surrogate_cpu.py pins those to the reference's helpers).  Tolerance 1e-5 (fp32), bit-exact where the
+kernel repeats the sampler's arithmetic.
+
+These two kernels were written after the round's GPU budget was spent: until their first run on a B200 the tests are
+opt-in (LR2_UNVALIDATED=1 python -m pytest tests/test_surrogate_gpu.py); DESIGN.md 6a tracks it."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("LR2_UNVALIDATED") != "1",
+                                 reason="kernels not yet run on a GPU; set LR2_UNVALIDATED=1 (DESIGN.md 6a)")]
+
+from lr2ppo_b200 import losses, ops
+from oracle import restate
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+H = json.load(open(os.path.join(ROOT, "tests", "golden", "ppo_helpers.json")))
+
+
+def cu(x, dtype=torch.float32):
+    return torch.tensor(x, dtype=dtype, device="cuda")
+
+
+@pytest.mark.parametrize("B,n", [(1, 1), (24, 2), (48, 5), (300, 20), (7, 64)])
+def test_rank_logprob_reproduces_the_sampler_bit_exactly(B, n):
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + n)
+    scores = torch.randn(B, n, generator=g, device="cuda")
+    u = torch.rand(B, n, generator=g, device="cuda")
+    perm, lp = ops.rank_sample(scores, u)
+    got = ops.rank_logprob(scores, perm)
+    assert torch.equal(got, lp)                                   # same arithmetic step by step: ratio == 1 exactly
+    ref = restate.rank_logprob(scores.cpu(), perm.cpu())
+    assert torch.allclose(got.cpu(), ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,n", [(24, 2), (48, 5), (9, 20)])
+def test_rank_logprob_gradient_vs_oracle(B, n):
+    g = torch.Generator().manual_seed(B + n)
+    scores = torch.randn(B, n, generator=g)
+    perm = torch.stack([torch.randperm(n, generator=g) for _ in range(B)])
+    up = torch.randn(B, generator=g)
+    x = scores.clone().requires_grad_(True)
+    (restate.rank_logprob(x, perm) * up).sum().backward()
+    y = scores.cuda().requires_grad_(True)
+    (losses.rank_logprob(y, perm.cuda()) * up.cuda()).sum().backward()
+    assert torch.allclose(y.grad.cpu(), x.grad, rtol=1e-5, atol=1e-5)
+
+
+def test_clip_surrogate_golden_and_oracle():
+    for c in H["surrogate"]:
+        r = ops.ppo_clip_surrogate(cu(c["logp"]), cu(c["logp_old"]), cu(c["adv"]), c["eps"], c["normalize"])
+        assert abs(float(r["loss"]) - c["loss"]) <= 1e-5 * max(1.0, abs(c["loss"]))
+        assert torch.allclose(r["dlogp"].cpu(), torch.tensor(c["dlogp"]), rtol=1e-5, atol=1e-6)
+    g = torch.Generator().manual_seed(5)
+    for B, eps, normalize in ((48, 0.2, True), (1000, 0.1, False), (3, 0.2, True)):
+        logp, logp_old, adv = (torch.randn(B, generator=g) * 0.4 for _ in range(3))
+        x = logp.clone().requires_grad_(True)
+        loss, frac = restate.ppo_clip_surrogate(x, logp_old, adv, eps, normalize)
+        loss.backward()
+        y = logp.cuda().requires_grad_(True)
+        gl, gf = losses.ppo_clip_surrogate(y, logp_old.cuda(), adv.cuda(), eps, normalize)
+        gl.backward()
+        assert abs(float(gl) - float(loss)) <= 1e-5 * max(1.0, abs(float(loss)))
+        assert abs(float(gf) - float(frac)) < 1e-6
+        assert torch.allclose(y.grad.cpu(), x.grad, rtol=1e-5, atol=1e-6)
+
+
+def test_sampled_ranking_ppo_step_end_to_end():
+    """sample -> (new scores) -> log-prob -> ratio-clipped surrogate -> gradient on the scores, all on the device."""
+    g = torch.Generator(device="cuda").manual_seed(11)
+    B, n = 48, 5
+    scores_old = torch.randn(B, n, generator=g, device="cuda")
+    perm, lp_old = ops.rank_sample(scores_old, torch.rand(B, n, generator=g, device="cuda"))
+    adv = torch.randn(B, generator=g, device="cuda")
+    s = (scores_old + 0.05 * torch.randn(B, n, generator=g, device="cuda")).requires_grad_(True)
+    loss, frac = losses.ppo_clip_surrogate(losses.rank_logprob(s, perm), lp_old, adv, 0.2, normalize=True)
+    loss.backward()
+    x = s.detach().cpu().requires_grad_(True)
+    rl, _ = restate.ppo_clip_surrogate(restate.rank_logprob(x, perm.cpu()), lp_old.cpu(), adv.cpu(), 0.2, True)
+    rl.backward()
+    assert abs(float(loss) - float(rl)) <= 1e-5 * max(1.0, abs(float(rl)))
+    assert torch.allclose(s.grad.cpu(), x.grad, rtol=1e-4, atol=1e-6)
