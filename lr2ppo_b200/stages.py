@@ -10,26 +10,37 @@ from . import losses
 from .ndcg import AverageNDCGMeter
 
 
-def pointwise_train_model(args, model, optimizer, scheduler, text_emb_batch, img_emb_batch, tgts_batch):
-    """loss = SmoothL1(beta 0.3)(logits, tgts); backward; AdamW; scheduler (per batch)."""
+def _step(grad_sync, model, optimizer):
+    """optimizer.step(); with grad_sync (dist.GradSync attached to `model`): gradient averaging over the ranks first —
+    out_layer.fc1 from all-gathered wgrad operands, everything else through the flat all-reduce bucket that runs
+    under the fc1 AdamW pass (same helper as stage 3)."""
+    from .ppo import _sync_and_step
+    _sync_and_step(grad_sync, model, optimizer)()
+
+
+def pointwise_train_model(args, model, optimizer, scheduler, text_emb_batch, img_emb_batch, tgts_batch,
+                          grad_sync=None):
+    """loss = SmoothL1(beta 0.3)(logits, tgts); backward; AdamW; scheduler (per batch).  grad_sync=None keeps the
+    reference's independent replicas; a dist.GradSync averages the gradients (north_star)."""
     model.zero_grad()
     loss, _ = model(text_emb_batch, img_emb_batch, tgts_batch)
     loss.backward()
-    optimizer.step()
+    _step(grad_sync, model, optimizer)
     scheduler.step()
     return loss
 
 
 def reward_train_model(args, model, optimizer, scheduler, text_emb_batch, img_emb_batch, tgts_batch,
-                       chosen_index_batch, reject_index_batch, margin=1.0):
+                       chosen_index_batch, reject_index_batch, margin=1.0, grad_sync=None):
     """Two forwards (chosen / reject 4-slot orderings) -> hinge relu(m - (c - r)).mean() -> one backward.
-    Returns (loss, acc) like the reference."""
+    Returns (loss, acc) like the reference.  grad_sync: see pointwise_train_model (BASELINE configs[2], data-parallel
+    stage 2: both backward passes accumulate the fc1 gradient from all-gathered operands, the rest is all-reduced)."""
     model.zero_grad()
     chosen = model(text_emb_batch, img_emb_batch, tgts_batch, chosen_index_batch)
     reject = model(text_emb_batch, img_emb_batch, tgts_batch, reject_index_batch)
     loss, acc = losses.pair_hinge_loss(chosen, reject, margin)
     loss.backward()
-    optimizer.step()
+    _step(grad_sync, model, optimizer)
     scheduler.step()
     return loss, acc
 
