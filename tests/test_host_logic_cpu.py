@@ -91,3 +91,33 @@ def test_adamw_chunk_span_arithmetic():
     launched = sorted([early] + late)
     covered = [c for a, n in launched for c in range(a, a + n)]
     assert covered == list(range(0, 20)) + list(range(40, 50)) + list(range(60, 100))     # once each, foreign rows never
+
+
+def test_checkpoint_contract_key_names_order_shapes_fp32():
+    """state_dict key names / shapes / fp32 are the checkpoint contract (strict=True loads at
+    finetune/ppo.py:361,371).  tests/golden_util.param_specs lists the reference's keys (test_oracle_cpu loads them into
+    the imported reference modules with strict=True); here the product modules must expose exactly the same keys, in
+    the same order, with the same shapes, as fp32 — on CPU, no kernel involved."""
+    import argparse
+    import torch
+    from lr2ppo_b200 import models, ppo
+    from tests import golden_util
+    cfg = golden_util.FUSION_CFG
+    args = argparse.Namespace(mode="reg", labels_num=3, seq_length=cfg["seq_length"], max_imgs=cfg["max_imgs"],
+                              visual_feat_dim=cfg["feat"])
+    for kind, cls in (("actor", models.Actor), ("reward", models.Reward)):
+        m = cls(args, args)
+        sd = m.state_dict()
+        specs = golden_util.param_specs(kind, cfg)
+        assert list(sd.keys()) == [n for n, _ in specs]
+        assert [tuple(v.shape) for v in sd.values()] == [tuple(s) for _, s in specs]
+        assert all(v.dtype == torch.float32 for v in sd.values())
+        assert sd["out_layer.fc1.weight"].shape == (3072, 162816)
+        if kind == "actor":
+            # stage-3 file = actor.* + critic.* (finetune/ppo.py:912-914 saves the ActorCritic)
+            ac = ppo.ActorCritic.__new__(ppo.ActorCritic)
+            torch.nn.Module.__init__(ac)
+            ac.actor = m
+            assert all(k.startswith("actor.") for k in ac.state_dict())
+            assert [k[len("actor."):] for k in ac.state_dict()] == list(sd.keys())
+        del m, sd
