@@ -121,3 +121,27 @@ def test_checkpoint_contract_key_names_order_shapes_fp32():
             assert all(k.startswith("actor.") for k in ac.state_dict())
             assert [k[len("actor."):] for k in ac.state_dict()] == list(sd.keys())
         del m, sd
+
+
+def test_tower_checkpoint_contract_names_and_shapes():
+    """The TencentPretrain towers built by lr2ppo_b200.tower.build_model carry the reference's parameter names and
+    shapes (tests/golden/tower.pt stores the reference's named_parameters() list of both towers)."""
+    import argparse
+    import os
+    import torch
+    from lr2ppo_b200 import tower
+    from tests import golden_util
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "tower.pt"))
+    vit = dict(emb_size=768, feedforward_size=3072, hidden_size=768, hidden_act="gelu", heads_num=12, layers_num=12,
+               dropout=0.1, max_seq_length=197, embedding=["patch", "pos"], remove_embedding_layernorm=True,
+               encoder="transformer", mask="fully_visible", layernorm_positioning="pre", image_height=224,
+               image_width=224, patch_size=16)
+    roberta = dict(emb_size=768, feedforward_size=3072, hidden_size=768, hidden_act="gelu", heads_num=12,
+                   layers_num=12, max_seq_length=514, dropout=0.1, embedding=["word", "pos", "seg"],
+                   encoder="transformer", mask="fully_visible")
+    for kind, cfg in (("vit", vit), ("roberta", roberta)):
+        model = tower.build_model(argparse.Namespace(**cfg), vocab_size=golden_util.TOWER_VOCAB)
+        got = [(n, tuple(p.shape)) for n, p in model.named_parameters()]
+        want = [(n, tuple(s)) for n, s in gold[kind]["names"]]
+        assert dict(got) == dict(want), set(dict(got)) ^ set(dict(want))
+        assert all(p.dtype == torch.float32 for p in model.parameters())
