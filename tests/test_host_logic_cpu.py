@@ -145,3 +145,19 @@ def test_tower_checkpoint_contract_names_and_shapes():
         want = [(n, tuple(s)) for n, s in gold[kind]["names"]]
         assert dict(got) == dict(want), set(dict(got)) ^ set(dict(want))
         assert all(p.dtype == torch.float32 for p in model.parameters())
+
+
+def test_trad_checkpoint_contract():
+    """MSLR ("trad") variants: same key contract against the reference's key list (golden_util.trad_param_specs,
+    loaded strict=True into the imported reference modules by test_oracle_cpu)."""
+    import argparse
+    import torch
+    from lr2ppo_b200 import trad
+    from tests import golden_util
+    args = argparse.Namespace(mode="reg", labels_num=5)
+    for kind, cls in (("actor", trad.Actor), ("critic", trad.Critic), ("reward", trad.Reward)):
+        sd = cls(args, args).state_dict()
+        specs = golden_util.trad_param_specs(kind)
+        assert list(sd.keys()) == [n for n, _ in specs]
+        assert [tuple(v.shape) for v in sd.values()] == [tuple(s) for _, s in specs]
+        assert all(v.dtype == torch.float32 for v in sd.values())
