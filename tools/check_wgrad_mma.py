@@ -26,7 +26,8 @@ def main():
     hyper = torch.tensor(HYPER, dtype=torch.float32, device=dev)
     g = torch.Generator(device=dev).manual_seed(0)
     impl = os.environ.get("LR2_WGRAD_ADAMW_IMPL", "tcgen05")
-    for K, out_f, in_f in ((48, 64, 1152), (40, 32, 256), (16, 16, 128)):
+    shapes = ((48, 64, 1152), (40, 32, 256), (16, 16, 128)) if impl == "mma" else ((48, 256, 1280), (40, 128, 256))
+    for K, out_f, in_f in shapes:      # (the tcgen05 implementation works on 128-row x 128/256-column tiles)
         dy = (torch.randn(K, out_f, generator=g, device=dev) * 0.1).bfloat16()
         x = torch.randn(K, in_f, generator=g, device=dev).bfloat16()
         p = torch.randn(out_f, in_f, generator=g, device=dev)
