@@ -1,9 +1,6 @@
 """GPU parity of the north_star extensions lr2_rank_logprob / lr2_ppo_clip_surrogate against the oracle restatements
 (tests/test_surrogate_cpu.py pins those to the reference's helpers).  Tolerance 1e-5 (fp32), bit-exact where the
-kernel repeats the sampler's arithmetic.
-
-These two kernels were written after the round's GPU budget was spent: until their first run on a B200 the tests are
-opt-in (LR2_UNVALIDATED=1 python -m pytest tests/test_surrogate_gpu.py); DESIGN.md 6a tracks it."""
+kernel repeats the sampler's arithmetic.  First run on a B200 in round 2: 10 / 10 green (gpurun_out/pending/surrogate.log)."""
 import json
 import os
 
@@ -11,9 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("LR2_UNVALIDATED") != "1",
-                                 reason="kernels not yet run on a GPU; set LR2_UNVALIDATED=1 (DESIGN.md 6a)")]
+pytestmark = pytest.mark.gpu
 
 from lr2ppo_b200 import losses, ops
 from oracle import restate
