@@ -182,12 +182,14 @@ int lr2_cast_bf16_to_f32(const void* src, float* dst, long long n, void* stream)
 /* ------------------------------------------------------------- PPO rows --
  * Stage-3 update losses, forward + analytic backward in one launch.
  * ref: finetune/ppo.py:38-55 (RankLoss), :431-432 (log), :544-575 (KL, entropy, advantage, policy loss).
- * s, s_old: [B, n] f32; reward, v_old: [B]; pi: [B, n] i64 (= next_state[:, -n:]).
+ * s, s_old: [B, n] f32; reward, v_old: [B]; pi: [B, k] i64 ranked index list with values in [0, n)
+ * (the update passes next_state[:, -2:], k = 2; RankLoss accepts any k, finetune/ppo.py:43-46).
  * out_scalars[0..3] = {policy_loss, rank_loss, hinge_cnt, sum|adv|}; per-row outputs [B] each;
- * ds = d policy_loss / d s  [B, n].
+ * ds = d policy_loss / d s  [B, n].  An index outside [0, n) is never dereferenced: policy_loss and rank_loss
+ * come back NaN.
  */
 int lr2_ppo_policy_loss(const float* s, const float* s_old, const float* reward, const float* v_old,
-                        const long long* pi, int B, int n, float w_kl, float w_ent, float margin, float adv_eps,
+                        const long long* pi, int B, int n, int k, float w_kl, float w_ent, float margin, float adv_eps,
                         float* out_scalars, float* kl, float* ent, float* reward_adj, float* adv, float* ds,
                         void* stream);
 /* ref: finetune/ppo.py:494-498.  out_loss[0] = mean(max((vc-R)^2,(V-R)^2)); dv = d loss / d V. */

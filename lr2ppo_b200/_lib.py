@@ -53,7 +53,7 @@ SIGNATURES = {
     "lr2_add_pos_bwd": (i32, [vp, vp, i32, i32, i32, vp]),
     "lr2_cast_f32_to_bf16": (i32, [vp, vp, i64, vp]),
     "lr2_cast_bf16_to_f32": (i32, [vp, vp, i64, vp]),
-    "lr2_ppo_policy_loss": (i32, [vp, vp, vp, vp, vp, i32, i32, f32, f32, f32, f32, vp, vp, vp, vp, vp, vp, vp]),
+    "lr2_ppo_policy_loss": (i32, [vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, f32, f32, vp, vp, vp, vp, vp, vp, vp]),
     "lr2_clipped_value_loss": (i32, [vp, vp, vp, i32, f32, vp, vp, vp]),
     "lr2_pair_hinge_loss": (i32, [vp, vp, i32, f32, vp, vp, vp, vp]),
     "lr2_smooth_l1_loss": (i32, [vp, vp, i64, f32, vp, vp, vp]),

@@ -35,12 +35,24 @@ __device__ __forceinline__ void block_sum(float (&v)[NV], float* sm /* [NV][PL_T
 __global__ void __launch_bounds__(PL_THREADS)
 ppo_policy_loss_kernel(const float* __restrict__ s, const float* __restrict__ s_old,
                        const float* __restrict__ reward, const float* __restrict__ v_old,
-                       const long long* __restrict__ pi, int B, int n, float w_kl, float w_ent, float margin,
+                       const long long* __restrict__ pi, int B, int n, int kp, float w_kl, float w_ent, float margin,
                        float adv_eps, float* __restrict__ out_scalars, float* __restrict__ kl_out,
                        float* __restrict__ ent_out, float* __restrict__ radj_out, float* __restrict__ adv_out,
                        float* __restrict__ ds) {
   __shared__ float sm[4 * (PL_THREADS / 32)];
+  __shared__ int bad_index;
+  if (threadIdx.x == 0) bad_index = 0;
+  __syncthreads();
   float acc[4] = {0.f, 0.f, 0.f, 0.f};  // sum h, cnt, sum|A|, sum H
+  // pi is [B, kp]: the reference's RankLoss takes any [B, k] index list (finetune/ppo.py:43-46); the update passes
+  // next_state[:, -2:] (k = 2).  An index outside [0, n) never dereferences s: the row is skipped and the loss is NaN.
+  for (int b = threadIdx.x; b < B; b += PL_THREADS) {
+    const long long* pchk = pi + (long long)b * kp;
+    for (int i = 0; i < kp; ++i)
+      if (pchk[i] < 0 || pchk[i] >= n) bad_index = 1;
+  }
+  __syncthreads();
+  const bool bad = bad_index != 0;
   for (int b = threadIdx.x; b < B; b += PL_THREADS) {
     const float* sb = s + (long long)b * n;
     const float* so = s_old + (long long)b * n;
@@ -58,12 +70,12 @@ ppo_policy_loss_kernel(const float* __restrict__ s, const float* __restrict__ s_
     const float radj = reward[b] - kl * w_kl;
     const float A = radj - v_old[b];
     const bool flip = !(A >= adv_eps);
-    const long long* pb = pi + (long long)b * n;
+    const long long* pb = pi + (long long)b * kp;
     float hs = 0.f, hc = 0.f;
-    for (int i = 0; i < n; ++i) {
-      const float si = sb[flip ? pb[n - 1 - i] : pb[i]];
-      for (int j = i + 1; j < n; ++j) {
-        const float sj = sb[flip ? pb[n - 1 - j] : pb[j]];
+    for (int i = 0; i < kp && !bad; ++i) {
+      const float si = sb[flip ? pb[kp - 1 - i] : pb[i]];
+      for (int j = i + 1; j < kp; ++j) {
+        const float sj = sb[flip ? pb[kp - 1 - j] : pb[j]];
         const float h = fmaxf(margin - (si - sj), 0.f);
         hs += h;
         hc += (h > 0.f) ? 1.f : 0.f;
@@ -78,8 +90,8 @@ ppo_policy_loss_kernel(const float* __restrict__ s, const float* __restrict__ s_
   const float invB = 1.f / (float)B;
   if (threadIdx.x == 0) {
     // mean_b(L_rank*|A_b| - w_e*H_b)
-    out_scalars[0] = (L_rank * sum_abs - w_ent * sum_H) * invB;
-    out_scalars[1] = L_rank;
+    out_scalars[0] = bad ? __int_as_float(0x7fc00000) : (L_rank * sum_abs - w_ent * sum_H) * invB;
+    out_scalars[1] = bad ? __int_as_float(0x7fc00000) : L_rank;
     out_scalars[2] = cnt;
     out_scalars[3] = sum_abs;
   }
@@ -111,11 +123,11 @@ ppo_policy_loss_kernel(const float* __restrict__ s, const float* __restrict__ s_
       db[k] = invB * L_rank * sgn * (-w_kl) * dkl - w_ent * invB * dH;
     }
     const bool flip = !(A >= adv_eps);
-    const long long* pb = pi + (long long)b * n;
-    for (int i = 0; i < n; ++i) {
-      const long long oi = flip ? pb[n - 1 - i] : pb[i];
-      for (int j = i + 1; j < n; ++j) {
-        const long long oj = flip ? pb[n - 1 - j] : pb[j];
+    const long long* pb = pi + (long long)b * kp;
+    for (int i = 0; i < kp && !bad; ++i) {
+      const long long oi = flip ? pb[kp - 1 - i] : pb[i];
+      for (int j = i + 1; j < kp; ++j) {
+        const long long oj = flip ? pb[kp - 1 - j] : pb[j];
         if (margin - (sb[oi] - sb[oj]) > 0.f) { db[oi] -= hinge_coef; db[oj] += hinge_coef; }
       }
     }
@@ -388,11 +400,11 @@ using namespace lr2;
 #define S_(x) reinterpret_cast<cudaStream_t>(x)
 
 extern "C" int lr2_ppo_policy_loss(const float* s, const float* s_old, const float* reward, const float* v_old,
-                                   const long long* pi, int B, int n, float w_kl, float w_ent, float margin,
+                                   const long long* pi, int B, int n, int k, float w_kl, float w_ent, float margin,
                                    float adv_eps, float* out_scalars, float* kl, float* ent, float* reward_adj,
                                    float* adv, float* ds, void* stream) {
-  if (B <= 0 || n <= 0) return LR2_ERR_BAD_SHAPE;
-  ppo_policy_loss_kernel<<<1, PL_THREADS, 0, S_(stream)>>>(s, s_old, reward, v_old, pi, B, n, w_kl, w_ent, margin,
+  if (B <= 0 || n <= 0 || k <= 0) return LR2_ERR_BAD_SHAPE;
+  ppo_policy_loss_kernel<<<1, PL_THREADS, 0, S_(stream)>>>(s, s_old, reward, v_old, pi, B, n, k, w_kl, w_ent, margin,
                                                            adv_eps, out_scalars, kl, ent, reward_adj, adv, ds); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }

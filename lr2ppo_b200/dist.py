@@ -22,13 +22,21 @@ class GradSync:
         self._flat = {}
         self._skip = set()
         self._sharded = {}
+        self._dirty = set()       # ids of modules whose non-owned fp32 master rows are stale on this rank
+        self._dirty_opt = set()   # ids of optimizers whose non-owned Adam moment rows are stale on this rank
+        self._opt_of = {}         # id(module) -> optimizer that row-shards it
+        self._guarded = set()
 
     def broadcast_params(self, module):
         """Replicas must start identical once gradients are averaged (rank 0's initialisation wins)."""
         for p in module.parameters():
             dist.broadcast(p.data, 0, group=self.group)
-        for e in self._engines(module):
-            e.bank = type(e.bank)()      # bf16 shadows are re-cast from the broadcast weights
+        # `.data` writes do not bump version counters: mark every bf16 copy stale.  The bank object and its tensors
+        # are kept (they may already be registered with an optimizer); the re-cast lands in them in place.
+        for m in module.modules():
+            for bank in (getattr(getattr(m, "_engine", None), "bank", None), getattr(m, "_bank", None)):
+                if bank is not None:
+                    bank.invalidate()
 
     @staticmethod
     def _engines(module):
@@ -80,8 +88,31 @@ class GradSync:
                 e.fc1_rows = (rank * rows, (rank + 1) * rows)
                 optimizer.set_window(w, rank, self.world)
                 self._sharded[id(module)] = (e, w)
+                if id(module) not in self._guarded:
+                    # state_dict() of a module whose foreign rows are stale would silently save torn weights:
+                    # refuse until consolidate() ran (checkpoint.save_sharded reads only the owned rows and opts out)
+                    module.register_state_dict_pre_hook(self._refuse_stale_state_dict)
+                    self._guarded.add(id(module))
+                self._opt_of[id(module)] = optimizer
+                if id(optimizer) not in self._guarded and hasattr(optimizer, "register_state_dict_pre_hook"):
+                    optimizer.register_state_dict_pre_hook(self._refuse_stale_optimizer_state)
+                    self._guarded.add(id(optimizer))
         optimizer.grad_scale = 1.0 / self.world
         optimizer._hyper.clear()
+
+    def _refuse_stale_state_dict(self, module, prefix, keep_vars):
+        if id(module) in self._dirty and not getattr(module, "_lr2_sharded_save", False):
+            raise RuntimeError(
+                "state_dict() of a module with a row-sharded out_layer.fc1: the fp32 master rows owned by other ranks "
+                "are stale on this rank.  Call GradSync.consolidate(module, optimizer) first, or save with "
+                "checkpoint.save_sharded(..., row_shards=GradSync.row_shards(module)).")
+
+    def _refuse_stale_optimizer_state(self, optimizer):
+        if id(optimizer) in self._dirty_opt and not getattr(optimizer, "_lr2_sharded_save", False):
+            raise RuntimeError(
+                "state_dict() of an optimizer that row-shards out_layer.fc1: the Adam moments of rows owned by other "
+                "ranks are stale on this rank.  Call GradSync.consolidate(module, optimizer) first, or save with "
+                "checkpoint.save_sharded.")
 
     def after_step(self, module):
         """After optimizer.step(): start the in-place all-gather of the updated bf16 shadow rows of a row-sharded
@@ -90,6 +121,9 @@ class GradSync:
         if ent is None:
             return lambda: None
         e, w = ent
+        self._dirty.add(id(module))
+        if id(module) in self._opt_of:
+            self._dirty_opt.add(id(self._opt_of[id(module)]))
         shadow = e.bank.get(w)
         r0, r1 = e.fc1_rows
         work = dist.all_gather_into_tensor(shadow, shadow[r0:r1], group=self.group, async_op=True)
@@ -122,6 +156,9 @@ class GradSync:
             tensors += [st["exp_avg"], st["exp_avg_sq"]]
         for t in tensors:
             dist.all_gather_into_tensor(t, t[r0:r1], group=self.group)
+        self._dirty.discard(id(module))          # master weight complete again: module.state_dict() is safe
+        if optimizer is not None:
+            self._dirty_opt.discard(id(optimizer))
 
     def start(self, module):
         """Begin the SUM all-reduce of every gradient except out_layer.fc1 (whose gradient is already global) on

@@ -31,11 +31,19 @@ LN_EPS = 1e-5          # nn.LayerNorm default
 
 
 class ShadowBank:
-    """bf16 copies of fp32 parameters, re-cast when the parameter was modified through torch
-    (tracked with Tensor._version); FusedAdamW refreshes them in place itself."""
+    """bf16 copies of fp32 parameters, re-cast when the parameter was modified (tracked with Tensor._version).
+    FusedAdamW refreshes the shadows that are registered with it in its own pass and leaves their parameter's
+    version alone; for every other parameter it updates through raw pointers it bumps the version, so the copy
+    held here is re-cast at the next `get`.  A re-cast always lands in the SAME bf16 tensor (shape permitting), so
+    tensors registered with an optimizer / captured in a CUDA graph stay the ones forward reads."""
 
     def __init__(self):
         self._sh = {}
+
+    def invalidate(self):
+        """Mark every copy stale (e.g. after `p.data` was overwritten by a broadcast or a checkpoint load, which do
+        not bump the version counter): the next `get` re-casts in place into the existing bf16 tensor."""
+        self._sh = {k: (sh, None, ptr) for k, (sh, _, ptr) in self._sh.items()}
 
     def get(self, p):
         ent = self._sh.get(id(p))
@@ -247,6 +255,9 @@ class FusionEngine:
         self.bank = ShadowBank()
         self._calls = 0
         self.seed_counter = None   # int64[1] device tensor: dropout seed offset
+        self.dropout_seed = None   # int: dropout seed of the NEXT training forward, incremented by one after each
+                                   # (mask replay / parity tests: the masks become a known function of this value,
+                                   # oracle/philox.py); None = torch.initial_seed()-derived base + the device counter
         self.persistent_grads = False  # keep .grad buffers across steps (see _GradSink); call begin_step() per step
         self._written = set()
         self.fc1_stash = None      # list of (dY, X) when out_layer.fc1 is updated by the fused wgrad+AdamW kernel
@@ -307,6 +318,10 @@ class FusionEngine:
         body_index = None if reuse else index
         items = bs * (Tsrc if reuse else T)
         seed_dev = None
+        if seed is None and self.dropout_seed is not None:
+            seed = int(self.dropout_seed)
+            if train:
+                self.dropout_seed = seed + 1
         if seed is None:
             # dropout seed = host base (torch.initial_seed) + a device-resident counter bumped per training
             # forward, so a CUDA-graph replay of this call sequence still draws fresh masks; backward reads the

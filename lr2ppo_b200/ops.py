@@ -287,7 +287,16 @@ def ppo_policy_loss(s, s_old, reward, v_old, pi, w_kl, w_ent, margin=0.01, adv_e
     for t, nm in ((s, "s"), (s_old, "s_old"), (reward, "reward"), (v_old, "v_old")):
         _cuda(t, f32, nm)
     _cuda(pi, i64, "pi")
+    if s.dim() != 2:
+        raise _lib.Lr2Error("s must be [B, n]")
     B, n = s.shape
+    if s_old.shape != s.shape:
+        raise _lib.Lr2Error(f"s_old must have the shape of s {tuple(s.shape)}, got {tuple(s_old.shape)}")
+    if pi.dim() != 2 or pi.shape[0] != B:
+        raise _lib.Lr2Error(f"pi must be [B, k] with B = {B}, got {tuple(pi.shape)}")
+    k = pi.shape[1]
+    if reward.numel() != B or v_old.numel() != B:
+        raise _lib.Lr2Error(f"reward and v_old must hold B = {B} values")
     dev = s.device
     scal = torch.empty(4, dtype=f32, device=dev)
     kl = torch.empty(B, dtype=f32, device=dev)
@@ -295,7 +304,7 @@ def ppo_policy_loss(s, s_old, reward, v_old, pi, w_kl, w_ent, margin=0.01, adv_e
     radj = torch.empty(B, dtype=f32, device=dev)
     adv = torch.empty(B, dtype=f32, device=dev)
     ds = torch.empty((B, n), dtype=f32, device=dev) if want_grad else None
-    _lib.run(L.lr2_ppo_policy_loss, ptr(s), ptr(s_old), ptr(reward), ptr(v_old), ptr(pi), B, n, float(w_kl),
+    _lib.run(L.lr2_ppo_policy_loss, ptr(s), ptr(s_old), ptr(reward), ptr(v_old), ptr(pi), B, n, k, float(w_kl),
                                 float(w_ent), float(margin), float(adv_eps), ptr(scal), ptr(kl), ptr(ent),
                                 ptr(radj), ptr(adv), ptr(ds), _lib.stream())
     return dict(loss=scal[0], rank_loss=scal[1], hinge_cnt=scal[2], sum_abs_adv=scal[3], kl=kl, entropy=ent,

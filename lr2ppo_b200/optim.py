@@ -156,21 +156,34 @@ class FusedAdamW(Optimizer):
         tab["ptrs"].copy_(ptrs)
         tab["gptrs"] = gptrs
 
+    def _group_t(self, group):
+        """Bias-correction step count of the NEXT update of this group = state[p]['step'] + 1 of its first parameter
+        that has state (the reference keeps it per parameter, tencentpretrain/utils/optimizers.py:379; all
+        parameters of a group step together here).  It lives in the optimizer state, so state_dict() saves it and a
+        resume / GradSync.attach does not restart the correction."""
+        for p in group["params"]:
+            st = self.state.get(p)
+            if st and "step" in st:
+                return int(st["step"]) + 1
+        return 1
+
+    def _hyper_values(self, group, t):
+        beta1, beta2 = group["betas"]
+        lr = group["lr"]
+        step_size = lr
+        if group["correct_bias"]:
+            step_size = lr * math.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+        return (step_size, beta1, beta2, group["eps"], 1.0 - beta1, 1.0 - beta2, self.grad_scale, lr)
+
     def _hyper_buf(self, gi, group, dev):
         """Device-side hyper-parameters of group gi: {step_size, b1, b2, eps, 1-b1, 1-b2, grad_scale, lr}."""
         ent = self._hyper.get(gi)
         if ent is None:
-            ent = {"dev": torch.zeros(8, dtype=torch.float32, device=dev), "host": None, "t": 0}
+            ent = {"dev": torch.zeros(8, dtype=torch.float32, device=dev), "host": None}
             self._hyper[gi] = ent
-        beta1, beta2 = group["betas"]
-        lr = group["lr"]
         if self.frozen_hyper and ent["host"] is not None:
             return ent["dev"]          # inside a captured CUDA graph: the caller refreshes it with update_hyper()
-        ent["t"] += 1
-        step_size = lr
-        if group["correct_bias"]:
-            step_size = lr * math.sqrt(1.0 - beta2 ** ent["t"]) / (1.0 - beta1 ** ent["t"])
-        hv = (step_size, beta1, beta2, group["eps"], 1.0 - beta1, 1.0 - beta2, self.grad_scale, lr)
+        hv = self._hyper_values(group, self._group_t(group))
         if ent["host"] != hv:
             ent["dev"].copy_(torch.tensor(hv, dtype=torch.float32))
             ent["host"] = hv
@@ -186,25 +199,35 @@ class FusedAdamW(Optimizer):
             total += p.numel() * (4 + g.element_size() + 4 + 4 + 4 + 4 + 4 + (2 if id(p) in self._shadows else 0))
         return total
 
+    _PIN_SLOTS = 4
+
     def update_hyper(self):
-        """Recompute lr / bias-correction on the host and upload the 8 floats of every group asynchronously
-        (pinned staging).  Used with CUDA graphs, where `step()` itself must not copy from the host."""
+        """Recompute lr / bias-correction on the host and upload the 8 floats of every group asynchronously.  Used with
+        CUDA graphs, where `step()` itself must not copy from the host (and is not re-run per replay: this call also
+        advances the per-parameter step counts the replay stands for).  The pinned staging is a small ring, each slot
+        guarded by an event recorded after its copy, so a host that runs ahead of the replays never overwrites a
+        buffer whose H2D copy has not executed yet."""
         for gi, group in enumerate(self.param_groups):
             ent = self._hyper.get(gi)
             if ent is None:
                 continue
-            beta1, beta2 = group["betas"]
-            lr = group["lr"]
-            ent["t"] += 1
-            step_size = lr
-            if group["correct_bias"]:
-                step_size = lr * math.sqrt(1.0 - beta2 ** ent["t"]) / (1.0 - beta1 ** ent["t"])
-            hv = (step_size, beta1, beta2, group["eps"], 1.0 - beta1, 1.0 - beta2, self.grad_scale, lr)
+            hv = self._hyper_values(group, self._group_t(group))
+            for p in group["params"]:
+                st = self.state.get(p)
+                if st and "step" in st:
+                    st["step"] += 1
             if ent["host"] != hv:
-                if "pin" not in ent:
-                    ent["pin"] = torch.empty(8, dtype=torch.float32).pin_memory()
-                ent["pin"].copy_(torch.tensor(hv, dtype=torch.float32))
-                ent["dev"].copy_(ent["pin"], non_blocking=True)
+                ring = ent.setdefault("ring", [])
+                k = ent.get("ring_i", 0)
+                if len(ring) <= k:
+                    ring.append((torch.empty(8, dtype=torch.float32).pin_memory(), torch.cuda.Event()))
+                else:
+                    ring[k][1].synchronize()          # the copy that last used this slot has executed
+                pin, ev = ring[k]
+                pin.copy_(torch.tensor(hv, dtype=torch.float32))
+                ent["dev"].copy_(pin, non_blocking=True)
+                ev.record(torch.cuda.current_stream(ent["dev"].device))
+                ent["ring_i"] = (k + 1) % self._PIN_SLOTS
                 ent["host"] = hv
 
     @torch.no_grad()
@@ -265,9 +288,14 @@ class FusedAdamW(Optimizer):
             prepared[k] = (group, live, fused, hyper, tab, sorted(spans))
         if between is not None:
             between()
+        stale = []
         for group, live, fused, hyper, tab, spans in prepared:
             for a, n in spans:
                 launch(tab, hyper, a, n)
+            # the kernel wrote these masters through raw pointers: bump their version counters so that any bf16 copy
+            # NOT refreshed by this pass (engine.ShadowBank entries that were never registered here) is re-cast at
+            # its next use instead of silently freezing the forward weights.  Registered shadows are already fresh.
+            stale += [p for p in live if id(p) not in self._shadows]
             for p in fused:
                 pairs = self._fused[id(p)]()
                 if not pairs:
@@ -286,6 +314,10 @@ class FusedAdamW(Optimizer):
                          out_f, in_f, p.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                          sh.data_ptr() if sh is not None else None, hyper.data_ptr(), float(group["weight_decay"]),
                          _lib.stream())
+                if sh is None:
+                    stale.append(p)
+        if stale:
+            torch._C._increment_version(stale)
         return loss
 
 
@@ -312,6 +344,36 @@ def get_constant_schedule_with_warmup(optimizer, num_warmup_steps, last_epoch=-1
             return float(current_step) / float(max(1.0, num_warmup_steps))
         return 1.0
     return LambdaLR(optimizer, lr_lambda, last_epoch=last_epoch)
+
+
+def decay_groups(named_parameters):
+    """The two parameter groups every stage script builds (finetune/ppo.py:381-393, finetune/pointwise.py:275-282):
+    weight decay 0.01 except for names containing bias / gamma / beta."""
+    named = list(named_parameters)
+    no_decay = ["bias", "gamma", "beta"]
+    return [{"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
+            {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
+
+
+def make_scheduler(args, optimizer):
+    """Scheduler selection of the stage scripts (finetune/pointwise.py:289-296, finetune/ppo.py:405-418)."""
+    sched = getattr(args, "scheduler", "linear")
+    if sched not in str2scheduler:
+        raise ValueError(f"scheduler {sched!r} is outside the LR2PPO hot path (linear / constant / "
+                         "constant_with_warmup are what the scripts can select)")
+    if sched == "constant":
+        return str2scheduler[sched](optimizer)
+    if sched == "constant_with_warmup":
+        return str2scheduler[sched](optimizer, args.train_steps * args.warmup)
+    return str2scheduler[sched](optimizer, args.train_steps * args.warmup, args.train_steps)
+
+
+def attach_shadows(engine, optimizer):
+    """Let the optimizer refresh the engine's bf16 weight copies in its own pass (no separate cast kernels)."""
+    for group in optimizer.param_groups:
+        for p in group["params"]:
+            if p.dim() >= 2 and p.is_cuda:
+                optimizer.register_shadow(p, engine.bank.get(p))
 
 
 str2optimizer = {"adamw": FusedAdamW}

@@ -15,7 +15,7 @@ from . import ops
 from .losses import RankLoss, clipped_value_loss, ppo_policy_loss  # noqa: F401  (re-exported, reference names)
 from .models import Actor, ActorCritic, Critic, Mlp, Reward  # noqa: F401
 from .ndcg import AverageNDCGMeter
-from .optim import str2optimizer, str2scheduler
+from .optim import attach_shadows, decay_groups, make_scheduler, str2optimizer, str2scheduler  # noqa: F401
 
 
 def log(t, eps=1e-20):
@@ -26,24 +26,17 @@ def log(t, eps=1e-20):
 def build_optimizer(args, model):
     """ref: finetune/ppo.py:378-419 — two AdamW optimizers (actor, critic), no decay for bias/gamma/beta,
     linear warm-up schedules.  Returns (optimizer, critic_optimizer, scheduler, critic_scheduler)."""
-    no_decay = ["bias", "gamma", "beta"]
-
-    def groups(named):
-        named = list(named)
-        return [{"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": 0.01},
-                {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
-
     opt_name = getattr(args, "optimizer", "adamw")
     if opt_name not in str2optimizer:
         raise ValueError(f"optimizer {opt_name!r} is outside the LR2PPO hot path (only adamw is used by the scripts)")
-    optimizer = str2optimizer[opt_name](groups(model.actor.named_parameters()), lr=args.learning_rate,
+    optimizer = str2optimizer[opt_name](decay_groups(model.actor.named_parameters()), lr=args.learning_rate,
                                         correct_bias=False)
-    critic_optimizer = str2optimizer[opt_name](groups(model.critic.named_parameters()),
+    critic_optimizer = str2optimizer[opt_name](decay_groups(model.critic.named_parameters()),
                                                lr=args.critic_learning_rate, correct_bias=False)
     for eng, opt in ((getattr(model.actor, "_engine", None), optimizer),
                      (getattr(model.critic, "_engine", None), critic_optimizer)):
-        if eng is None:          # trad (MSLR) models: plain autograd Functions, no fusion engine / bf16 shadows
-            continue
+        if eng is None:          # trad (MSLR) models: plain autograd Functions; FusedAdamW bumps the parameters'
+            continue             # version counters, so their ShadowBank copies are re-cast after every step
         attach_shadows(eng, opt)
         # opt-in: correct, but its drain keeps too few loads in flight today (3.2 TB/s, DESIGN.md §6.3), so it is slower
         # than wgrad + AdamW; LR2_WGRAD_ADAMW_IMPL=mma selects the linear-pass variant (adamw_wgrad.cu)
@@ -51,25 +44,7 @@ def build_optimizer(args, model):
             eng.enable_fused_fc1(opt)
         elif getattr(args, "fc1_grad_bf16", False):
             eng.enable_bf16_fc1_grad(opt)
-    sched = getattr(args, "scheduler", "linear")
-    if sched == "constant":
-        scheduler = str2scheduler[sched](optimizer)
-        critic_scheduler = str2scheduler[sched](critic_optimizer)
-    elif sched == "constant_with_warmup":
-        scheduler = str2scheduler[sched](optimizer, args.train_steps * args.warmup)
-        critic_scheduler = str2scheduler[sched](critic_optimizer, args.train_steps * args.warmup)
-    else:
-        scheduler = str2scheduler[sched](optimizer, args.train_steps * args.warmup, args.train_steps)
-        critic_scheduler = str2scheduler[sched](critic_optimizer, args.train_steps * args.warmup, args.train_steps)
-    return optimizer, critic_optimizer, scheduler, critic_scheduler
-
-
-def attach_shadows(engine, optimizer):
-    """Let the optimizer refresh the engine's bf16 weight copies in its own pass (no separate cast kernels)."""
-    for group in optimizer.param_groups:
-        for p in group["params"]:
-            if p.dim() >= 2 and p.is_cuda:
-                optimizer.register_shadow(p, engine.bank.get(p))
+    return optimizer, critic_optimizer, make_scheduler(args, optimizer), make_scheduler(args, critic_optimizer)
 
 
 @torch.no_grad()

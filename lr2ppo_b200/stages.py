@@ -10,6 +10,26 @@ from . import losses
 from .ndcg import AverageNDCGMeter
 
 
+def build_optimizer(args, model):
+    """ref: finetune/pointwise.py:274-297 == finetune/reward_pair_dataloader.py:321-344 — AdamW (no decay for
+    bias / gamma / beta, correct_bias=False) + the selected schedule.  Returns (optimizer, scheduler).  The fusion
+    engine's bf16 weight copies are registered with the optimizer, which refreshes them in its own pass; stage 1
+    (one backward per step) additionally keeps the out_layer.fc1 gradient in the bf16 side buffer when
+    args.fc1_grad_bf16 is set (stage 2 accumulates two backward passes in fp32 and must not)."""
+    from .optim import attach_shadows, decay_groups, make_scheduler, str2optimizer
+    opt_name = getattr(args, "optimizer", "adamw")
+    if opt_name not in str2optimizer:
+        raise ValueError(f"optimizer {opt_name!r} is outside the LR2PPO hot path (only adamw is used by the scripts)")
+    optimizer = str2optimizer[opt_name](decay_groups(model.named_parameters()), lr=args.learning_rate,
+                                        correct_bias=False)
+    eng = getattr(model, "_engine", None)
+    if eng is not None:
+        attach_shadows(eng, optimizer)
+        if getattr(args, "fc1_grad_bf16", False):
+            eng.enable_bf16_fc1_grad(optimizer)
+    return optimizer, make_scheduler(args, optimizer)
+
+
 def _step(grad_sync, model, optimizer):
     """optimizer.step(); with grad_sync (dist.GradSync attached to `model`): gradient averaging over the ranks first —
     out_layer.fc1 from all-gathered wgrad operands, everything else through the flat all-reduce bucket that runs

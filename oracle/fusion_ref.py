@@ -50,33 +50,43 @@ def xit(sd, pre, x, y, heads=8, masks=None):
     return F.layer_norm(x2, (E,), sd[pre + "1.0.weight"], sd[pre + "1.0.bias"], 1e-5)
 
 
-def fusion_body(sd, text, img):
-    """ref: finetune/ppo.py:214-225 — projections, XiT, concat, out_layer.  text [bs,T,S,E], img [bs,T,I,E]."""
+def _view_masks(masks, keys, n, S):
+    """{site: [n*S, C]} -> {1,2,3: [n, S, C]} for the xit() call that owns sites `keys` (None stays None)."""
+    if masks is None:
+        return None
+    return {i + 1: masks[k].view(n, S, -1) for i, k in enumerate(keys)}
+
+
+def fusion_body(sd, text, img, masks=None):
+    """ref: finetune/ppo.py:214-225 — projections, XiT, concat, out_layer.  text [bs,T,S,E], img [bs,T,I,E].
+    masks: train mode — {1,2,3: multiplier [bs*T*S, C]} for the three nn.Dropout(0.1) of `xit` (finetune/xit.py:26-41),
+    as produced by oracle/philox.py; None = eval mode."""
     bs, T, S, E = text.shape
     tf = mlp(sd, "text_proj.", text).reshape(bs * T, S, E)
     imf = mlp(sd, "img_proj.", img).reshape(bs * T, -1, E)
-    x = xit(sd, "xit.", tf, imf)
+    x = xit(sd, "xit.", tf, imf, masks=_view_masks(masks, (1, 2, 3), bs * T, S))
     x = torch.cat([x, imf], dim=1)
     x = mlp(sd, "out_layer.", x.reshape(bs * T, -1))
     return x.view(bs, T, E)
 
 
-def actor_forward(sd, text, img):
+def actor_forward(sd, text, img, masks=None):
     """ref: finetune/ppo.py:214-232 (mode 'reg'): logits [bs*T]."""
-    x = fusion_body(sd, text, img)
+    x = fusion_body(sd, text, img, masks)
     return F.linear(x, sd["head.weight"], sd["head.bias"]).view(-1)
 
 
-def critic_forward(sd, text, img, index):
-    """ref: finetune/ppo.py:265-297 / :318-350 — gather by index, body, + pos_emb, xitt, head, last token."""
+def critic_forward(sd, text, img, index, masks=None):
+    """ref: finetune/ppo.py:265-297 / :318-350 — gather by index, body, + pos_emb, xitt, head, last token.
+    masks (train mode): sites 1-3 for `xit` as in fusion_body, 4-6 [bs*T, C] for `xitt`."""
     bs = text.shape[0]
     bi = torch.arange(bs).view(bs, 1)
     text = text[bi, index]
     img = img[bi, index]
-    x = fusion_body(sd, text, img)
+    x = fusion_body(sd, text, img, masks)
     T = x.shape[1]
     x = x + sd["pos_emb.weight"][:T].unsqueeze(0)
-    x = xit(sd, "xitt.", x, x)
+    x = xit(sd, "xitt.", x, x, masks=_view_masks(masks, (4, 5, 6), bs, T))
     logits = F.linear(x, sd["head.weight"], sd["head.bias"])
     return logits[:, -1].reshape(bs)
 

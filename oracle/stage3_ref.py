@@ -45,13 +45,15 @@ def rollout(actor, critic, reward, text, img):
     return state, next_state, scores, rewards, value
 
 
-def update(actor, critic, memory, text, img, lr_actor, lr_critic, w_kl=0.001, w_ent=0.001, value_clip=0.5):
-    """ref: finetune/ppo.py:518-587 (one stored batch)."""
+def update(actor, critic, memory, text, img, lr_actor, lr_critic, w_kl=0.001, w_ent=0.001, value_clip=0.5,
+           actor_masks=None, critic_masks=None):
+    """ref: finetune/ppo.py:518-587 (one stored batch).  actor_masks / critic_masks: the update runs in train mode in
+    the reference (dropout 0.1 live, :515); pass the replayed masks (oracle/philox.py) to restate that, None = eval."""
     state, next_state, old_scores, rewards, old_value = memory
     bs, T = old_scores.shape
     actor.zero_grad(); critic.zero_grad()
-    scores = fusion_ref.actor_forward(actor.sd, text, img).view(bs, T)
-    value = fusion_ref.critic_forward(critic.sd, text, img, state)
+    scores = fusion_ref.actor_forward(actor.sd, text, img, actor_masks).view(bs, T)
+    value = fusion_ref.critic_forward(critic.sd, text, img, state, critic_masks)
     r = restate.ppo_policy_loss(scores, old_scores, rewards, old_value, next_state[:, -2:], w_kl, w_ent)
     r["loss"].backward()
     actor.adamw(lr_actor)

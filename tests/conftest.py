@@ -20,3 +20,9 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Measured parity errors of this session -> gpurun_out/parity_errors.json (tests/parity.py)."""
+    from tests import parity
+    parity.dump(os.path.join(ROOT, "gpurun_out", "parity_errors.json"))

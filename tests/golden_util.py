@@ -209,3 +209,36 @@ def make_api_state_dict(names, seed):
 def api_input(kind):
     g = torch.Generator().manual_seed(7900 + API_SEEDS[kind])
     return torch.randn(5, 16, 768, generator=g) if kind == "video" else torch.randn(7, 33, 768, generator=g)
+
+
+# ---- round 2: train-mode (replayed dropout masks) and BASELINE-size goldens (oracle/make_golden_r2.py) -----------
+TRAIN_SEEDS = dict(actor=70001, critic=70002, reward=70003)     # engine.FusionEngine.dropout_seed of fusion_train.pt
+S3 = dict(bs=24, tags=2, seed=4242, actor_seed=81001, critic_seed=81002, lr=1e-3, train_steps=100, warmup=0.1)
+S12 = {1: dict(bs=2, tags=20, seed=5151, mask_seed=82001), 2: dict(bs=64, tags=2, seed=5252, mask_seed=82002)}
+
+
+def stage3_inputs():
+    """ppo.sh:21 batch: text [24,2,196,768], img [24,16,768] as the loader yields it (finetune/ppo.py:831), tgts."""
+    g = torch.Generator().manual_seed(S3["seed"])
+    text = torch.randn(S3["bs"], S3["tags"], 196, 768, generator=g)
+    img = torch.randn(S3["bs"], 16, 768, generator=g)
+    tgts = torch.randint(0, 3, (S3["bs"], S3["tags"]), generator=g)
+    return text, img, tgts
+
+
+def stage12_inputs(stage):
+    """pointwise.sh (2 clips x 20 tags) / reward_pair_dataloader.sh (64 pairs, chosen / reject 4-slot sequences)."""
+    c = S12[stage]
+    g = torch.Generator().manual_seed(c["seed"])
+    text = torch.randn(c["bs"], c["tags"], 196, 768, generator=g)
+    img = torch.randn(c["bs"], 16, 768, generator=g)
+    tgts = torch.randint(0, 3, (c["bs"], c["tags"]), generator=g)
+    chosen = reject = None
+    if stage == 2:
+        # finetune/reward_pair_dataloader.py:128-141: [0,1,0,1] / [0,1,1,0] or [1,0,0,1] / [1,0,1,0]
+        flip = torch.rand(c["bs"], generator=g) < 0.5
+        a = torch.tensor([[0, 1, 0, 1], [1, 0, 0, 1]])
+        b = torch.tensor([[0, 1, 1, 0], [1, 0, 1, 0]])
+        chosen = a[flip.long()]
+        reject = b[flip.long()]
+    return text, img, tgts, chosen, reject

@@ -11,7 +11,7 @@ import torch.multiprocessing as mp
 
 class _Eng:
     def __init__(self, m):
-        self.m, self.dp_gather, self.bank = m, None, type("B", (), {})()
+        self.m, self.dp_gather, self.bank = m, None, type("B", (), {"invalidate": lambda self: None})()
 
 
 class _Net(torch.nn.Module):
@@ -96,6 +96,9 @@ class _Bank:
     def __init__(self):
         self.d = {}
 
+    def invalidate(self):       # host stand-in of engine.ShadowBank.invalidate: re-cast in place at the next get()
+        self.stale = True
+
     def get(self, w):
         if id(w) not in self.d:
             self.d[id(w)] = w.detach().to(torch.bfloat16)
@@ -172,6 +175,13 @@ def _shard_worker(rank, world, path, ckdir):
     own = slice(rank * per, (rank + 1) * per)
     stale = torch.ones(w.shape[0], dtype=torch.bool); stale[own] = False
     assert torch.equal(w.detach()[own], full[own]) and torch.equal(w.detach()[stale], w0[stale])   # master: own rows only
+    # the foreign rows are stale now: a plain state_dict() must refuse instead of saving torn weights / moments
+    for obj in (net, opt):
+        try:
+            obj.state_dict()
+            raise AssertionError("state_dict() on stale row shards did not raise")
+        except RuntimeError as e:
+            assert "consolidate" in str(e)
     # sharded checkpoint: no consolidate; every rank writes its rows, rank 0 the rest
     sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0)
     checkpoint.save_sharded(ckdir, {"actor": net}, {"actor": opt}, {"actor": sched}, step=1, rank=rank, world=world,
@@ -188,6 +198,7 @@ def _shard_worker(rank, world, path, ckdir):
     sync.consolidate(net, opt)
     assert torch.equal(w.detach(), full)
     assert torch.equal(opt.state[w]["exp_avg"], 0.1 * grads[id(w)] / world)
+    assert torch.equal(net.state_dict()["out_layer.fc1.weight"], full) and opt.state_dict()["state"]   # allowed again
     dist.barrier()
     dist.destroy_process_group()
 

@@ -8,7 +8,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from tests import golden_util
+from tests import golden_util, parity
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = torch.load(os.path.join(ROOT, "tests", "golden", "fusion.pt"))
@@ -46,31 +46,14 @@ def test_forward_backward_vs_reference_golden(kind):
         logits = model(text, img, tgts, index.cuda())
     gold = GOLD[kind]
     assert logits.dtype == torch.float32 and logits.shape == gold["logits"].shape
-    assert _rel(logits, gold["logits"]) < TOL, (logits, gold["logits"])
+    parity.check(f"fusion[{kind}] bs2x2 eval", "logits", _rel(logits, gold["logits"]), TOL)
     gw = golden_util.out_grad(kind, logits.numel()).cuda()
     (logits * gw).sum().backward()
-    worst = {}
-    rms = {n: gold["gnorm/" + n].item() / max(1.0, p.numel() ** 0.5) for n, p in model.named_parameters()}
-    top = max(rms.values())
-    for name, p in model.named_parameters():
+    named = list(model.named_parameters())
+    for name, p in named:
         assert p.grad is not None and p.grad.dtype == torch.float32, name
-        g = p.grad
-        ref = gold["grad/" + name]
-        got = g if g.numel() <= 4096 else golden_util.grad_sample(g)
-        gn = gold["gnorm/" + name].item()
-        if rms[name] < 1e-4 * top:
-            # mathematically-zero gradients (e.g. keys.bias: softmax is invariant to a per-query shift):
-            # the reference holds fp32 rounding noise; ours must be negligible against real gradients too
-            assert g.double().norm().item() / max(1.0, g.numel() ** 0.5) < 1e-2 * top, name
-            continue
-        # error relative to the gradient's magnitude (max of a 4096-sample, floored by its RMS)
-        scale = max(ref.abs().max().item(), rms[name])
-        err = (got.detach().float().cpu().reshape(-1) - ref.reshape(-1)).abs().max().item() / scale
-        worst[name] = err
-        n_err = abs(g.double().norm().item() - gn) / gn
-        assert n_err < TOL, (name, "norm", n_err)
-    bad = {k: v for k, v in worst.items() if v > 5 * TOL}
-    assert not bad, bad
+    parity.check_param_tensors(f"fusion[{kind}] bs2x2 eval", named, lambda p: p.grad, lambda n: gold["grad/" + n],
+                               lambda n: gold["gnorm/" + n].item(), golden_util.grad_sample)
 
 
 def test_actor_no_grad_and_tgts_none():

@@ -9,7 +9,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from tests import golden_util
+from tests import golden_util, parity
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = os.path.join(ROOT, "tests", "golden")
@@ -21,21 +21,9 @@ def _rel(d, ref):
     return ((d - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
 
 
-def _check_grads(named, getter, gold, prefix, nprefix):
-    rms = {n: gold[nprefix + n].item() / max(1.0, p.numel() ** 0.5) for n, p in named}
-    top = max(rms.values())
-    for n, p in named:
-        got = getter(p)
-        if rms[n] < 1e-4 * top:
-            assert got.double().norm().item() / max(1.0, got.numel() ** 0.5) < 1e-2 * top, n
-            continue
-        ref = gold[prefix + n]
-        gs = got if got.numel() <= 4096 and ref.numel() == got.numel() else golden_util.grad_sample(got, 4096)
-        scale = max(ref.abs().max().item(), rms[n])
-        err = (gs.detach().float().cpu().reshape(-1) - ref.reshape(-1)).abs().max().item() / scale
-        assert err < 5 * TOL, (n, err)
-        nerr = abs(got.double().norm().item() - gold[nprefix + n].item()) / gold[nprefix + n].item()
-        assert nerr < TOL, (n, nerr)
+def _check_grads(test, named, getter, gold, prefix, nprefix):
+    parity.check_param_tensors(test, named, getter, lambda n: gold[prefix + n], lambda n: gold[nprefix + n].item(),
+                               lambda t: golden_util.grad_sample(t, 4096))
 
 
 @pytest.mark.parametrize("kind", ["actor", "critic", "reward"])
@@ -51,9 +39,9 @@ def test_trad_models_vs_reference_golden(kind):
         _, logits = model(text.cuda(), None, tgts.cuda())
     else:
         logits = model(text.cuda(), None, tgts.cuda(), index.cuda())
-    assert _rel(logits, gold["logits"]) < TOL
+    parity.check(f"trad[{kind}]", "logits", _rel(logits, gold["logits"]), TOL)
     (logits * golden_util.out_grad(kind, logits.numel()).cuda()).sum().backward()
-    _check_grads(list(model.named_parameters()), lambda p: p.grad, gold, "grad/", "gnorm/")
+    _check_grads(f"trad[{kind}]", list(model.named_parameters()), lambda p: p.grad, gold, "grad/", "gnorm/")
 
 
 @pytest.mark.parametrize("stage", [1, 2])
@@ -83,8 +71,8 @@ def test_stage_train_step_vs_reference_train_model(stage):
         loss, acc = stages.reward_train_model(args, model, opt, sch, text.cuda(), img.cuda(), tgts.cuda(),
                                               chosen.cuda(), reject.cuda())
         assert abs(acc.item() - gold["acc"].item()) < 1e-6
-    assert abs(loss.item() - gold["loss"].item()) <= TOL * abs(gold["loss"].item())
-    _check_grads(named, lambda p: opt.state[p]["exp_avg"], gold, "m/", "mnorm/")
+    parity.check(f"stage{stage} train step", "loss", abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item()), TOL)
+    _check_grads(f"stage{stage} train step [exp_avg]", named, lambda p: opt.state[p]["exp_avg"], gold, "m/", "mnorm/")
     # parameter update direction: delta = -lr * m/(sqrt(v)+eps) - lr*wd*p ; compare on the sampled entries
     rms = {n: gold["mnorm/" + n].item() / max(1.0, p.numel() ** 0.5) for n, p in named}
     top = max(rms.values())
@@ -110,7 +98,8 @@ def test_api_modules_vs_reference(kind):
     model = model.cuda().eval()
     x = golden_util.api_input(kind).cuda().requires_grad_(True)
     y = model(x)
-    assert y.shape == gold["y"].shape and _rel(y, gold["y"]) < TOL
+    assert y.shape == gold["y"].shape
+    parity.check(f"api[{kind}]", "y", _rel(y, gold["y"]), TOL)
     (y * golden_util.out_grad("critic", y.numel()).view_as(y).cuda()).sum().backward()
-    assert _rel(x.grad, gold["dx"]) < 2 * TOL
-    _check_grads(list(model.named_parameters()), lambda p: p.grad, gold, "grad/", "gnorm/")
+    parity.check(f"api[{kind}]", "dx", _rel(x.grad, gold["dx"]), TOL)
+    _check_grads(f"api[{kind}]", list(model.named_parameters()), lambda p: p.grad, gold, "grad/", "gnorm/")

@@ -10,7 +10,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-from tests import golden_util
+from tests import golden_util, parity
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLD = torch.load(os.path.join(ROOT, "tests", "golden", "tower.pt"))
@@ -41,25 +41,13 @@ def test_tower_forward_backward_vs_reference_golden(kind):
     hidden = model(src.cuda(), None, seg.cuda()).float()
     ref = gold["hidden"]
     err = ((hidden.detach().cpu() - ref).abs().max() / ref.abs().max()).item()
-    assert err < 2e-2, err
+    parity.check(f"tower[{kind}] 12 layers", "hidden", err, 2e-2)
     gw = golden_util.out_grad("actor", hidden.numel()).view_as(hidden).cuda()
     (hidden * gw).sum().backward()
     named = [(n, p) for n, p in model.named_parameters() if ("gnorm/" + n) in gold]
     assert len(named) == len(gold["names"])
-    rms = {n: gold["gnorm/" + n].item() / max(1.0, p.numel() ** 0.5) for n, p in named}
-    top = max(rms.values())
-    for n, p in named:
-        assert p.grad is not None, n
-        if rms[n] < 1e-4 * top:
-            assert p.grad.double().norm().item() / max(1.0, p.numel() ** 0.5) < 1e-2 * top, n
-            continue
-        gref = gold["grad/" + n]
-        got = p.grad if p.grad.numel() <= 4096 else golden_util.grad_sample(p.grad)
-        scale = max(gref.abs().max().item(), rms[n])
-        e = (got.detach().float().cpu().reshape(-1) - gref.reshape(-1)).abs().max().item() / scale
-        assert e < 0.1, (n, e)
-        gn = gold["gnorm/" + n].item()
-        assert abs(p.grad.double().norm().item() - gn) / gn < 3e-2, (n, p.grad.double().norm().item(), gn)
+    parity.check_param_tensors(f"tower[{kind}] 12 layers", named, lambda p: p.grad, lambda n: gold["grad/" + n],
+                               lambda n: gold["gnorm/" + n].item(), golden_util.grad_sample)
 
 
 def test_tower_train_mode_runs():

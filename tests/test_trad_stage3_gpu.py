@@ -12,7 +12,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 from lr2ppo_b200 import ppo, trad
-from tests import golden_util
+from tests import golden_util, parity
 
 GOLD = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "trad_stage3.pt"))
 
@@ -40,13 +40,13 @@ def test_trad_stage3_step_vs_reference_train_model():
     assert torch.equal(next_state.cpu(), ro["next_state"])                        # permutation: bit-exact
     for got, key in ((scores, "action_scores"), (value, "value"), (rewards, "rewards")):
         ref = ro[key]
-        assert (got.float().cpu() - ref).abs().max().item() < 2e-2 * max(ref.abs().max().item(), 0.1), key
+        parity.check("trad stage3", key, (got.float().cpu() - ref).abs().max().item() / max(ref.abs().max().item(), 0.1), 2e-2)
     w_before = [p.detach().clone() for p in model.parameters()]
     model.train()
     stats = trad.train_model(args, model, opt, copt, sch, csch, [mem], 0)
     got = [float(s) for s in stats]
-    for g, r in zip(got, GOLD["stats"]):
-        assert abs(g - r) < 2e-2 * max(abs(r), 0.1), (got, GOLD["stats"])
+    for i, (g, r) in enumerate(zip(got, GOLD["stats"])):
+        parity.check("trad stage3", f"stat[{i}]", abs(g - r) / max(abs(r), 0.1), 2e-2)
     for p, w in zip(model.parameters(), w_before):                                 # lr = 0 on the first step
         assert torch.equal(p.detach(), w)
     checked = 0
@@ -58,10 +58,9 @@ def test_trad_stage3_step_vs_reference_train_model():
             if ref_n < 1e-9:
                 assert n < 1e-6, (tag, name, n)
                 continue
-            assert abs(n - ref_n) / ref_n < 6e-2, (tag, name, n, ref_n)
+            parity.check("trad stage3 [exp_avg]", f"{tag}.{name} [norm]", abs(n - ref_n) / ref_n, parity.NORM_TOL)
             full = GOLD.get(f"mfull/{tag}.{name}")
             if full is not None and ref_n > 1e-7:
-                e = (m1.float().cpu() - full).abs().max().item() / max(full.abs().max().item(), 1e-12)
-                assert e < 0.1, (tag, name, e)
+                parity.check("trad stage3 [exp_avg]", f"{tag}.{name} [elem]", parity.rel_err(m1, full), parity.ELEM_TOL)
             checked += 1
     assert checked > 40
