@@ -31,10 +31,14 @@ FLOP_PER_QUERY = 107.5e9
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)      # ~2 s timed region per leg at 10 ms/step (power steady state)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true",
+                    help="skip the same-B200 stock-eager fp32 (TF32 off) leg of the reference path")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the BASELINE configs[1] / [2] / [4] measurements appended to the JSON line")
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--fp32-fc1-grad", action="store_true",
                     help="materialise the out_layer.fc1 weight gradient in fp32 (.grad) instead of the bf16 side buffer")
@@ -93,7 +97,7 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------ reference arm (CPU oracle port) ------
-def cpu_stage3(steps, warmup, budget_s, threads=None):
+def cpu_stage3(steps, warmup, budget_s, threads=None, keep_models=False):
     """Times oracle/stage3_ref.step on the host cores. Returns dict(value q/s, cores, sample, ms_per_step)."""
     import torch
     from oracle import stage3_ref
@@ -129,10 +133,110 @@ def cpu_stage3(steps, warmup, budget_s, threads=None):
     for _ in range(steps):
         stage3_ref.step(actor, critic, reward, text, img, lr, lr)
     dt = time.perf_counter() - t0
-    return {"value": bs * steps / dt, "unit": "queries/s", "cores": cores, "kind": "port",
+    extra = {"models": (actor, critic, reward)} if keep_models else {}
+    return {**extra, "value": bs * steps / dt, "unit": "queries/s", "cores": cores, "kind": "port",
             "sample": f"{steps} stage-3 steps (rollout+update, full-size 519M/526M/526M-param fp32 models) of "
                       f"{bs} queries each through oracle/stage3_ref.py (torch CPU fp32, {cores} threads); "
                       f"model build {build_s:.0f}s not timed", "ms_per_step": dt / steps * 1e3, "bs": bs}
+
+
+def eager_b200_stage3(torch, dev, models, steps=10, warmup=3):
+    """The like-for-like denominator (SURVEY.md §8d last row): the reference path as stock PyTorch eager fp32 with TF32
+    off on the SAME B200 -- oracle/stage3_ref.py (plain torch: cuBLAS SGEMM + ATen elementwise kernels, the Python
+    per-row loop and per-tensor AdamW loop of the reference included), full batch of 24 queries, device-resident
+    inputs, CUDA-event timed."""
+    from oracle import stage3_ref
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    if models is None:
+        from tests import golden_util
+        models = tuple(stage3_ref.RefModel(golden_util.make_state_dict(k), trainable=(k != "reward"))
+                       for k in ("actor", "critic", "reward"))
+    gpu = []
+    for m in models:
+        trainable = m.m is not None
+        gpu.append(stage3_ref.RefModel({k: v.detach().to(dev) for k, v in m.sd.items()}, trainable=trainable))
+    actor, critic, reward = gpu
+    g = torch.Generator().manual_seed(11)
+    text = torch.randn(BS, TAGS, SEQ, FEAT, generator=g).to(dev)
+    img = torch.randn(BS, 1, IMGS, FEAT, generator=g).repeat(1, TAGS, 1, 1).to(dev)
+    lr = LR * (1.0 / (TRAIN_STEPS * 0.1))
+    for _ in range(warmup):
+        stage3_ref.step(actor, critic, reward, text, img, lr, lr)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        stage3_ref.step(actor, critic, reward, text, img, lr, lr)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    del gpu, actor, critic, reward
+    torch.cuda.empty_cache()
+    return {"value": BS / (ms * 1e-3), "unit": "queries/s", "ms_per_step": ms, "steps": steps,
+            "what": "reference path restated in plain torch (oracle/stage3_ref.py: cuBLAS SGEMM fp32, TF32 off, ATen "
+                    "elementwise, per-row Python loop, per-tensor AdamW loop) on the same B200, 24 queries/step, "
+                    "device-resident inputs"}
+
+
+def other_configs(torch, dist, dev, world, rank, peaks):
+    """BASELINE configs[1], [2], [4] measured in the same run, so that every north_star target can be read off the one
+    JSON line.  configs[2] (stage-2 data parallel) runs on all ranks; the single-GPU ones on rank 0 at N = 1."""
+    from tools import workloads
+    out = {}
+    # ---- configs[2]: stage-2 pairwise reward model, 64 pairs per GPU, data parallel over `world`
+    st2 = workloads.Stage2Step(dev, pairs=64, world=world, rank=rank)
+    from lr2ppo_b200 import stages
+    c0 = _launches()
+    st2()
+    per_step = _launches() - c0
+    gstep = stages.GraphedTrainStep(st2, st2.model, st2.opt, st2.sch, warmup=2)
+    for _ in range(3):
+        gstep.replay()
+    n = 20
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        gstep.replay()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    out["configs[2] stage-2 reward model"] = {
+        "value": world * 64 / (ms * 1e-3), "unit": "pair-samples/s", "ms_per_step": ms, "n_gpus": world,
+        "pairs_per_step_per_gpu": 64, "launches_per_step": per_step, "launch_mode": "cuda_graph_replay",
+        "model_tflops_per_gpu": 129.1e9 * 64 / (ms * 1e-3) / 1e12,
+        "workload": "reward_pair_dataloader.sh: 64 label pairs / GPU, two forwards over 4-slot orderings (2 x 256 "
+                    "items), hinge loss, backward, AdamW over 526 M params, train mode (dropout live)"}
+    del gstep, st2
+    torch.cuda.empty_cache()
+    if world > 1 or rank != 0:
+        return out
+    # ---- configs[1]: encoder towers
+    out["configs[1] encoder towers"] = workloads.encoder_bench(clips=16, iters=5, peaks=peaks)
+    # ---- configs[4]: NDCG@k sweep corners + the headline point
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    pts = {}
+    for N, B in ((16, 64), (16, 4096), (64, 4096), (128, 4096), (1024, 64), (1024, 4096)):
+        sec, byts = workloads.ndcg_point(N, B)
+        pts[f"N{N}_B{B}"] = {"us": round(sec * 1e6, 2), "queries_per_s": round(B / sec), "GB_per_s": round(byts / sec / 1e9, 1),
+                            "frac_of_hbm_peak": round(byts / sec / 1e9 / hbm, 4)}
+    out["configs[4] NDCG@k"] = {"points": pts, "algorithmic_bytes": "B * (N * 12 + 24)", "hbm_peak_gbs": hbm,
+                                "full_sweep": "python bench.py --ndcg-sweep OUT.md (with the CPU oracle beside it)"}
+    return out
+
+
+def _launches():
+    from lr2ppo_b200 import _lib
+    return _lib.launch_count()
 
 
 def workload_config(world, bf16_fc1_grad=True):
@@ -157,9 +261,9 @@ def run_reference(args, rank):
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
-            "config": dict(workload_config(max(1, args.gpus)),
-                           reference_arm=f"CPU oracle port of the reference path (fp32, torch CPU); each step is a "
-                                         f"sample of {r['bs']} of the 24 queries"),
+            "config": workload_config(max(1, args.gpus)),          # identical to the B200 arm's config object
+            "reference_arm": f"CPU oracle port of the reference path (fp32, torch CPU); each step is a sample of "
+                             f"{r['bs']} of the 24 queries",
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -359,6 +463,7 @@ def main():
         for e in (model.actor._engine, model.critic._engine):
             e.persistent_grads = True
     launches_per_step = None
+    gstep = None
     if use_graph:
         for i in range(2):
             eager_step(resident[i])
@@ -457,38 +562,56 @@ def main():
             eager_step(resident[i % len(resident)])
         torch.cuda.synchronize()
         prof, _lib.PROFILE = _lib.PROFILE, None
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):            # driver file absent: the profiling recipe's fallbacks below
+        pass
+    roofline_tensor = None
     if rank == 0 and args.profile_steps > 0:
         groups = summarize_profile(torch, prof, args.profile_steps)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except (OSError, ValueError):
-            pass
         hbm_peak, hbm_src = (peaks["hbm_gbs"], "measured") if "hbm_gbs" in peaks else (6650.0, "fallback")
         tf_peak, tf_src = (peaks["bf16_tflops_sustained"], "measured sustained") if "bf16_tflops_sustained" in peaks \
             else (1400.0, "fallback sustained")
+        tf_burst = peaks.get("bf16_tflops", 1650.0)
         total_ms = sum(gp["ms_per_step"] for gp in groups.values())
-        top = max(groups, key=lambda k: groups[k]["ms"])
-        gp = groups[top]
-        n_params = sum(p.numel() for p in model.parameters())
-        if top == "lr2_adamw_multi":
-            # the two weight-matrix launches (actor, critic): read p, g, m, v + write p, m, v + bf16 shadow
-            big = sorted((e0.elapsed_time(e1) for nm, a, e0, e1 in prof if nm == "lr2_adamw_multi" and a[3] > 1000))
-            per_launch = (opt.algorithmic_bytes(0) + copt.algorithmic_bytes(0)) / 2.0
-            ach = per_launch / (sum(big) / len(big) * 1e-3) / 1e9
-            roofline = {"kernel": "adamw_multi_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
-                        "unit": "GB/s", "frac": ach / hbm_peak, "traffic": ncu_traffic("r01_adamw_full.md"),
-                        "peak_source": hbm_src,
-                        "share_of_step": gp["ms_per_step"] / total_ms,
-                        "algorithmic_bytes_per_launch": per_launch}
-        elif top.startswith("gemm"):
-            ach = gp["work"] / (gp["ms"] * 1e-3) / 1e12
-            roofline = {"kernel": f"gemm_kernel<{top}>", "bound": "tensor", "achieved": ach, "peak": tf_peak,
-                        "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None, "peak_source": tf_src,
-                        "share_of_step": gp["ms_per_step"] / total_ms}
-        else:
-            roofline = {"kernel": top, "bound": "hbm", "achieved": None, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": None, "traffic": None, "share_of_step": gp["ms_per_step"] / total_ms}
+        # (a) the HBM-bound family: lr2_adamw_multi.  Algorithmic bytes come from the optimizer's own chunk tables, per
+        # launch, for exactly the chunk span each launch covered (row-sharded runs: only the owned rows are launched),
+        # matched in order with the CUDA-event duration of that launch.  The roofline is quoted on the launches that
+        # carry out_layer.fc1 (>= 100 MB each); the few-microsecond bias / LayerNorm group launches are listed apart.
+        ad_ms = [e0.elapsed_time(e1) for nm, a, e0, e1 in prof if nm == "lr2_adamw_multi"]
+        ad_bytes = []
+        for o in (opt, copt):
+            ad_bytes.append(list(o.launch_bytes)); o.launch_bytes.clear()
+        # launch order inside one step: all of the actor optimizer's launches, then the critic's
+        per_step_a, per_step_c = len(ad_bytes[0]) // args.profile_steps, len(ad_bytes[1]) // args.profile_steps
+        order = []
+        for i in range(args.profile_steps):
+            order += ad_bytes[0][i * per_step_a:(i + 1) * per_step_a] + ad_bytes[1][i * per_step_c:(i + 1) * per_step_c]
+        assert len(order) == len(ad_ms), (len(order), len(ad_ms))
+        big = [(b, t) for b, t in zip(order, ad_ms) if b >= 100e6]
+        gp = groups["lr2_adamw_multi"]
+        ach = sum(b for b, _ in big) / (sum(t for _, t in big) * 1e-3) / 1e9
+        roofline = {"kernel": "adamw_multi_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
+                    "unit": "GB/s", "frac": ach / hbm_peak,
+                    "traffic": ncu_traffic("r01_adamw_full.md") if world == 1 else None,
+                    "peak_source": hbm_src, "share_of_step": gp["ms_per_step"] / total_ms,
+                    "algorithmic_bytes_per_launch": sum(b for b, _ in big) / len(big),
+                    "launch_ms": sum(t for _, t in big) / len(big), "launches_per_step": len(big) / args.profile_steps,
+                    "small_launches_per_step": (len(order) - len(big)) / args.profile_steps,
+                    "note": "bytes = chunk span of each launch x (read p, g, m, v + write p, m, v + bf16 shadow); "
+                            "data-parallel runs launch only this rank's rows of out_layer.fc1"}
+        # (b) the tensor-bound family with the largest share: always reported next to it
+        gemm_keys = [k for k in groups if k.startswith("gemm") and "fc1" not in k]
+        if gemm_keys:
+            top = max(gemm_keys, key=lambda k: groups[k]["ms"])
+            g2 = groups[top]
+            ach2 = g2["work"] / (g2["ms"] * 1e-3) / 1e12
+            roofline_tensor = {"kernel": f"gemm2_kernel / gemm_kernel <{top}>", "bound": "tensor", "achieved": ach2,
+                               "peak": tf_peak, "unit": "TFLOP/s", "frac": ach2 / tf_peak, "peak_source": tf_src,
+                               "frac_of_burst_peak": ach2 / tf_burst, "traffic": None,
+                               "share_of_step": g2["ms_per_step"] / total_ms,
+                               "note": "eager per-call CUDA events: includes the small-shape launches of the family"}
         gemm_flops = sum(v["work"] for k, v in groups.items() if k.startswith("gemm"))
         gemm_ms = sum(v["ms"] for k, v in groups.items() if k.startswith("gemm"))
         breakdown = {k: {"ms_per_step": round(v["ms_per_step"], 4), "calls_per_step": v["calls"] / args.profile_steps,
@@ -498,13 +621,27 @@ def main():
                                   "tensor_frac_of_" + tf_src.replace(" ", "_"): round(
                                       gemm_flops / (gemm_ms * 1e-3) / 1e12 / tf_peak, 3) if gemm_ms else None}
 
+    # ---- (3b) the other BASELINE configs, measured in the same run ------------------------------------------
+    others = None
+    if not args.no_other_configs:
+        del gstep
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+        others = other_configs(torch, dist, dev, world, rank, peaks)
+
     # ---- (4) CPU baseline (oracle port) on rank 0, N=1 only -------------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    cpu, eager = None, None
+    if rank == 0 and world == 1:
         del resident
         torch.cuda.empty_cache()
-        r = cpu_stage3(steps=2, warmup=1, budget_s=60.0)
-        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        ref_models = None
+        if not args.no_cpu_baseline:
+            r = cpu_stage3(steps=2, warmup=1, budget_s=60.0, keep_models=True)
+            cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+            ref_models = r["models"]
+        if not args.no_eager_baseline:
+            eager = eager_b200_stage3(torch, dev, ref_models)
 
     if rank == 0:
         line = {"metric": "LR2PPO stage-3 train queries/sec", "value": value, "unit": "queries/s", "n_gpus": world,
@@ -521,17 +658,33 @@ def main():
                 "model_tflops_per_gpu": FLOP_PER_QUERY * BS * args.steps / (ms / 1e3) / 1e12}
         if roofline is not None:
             line["roofline"] = roofline
+            if roofline_tensor is not None:
+                line["roofline_tensor"] = roofline_tensor
             line["breakdown"] = breakdown
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if eager is not None:
+            line["eager_b200"] = eager
+            line["speedup_vs_eager_b200"] = value / eager["value"]
+        if others is not None:
+            line["other_configs"] = others
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
-        # NCCL work captured in the CUDA graph makes communicator teardown hang on some stacks: synchronise,
-        # flush and leave without running the destructors.
+        # Orderly teardown: the captured graphs hold the NCCL work, so they are released BEFORE the communicator is
+        # destroyed (destroying it first is what hung in round 1).  A watchdog bounds the wait: the JSON line is
+        # already printed and flushed, so a stack that still hangs cannot take the result with it.
+        import gc
         torch.cuda.synchronize()
         dist.barrier()
-        sys.stdout.flush(); sys.stderr.flush()
-        os._exit(0)
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        gstep = step = e2e_step = None  # noqa: F841
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+        watchdog.cancel()
 
 
 if __name__ == "__main__":

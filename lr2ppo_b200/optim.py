@@ -59,6 +59,7 @@ class FusedAdamW(Optimizer):
         self._fused = {}       # id(p) -> provider() of [(dY, X)] for the fused wgrad+AdamW kernel
         self._hyper = {}       # group index -> device hyper-parameter buffer
         self.frozen_hyper = False  # True while the step is replayed from a CUDA graph
+        self.launch_bytes = []     # algorithmic HBM bytes of every lr2_adamw_multi launch made while _lib.PROFILE is on
 
     # -- extras -----------------------------------------------------------
     def register_shadow(self, p, shadow):
@@ -139,7 +140,12 @@ class FusedAdamW(Optimizer):
         for t, p in enumerate(ps):          # chunk range of every tensor (two-phase step: see step(first=...))
             starts[id(p)] = (acc, chunks[t].shape[0])
             acc += chunks[t].shape[0]
+        # bytes moved by chunks [0, i): lets a profiling pass attribute algorithmic bytes to each launch (chunk span)
+        per_chunk = torch.cat([torch.clamp(p.numel() - chunks[t][:, 1], max=chunk) *
+                               self._bytes_per_element(p, self._grad_of(p)) for t, p in enumerate(ps)])
+        prefix = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(per_chunk, 0)])
         tab = dict(params=ps, ids=[id(p) for p in ps], gptrs=gptrs, n_chunks=chunk_t.shape[0], ranges=starts,
+                   byte_prefix=prefix,
                    ptrs=torch.tensor(ptrs, dtype=torch.int64, device=dev),
                    meta=torch.tensor(meta, dtype=torch.int64, device=dev),
                    chunks=chunk_t.to(dev))
@@ -196,8 +202,12 @@ class FusedAdamW(Optimizer):
             g = self._grad_of(p)
             if g is None or id(p) in self._fused:
                 continue
-            total += p.numel() * (4 + g.element_size() + 4 + 4 + 4 + 4 + 4 + (2 if id(p) in self._shadows else 0))
+            parts = getattr(self, "_windows", {}).get(id(p), (0, 1))[1]      # row-sharded: this rank moves 1/parts
+            total += p.numel() // parts * self._bytes_per_element(p, g)
         return total
+
+    def _bytes_per_element(self, p, g):
+        return 4 + g.element_size() + 4 + 4 + 4 + 4 + 4 + (2 if id(p) in self._shadows else 0)
 
     _PIN_SLOTS = 4
 
@@ -264,6 +274,8 @@ class FusedAdamW(Optimizer):
             prepared.append((group, live, fused, hyper, tab, spans))
 
         def launch(tab, hyper, a, n):
+            if _lib.PROFILE is not None:         # bench.py's roofline pass: algorithmic bytes of this launch
+                self.launch_bytes.append(int(tab["byte_prefix"][a + n] - tab["byte_prefix"][a]))
             _lib.run(L.lr2_adamw_multi, tab["ptrs"].data_ptr(), tab["meta"].data_ptr(),
                      tab["chunks"].data_ptr() + 16 * a, n, hyper.data_ptr(), _lib.stream())
 

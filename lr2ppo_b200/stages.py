@@ -38,11 +38,57 @@ def _step(grad_sync, model, optimizer):
     _sync_and_step(grad_sync, model, optimizer)()
 
 
+def _zero_grad(model):
+    """model.zero_grad() (finetune/pointwise.py:302); with persistent gradient buffers (CUDA-graph replay) the buffers
+    are kept and the first write of the step overwrites them instead."""
+    eng = getattr(model, "_engine", None)
+    if eng is not None and eng.persistent_grads:
+        eng.begin_step()
+    else:
+        model.zero_grad()
+
+
+class GraphedTrainStep:
+    """A stage-1 / stage-2 training step captured in a CUDA graph and replayed (the ~700 launches of a stage-2 step
+    cost more host time through Python than they take on the GPU).
+
+        step = GraphedTrainStep(lambda: reward_train_model(args, model, opt, sch, *static_batch), model, opt, sch)
+        for batch in loader:
+            for dst, src in zip(static_batch, batch): dst.copy_(src, non_blocking=True)
+            loss, acc = step.replay()
+
+    `fn` must read its inputs from fixed device tensors and call the scheduler itself (as the reference's train_model
+    does); per replay the scheduler is stepped on the host and the optimizer's hyper-parameters are uploaded
+    asynchronously, exactly like ppo.GraphedStage3Step.  Dropout seeds come from the engine's device counter, so every
+    replay draws fresh masks.  With a dist.GradSync inside `fn` the NCCL calls are captured too."""
+
+    def __init__(self, fn, model, optimizer, scheduler, warmup=3):
+        self.opt, self.sch = optimizer, scheduler
+        model._engine.persistent_grads = True
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.out = fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.opt.frozen_hyper = True
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn()
+
+    def replay(self):
+        self.opt.update_hyper()          # lr of THIS step (the schedule is stepped after the update, as in train_model)
+        self.graph.replay()
+        self.sch.step()
+        return self.out
+
+
 def pointwise_train_model(args, model, optimizer, scheduler, text_emb_batch, img_emb_batch, tgts_batch,
                           grad_sync=None):
     """loss = SmoothL1(beta 0.3)(logits, tgts); backward; AdamW; scheduler (per batch).  grad_sync=None keeps the
     reference's independent replicas; a dist.GradSync averages the gradients (north_star)."""
-    model.zero_grad()
+    _zero_grad(model)
     loss, _ = model(text_emb_batch, img_emb_batch, tgts_batch)
     loss.backward()
     _step(grad_sync, model, optimizer)
@@ -55,7 +101,7 @@ def reward_train_model(args, model, optimizer, scheduler, text_emb_batch, img_em
     """Two forwards (chosen / reject 4-slot orderings) -> hinge relu(m - (c - r)).mean() -> one backward.
     Returns (loss, acc) like the reference.  grad_sync: see pointwise_train_model (BASELINE configs[2], data-parallel
     stage 2: both backward passes accumulate the fc1 gradient from all-gathered operands, the rest is all-reduced)."""
-    model.zero_grad()
+    _zero_grad(model)
     chosen = model(text_emb_batch, img_emb_batch, tgts_batch, chosen_index_batch)
     reject = model(text_emb_batch, img_emb_batch, tgts_batch, reject_index_batch)
     loss, acc = losses.pair_hinge_loss(chosen, reject, margin)

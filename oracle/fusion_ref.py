@@ -80,7 +80,7 @@ def critic_forward(sd, text, img, index, masks=None):
     """ref: finetune/ppo.py:265-297 / :318-350 — gather by index, body, + pos_emb, xitt, head, last token.
     masks (train mode): sites 1-3 for `xit` as in fusion_body, 4-6 [bs*T, C] for `xitt`."""
     bs = text.shape[0]
-    bi = torch.arange(bs).view(bs, 1)
+    bi = torch.arange(bs, device=text.device).view(bs, 1)
     text = text[bi, index]
     img = img[bi, index]
     x = fusion_body(sd, text, img, masks)
@@ -107,7 +107,7 @@ def trad_actor_forward(sd, text):
 
 def trad_critic_forward(sd, text, index):
     bs = text.shape[0]
-    text = text[torch.arange(bs).view(bs, 1), index]
+    text = text[torch.arange(bs, device=text.device).view(bs, 1), index]
     x = trad_body(sd, text)
     T = x.shape[1]
     x = x + sd["pos_emb.weight"][:T].unsqueeze(0)

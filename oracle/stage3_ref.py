@@ -36,11 +36,12 @@ def rollout(actor, critic, reward, text, img):
     """ref: finetune/ppo.py:845-883 with timestep 0: state = arange(tags)."""
     bs, T = text.shape[:2]
     with torch.no_grad():
-        state = torch.arange(T).unsqueeze(0).repeat(bs, 1)
+        state = torch.arange(T, device=text.device).unsqueeze(0).repeat(bs, 1)
         scores = fusion_ref.actor_forward(actor.sd, text, img).view(bs, T)
         value = fusion_ref.critic_forward(critic.sd, text, img, state)
         _, idx = torch.sort(scores, dim=-1, descending=True, stable=True)
-        next_state = torch.cat([torch.arange(2).unsqueeze(0).repeat(bs, 1), torch.gather(state, 1, idx)], dim=1)
+        next_state = torch.cat([torch.arange(2, device=text.device).unsqueeze(0).repeat(bs, 1),
+                                torch.gather(state, 1, idx)], dim=1)
         rewards = fusion_ref.critic_forward(reward.sd, text, img, next_state)
     return state, next_state, scores, rewards, value
 

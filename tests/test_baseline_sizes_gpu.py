@@ -29,10 +29,12 @@ def _margs():
 def _check_updates(test, named, before, gold, prefix="delta/"):
     """AdamW's first step moves every weight by ~lr * 3.16 * sign(g): compare the direction on the entries whose
     gradient is well above bf16 noise (sampled like the golden)."""
+    rms = {n: gold["mnorm/" + n].item() / max(1.0, p.numel() ** 0.5) for n, p in named}
+    top = max(rms.values())
     for n, p in named:
         ref = gold[prefix + n]
-        if ref.abs().max().item() == 0:
-            continue
+        if ref.abs().max().item() == 0 or rms[n] < 1e-3 * top or p.numel() < 64:
+            continue          # mathematically-zero gradients (keys.bias, the actor's head.bias): the sign is noise
         got = golden_util.grad_sample(p.detach() - before[n], 4096).cpu()
         m = gold["m/" + n].reshape(-1)
         m = m if m.numel() == got.numel() else m[:got.numel()]
