@@ -265,6 +265,7 @@ class FusionEngine:
         self.dp_gather_async = None  # optional callable(t) -> handle; handle() waits and returns the gathered rows
         self.fc1_rows = None         # (r0, r1): rows of out_layer.fc1 this rank owns (row-sharded optimizer)
         self.fc1_grad_bf16 = None  # bf16 [out, in] gradient buffer of out_layer.fc1.weight (see enable_bf16_fc1_grad)
+        self._zero_index = {}      # (bs, T, device) -> int64 zeros [bs, T]: broadcast index of un-repeated img_emb
 
     def begin_step(self):
         """Persistent-gradient mode: start of a new optimizer step (replaces model.zero_grad())."""
@@ -333,7 +334,18 @@ class FusionEngine:
                 ops.bump_counter(self.seed_counter, 1)
                 seed_dev = self.seed_counter.clone() if save else self.seed_counter
         xt = ops.cast_gather(text.reshape(bs, Tsrc, S * E), body_index).view(items * S, E)
-        xi = ops.cast_gather(img.reshape(bs, Tsrc, I * E), body_index).view(items * I, E)
+        if img.shape[1] == 1 and Tsrc > 1:
+            # img_emb as the loader yields it, [bs, 1, I, E]: one keyframe set per clip shared by all of its tags.
+            # The reference materialises img_emb.unsqueeze(1).repeat(1, tags, 1, 1) on the host and uploads the copies
+            # (finetune/ppo.py:831); here the broadcast happens inside the gather + cast kernel (all-zero tag index).
+            T_items = items // bs
+            key = (bs, T_items, str(img.device))
+            zi = self._zero_index.get(key)
+            if zi is None:
+                zi = self._zero_index[key] = torch.zeros((bs, T_items), dtype=torch.int64, device=img.device)
+            xi = ops.cast_gather(img.reshape(bs, 1, I * E), zi).view(items * I, E)
+        else:
+            xi = ops.cast_gather(img.reshape(bs, Tsrc, I * E), body_index).view(items * I, E)
         tf, c_tp = mlp_forward(W["tp1"], W["tp2"], xt, save)
         imf, c_ip = mlp_forward(W["ip1"], W["ip2"], xi, save)
         cat = torch.empty((items, (S + I) * E), dtype=bf16, device=text.device)

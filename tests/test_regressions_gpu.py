@@ -151,3 +151,30 @@ def test_policy_loss_index_lists_k_not_n_and_out_of_range():
     assert torch.isnan(out["loss"]).item() and torch.isfinite(out["ds"]).all()
     with pytest.raises(Exception):
         ops.ppo_policy_loss(s, s, z[:5], z, bad, 0.0, 0.0)               # reward with the wrong number of rows
+
+
+@pytest.mark.parametrize("kind", ["actor", "critic", "reward"])
+def test_unrepeated_img_emb_is_broadcast_inside_the_gather(kind):
+    """img_emb [bs, 1, I, E] (as the loader yields it) must give bit-identical results to the reference's
+    img_emb.unsqueeze(1).repeat(1, tags, 1, 1) (finetune/ppo.py:831), forward and backward."""
+    from lr2ppo_b200 import models
+    cls = {"actor": models.Actor, "critic": models.Critic, "reward": models.Reward}[kind]
+    model = cls(_margs(), _margs())
+    model.load_state_dict(golden_util.make_state_dict(kind), strict=True)
+    model = model.cuda().eval()
+    text, img, tgts, index = golden_util.make_inputs(kind)
+    text, one = text.cuda(), img[:, :1].contiguous().cuda()
+    rep = one.repeat(1, text.shape[1], 1, 1)
+    idx = None if index is None else index.cuda()
+
+    def run(im):
+        model.zero_grad(set_to_none=True)
+        y = model.scores(text, im) if kind == "actor" else model(text, im, None, idx)
+        y.sum().backward()
+        return y.detach().clone(), {n: p.grad.clone() for n, p in model.named_parameters()}
+
+    y1, g1 = run(one)
+    y2, g2 = run(rep)
+    assert torch.equal(y1, y2)
+    for n in g1:
+        assert torch.equal(g1[n], g2[n]), n
