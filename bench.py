@@ -630,7 +630,12 @@ def main():
         import gc
         gc.collect()
         torch.cuda.empty_cache()
-        others = other_configs(torch, dist, dev, world, rank, peaks)
+        try:
+            others = other_configs(torch, dist, dev, world, rank, peaks)
+        except Exception as e:   # an auxiliary workload must not take the headline line with it: reported, not hidden
+            import traceback
+            traceback.print_exc()
+            others = {"error": repr(e)}
 
     # ---- (4) CPU baseline (oracle port) on rank 0, N=1 only -------------------------------------------------
     cpu, eager = None, None

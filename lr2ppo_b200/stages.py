@@ -6,8 +6,12 @@
 import torch
 import torch.distributed as dist
 
-from . import losses
+from . import losses, models, ops
 from .ndcg import AverageNDCGMeter
+
+
+def _all_trainable(model):
+    return all(p.requires_grad for p in model.parameters())
 
 
 def build_optimizer(args, model):
@@ -89,8 +93,20 @@ def pointwise_train_model(args, model, optimizer, scheduler, text_emb_batch, img
     """loss = SmoothL1(beta 0.3)(logits, tgts); backward; AdamW; scheduler (per batch).  grad_sync=None keeps the
     reference's independent replicas; a dist.GradSync averages the gradients (north_star)."""
     _zero_grad(model)
-    loss, _ = model(text_emb_batch, img_emb_batch, tgts_batch)
-    loss.backward()
+    eng = getattr(model, "_engine", None)
+    if eng is not None and getattr(model, "mode", None) == "reg" and _all_trainable(model):
+        # explicit forward -> fused loss kernel (value + d loss / d logits in one launch) -> explicit backward: the
+        # fusion model is ONE node anyway, so torch's autograd engine adds nothing but host time (and its stream
+        # bookkeeping does not survive CUDA-graph capture of two nodes in one backward, stage 2)
+        models._check_inputs(text_emb_batch, img_emb_batch)
+        with torch.no_grad():
+            logits, ctx = eng.forward(text_emb_batch.contiguous(), img_emb_batch.contiguous(), None,
+                                      train=model.training, save=True)
+            loss, dl = ops.smooth_l1_loss(logits.view(-1), tgts_batch.contiguous().view(-1), 0.3)
+            eng.backward(ctx, dl)
+    else:
+        loss, _ = model(text_emb_batch, img_emb_batch, tgts_batch)
+        loss.backward()
     _step(grad_sync, model, optimizer)
     scheduler.step()
     return loss
@@ -102,10 +118,23 @@ def reward_train_model(args, model, optimizer, scheduler, text_emb_batch, img_em
     Returns (loss, acc) like the reference.  grad_sync: see pointwise_train_model (BASELINE configs[2], data-parallel
     stage 2: both backward passes accumulate the fc1 gradient from all-gathered operands, the rest is all-reduced)."""
     _zero_grad(model)
-    chosen = model(text_emb_batch, img_emb_batch, tgts_batch, chosen_index_batch)
-    reject = model(text_emb_batch, img_emb_batch, tgts_batch, reject_index_batch)
-    loss, acc = losses.pair_hinge_loss(chosen, reject, margin)
-    loss.backward()
+    eng = getattr(model, "_engine", None)
+    if eng is not None and _all_trainable(model):
+        models._check_inputs(text_emb_batch, img_emb_batch)
+        text, img = text_emb_batch.contiguous(), img_emb_batch.contiguous()
+        with torch.no_grad():
+            chosen, ctx_c = eng.forward(text, img, chosen_index_batch.to(torch.int64).contiguous(),
+                                        train=model.training, save=True)
+            reject, ctx_r = eng.forward(text, img, reject_index_batch.to(torch.int64).contiguous(),
+                                        train=model.training, save=True)
+            loss, acc, dc, dr = ops.pair_hinge_loss(chosen, reject, margin)
+            eng.backward(ctx_c, dc)
+            eng.backward(ctx_r, dr)
+    else:
+        chosen = model(text_emb_batch, img_emb_batch, tgts_batch, chosen_index_batch)
+        reject = model(text_emb_batch, img_emb_batch, tgts_batch, reject_index_batch)
+        loss, acc = losses.pair_hinge_loss(chosen, reject, margin)
+        loss.backward()
     _step(grad_sync, model, optimizer)
     scheduler.step()
     return loss, acc

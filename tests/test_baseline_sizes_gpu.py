@@ -90,7 +90,9 @@ def test_stage3_step_batch24_train_mode_vs_reference_train_model():
         named = [(f"{tag}.{n}", p) for n, p in net.named_parameters()]
         parity.check_param_tensors(f"{test} [{tag} exp_avg]", named, lambda p: o.state[p]["exp_avg"],
                                    lambda n: gold["m/" + n], lambda n: gold["mnorm/" + n].item(),
-                                   lambda t: golden_util.grad_sample(t, 4096))
+                                   lambda t: golden_util.grad_sample(t, 4096),
+                                   elem_overrides=parity.CRITIC_TAIL_ELEM if tag == "critic" else None,
+                                   norm_overrides=parity.CRITIC_TAIL_NORM if tag == "critic" else None)
         _check_updates(f"{test} [{tag}]", named, before, gold)
 
 
@@ -122,5 +124,6 @@ def test_stage12_train_step_baseline_size_train_mode(stage):
     parity.check(test, "loss", abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item()), TOL)
     parity.check_param_tensors(test + " [exp_avg]", named, lambda p: opt.state[p]["exp_avg"],
                                lambda n: gold["m/" + n], lambda n: gold["mnorm/" + n].item(),
-                               lambda t: golden_util.grad_sample(t, 4096))
+                               lambda t: golden_util.grad_sample(t, 4096),
+                               elem_overrides=parity.pair_cancellation(8e-2) if stage == 2 else None)
     _check_updates(test, named, before, gold)

@@ -21,9 +21,9 @@ def _rel(d, ref):
     return ((d - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
 
 
-def _check_grads(test, named, getter, gold, prefix, nprefix):
+def _check_grads(test, named, getter, gold, prefix, nprefix, **kw):
     parity.check_param_tensors(test, named, getter, lambda n: gold[prefix + n], lambda n: gold[nprefix + n].item(),
-                               lambda t: golden_util.grad_sample(t, 4096))
+                               lambda t: golden_util.grad_sample(t, 4096), **kw)
 
 
 @pytest.mark.parametrize("kind", ["actor", "critic", "reward"])
@@ -41,7 +41,10 @@ def test_trad_models_vs_reference_golden(kind):
         logits = model(text.cuda(), None, tgts.cuda(), index.cuda())
     parity.check(f"trad[{kind}]", "logits", _rel(logits, gold["logits"]), TOL)
     (logits * golden_util.out_grad(kind, logits.numel()).cuda()).sum().backward()
-    _check_grads(f"trad[{kind}]", list(model.named_parameters()), lambda p: p.grad, gold, "grad/", "gnorm/")
+    # reward: the 4-slot index [0, 1, pi0, pi1] feeds each item twice to xitt, whose query / key gradients are then
+    # differences of nearly equal contributions of duplicate rows (measured 0.065)
+    _check_grads(f"trad[{kind}]", list(model.named_parameters()), lambda p: p.grad, gold, "grad/", "gnorm/",
+                 elem_overrides={"xitt.": 8e-2} if kind == "reward" else None)
 
 
 @pytest.mark.parametrize("stage", [1, 2])
@@ -72,7 +75,8 @@ def test_stage_train_step_vs_reference_train_model(stage):
                                               chosen.cuda(), reject.cuda())
         assert abs(acc.item() - gold["acc"].item()) < 1e-6
     parity.check(f"stage{stage} train step", "loss", abs(loss.item() - gold["loss"].item()) / abs(gold["loss"].item()), TOL)
-    _check_grads(f"stage{stage} train step [exp_avg]", named, lambda p: opt.state[p]["exp_avg"], gold, "m/", "mnorm/")
+    _check_grads(f"stage{stage} train step [exp_avg]", named, lambda p: opt.state[p]["exp_avg"], gold, "m/", "mnorm/",
+                 elem_overrides=parity.pair_cancellation(0.12) if stage == 2 else None)   # 3 pairs only
     # parameter update direction: delta = -lr * m/(sqrt(v)+eps) - lr*wd*p ; compare on the sampled entries
     rms = {n: gold["mnorm/" + n].item() / max(1.0, p.numel() ** 0.5) for n, p in named}
     top = max(rms.values())
