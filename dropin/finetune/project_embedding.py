@@ -1,0 +1,7 @@
+"""finetune/project_embedding.py of the reference tree."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import _bootstrap  # noqa: E402,F401
+from lr2ppo_b200.project_embedding import ProjectionLayer  # noqa: E402,F401

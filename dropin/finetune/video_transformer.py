@@ -1,0 +1,7 @@
+"""finetune/video_transformer.py of the reference tree."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import _bootstrap  # noqa: E402,F401
+from lr2ppo_b200.video_transformer import VideoTransformer  # noqa: E402,F401

@@ -333,7 +333,7 @@ class FusionEngine:
                     self.seed_counter = torch.zeros(1, dtype=torch.int64, device=text.device)
                 ops.bump_counter(self.seed_counter, 1)
                 seed_dev = self.seed_counter.clone() if save else self.seed_counter
-        xt = ops.cast_gather(text.reshape(bs, Tsrc, S * E), body_index).view(items * S, E)
+        xt = _to_items(text.reshape(bs, Tsrc, S * E), body_index).view(items * S, E)
         if img.shape[1] == 1 and Tsrc > 1:
             # img_emb as the loader yields it, [bs, 1, I, E]: one keyframe set per clip shared by all of its tags.
             # The reference materialises img_emb.unsqueeze(1).repeat(1, tags, 1, 1) on the host and uploads the copies
@@ -343,9 +343,9 @@ class FusionEngine:
             zi = self._zero_index.get(key)
             if zi is None:
                 zi = self._zero_index[key] = torch.zeros((bs, T_items), dtype=torch.int64, device=img.device)
-            xi = ops.cast_gather(img.reshape(bs, 1, I * E), zi).view(items * I, E)
+            xi = _to_items(img.reshape(bs, 1, I * E), zi).view(items * I, E)
         else:
-            xi = ops.cast_gather(img.reshape(bs, Tsrc, I * E), body_index).view(items * I, E)
+            xi = _to_items(img.reshape(bs, Tsrc, I * E), body_index).view(items * I, E)
         tf, c_tp = mlp_forward(W["tp1"], W["tp2"], xt, save)
         imf, c_ip = mlp_forward(W["ip1"], W["ip2"], xi, save)
         cat = torch.empty((items, (S + I) * E), dtype=bf16, device=text.device)
@@ -472,6 +472,15 @@ class FusionEngine:
                 ops.gemm(dy_[:, r0:r1], x_, a_mn=True, b_mn=True, out=self.fc1_grad_bf16[r0:r1], block_n=bn)
             else:
                 ops.gemm(dy_, x_, a_mn=True, b_mn=True, out=self.fc1_grad_bf16, block_n=bn)
+
+
+def _to_items(src, index):
+    """[bs, T_src, row] -> bf16 [bs, T_dst, row]: fp32 sources (batches as the loader yields them) go through the fused
+    gather + cast kernel; bf16 sources (ppo.RolloutMemory keeps the stored rollout batches in bf16) are gathered as
+    they are, or used in place when no gather is asked for."""
+    if src.dtype == bf16:
+        return src if index is None else ops.gather_rows(src.contiguous(), index)
+    return ops.cast_gather(src, index)
 
 
 def _add_bf16(a, b):

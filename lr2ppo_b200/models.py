@@ -84,8 +84,10 @@ class _FusionFn(torch.autograd.Function):
 def _check_inputs(text_emb, img_emb):
     if not (text_emb.is_cuda and img_emb.is_cuda):
         raise RuntimeError("lr2ppo_b200 models run on CUDA (sm_100a) only; there is no CPU fallback")
-    if text_emb.dtype != torch.float32 or img_emb.dtype != torch.float32:
-        raise RuntimeError("text_emb / img_emb must be fp32 (as read from clean_feat.h5)")
+    ok = (torch.float32, torch.bfloat16)
+    if text_emb.dtype not in ok or img_emb.dtype not in ok:
+        raise RuntimeError("text_emb / img_emb must be fp32 (as read from clean_feat.h5) or bf16 (stored rollout "
+                           "batches, ppo.RolloutMemory)")
 
 
 class Actor(nn.Module):

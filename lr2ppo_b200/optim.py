@@ -268,8 +268,9 @@ class FusedAdamW(Optimizer):
                 self._tables[gi] = tab
             spans = []
             if live:
-                for p in live:
-                    self.state[p]["step"] += 1
+                if not (live[0].is_cuda and torch.cuda.is_current_stream_capturing()):
+                    for p in live:                       # a capture pass executes nothing: update_hyper() counts the
+                        self.state[p]["step"] += 1       # steps its replays stand for
                 spans = [(0, tab["n_chunks"])]
             prepared.append((group, live, fused, hyper, tab, spans))
 

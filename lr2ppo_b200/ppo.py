@@ -65,7 +65,9 @@ def rollout(model, reward_model, text_emb_batch, img_emb_batch, tgts_batch, stat
         action_scores = pr[:, :, 1] + 2 * pr[:, :, 2]
     else:
         action_scores = action_logits.view(bs, tags_num)
-    next_state = ops.ppo_rollout(action_scores.contiguous(), state.contiguous(), 2)
+    # timestep > 0 passes the previous next_state (prefix + permutation) as state: the reference's index_select with
+    # the tags_num sort indices reads its first tags_num entries (finetune/ppo.py:869-871)
+    next_state = ops.ppo_rollout(action_scores.contiguous(), state[:, :tags_num].contiguous(), 2)
     rewards = reward_model(text_emb_batch, img_emb_batch, tgts_batch, next_state)
     if before_critic is not None:
         before_critic()
@@ -159,11 +161,15 @@ def evaluate_scores(model, text_emb, img_emb):
 
 
 @torch.no_grad()
-def evaluate(args, val_loader, step, split="test", num_tasks=None):
-    """ref: finetune/ppo.py:620-681.  Scores every clip of this rank's shard, then ONE segmented NDCG launch
-    and ONE all_gather for the whole pass (the reference gathers once per clip)."""
+def evaluate(args, val_loader, step, split="test", num_tasks=None, cases_path=None):
+    """ref: finetune/ppo.py:620-681 and finetune/ppo_eval.py:401-471.  Scores every clip of this rank's shard, then ONE
+    segmented NDCG launch and ONE all_gather for the whole pass (the reference gathers once per clip).
+
+    The loader yields (text_emb [1, tags, S, E], img_emb [1, I, E], tgts [1, tags]) or, for ppo_eval, a fourth element:
+    the clip record as default_collate batches it.  cases_path: write the per-clip dump of ppo_eval.py:441-459
+    (`case/ppo_cases.json`: filename, id, description, tags, ndcg[6], predict = tags in predicted order with scores)."""
     args.model.eval()
-    scores_l, gold_l = [], []
+    scores_l, gold_l, clips = [], [], []
     # The reference scores one clip per forward (batch_size 1, finetune/ppo.py:697-698), i.e. it streams the whole
     # 500 M-parameter out_layer weight once per clip.  Tags of different clips are independent for the actor, so the
     # (clip, tag) items of consecutive clips are packed into one forward of up to `eval_items` items (SURVEY §8(f) 3).
@@ -182,16 +188,19 @@ def evaluate(args, val_loader, step, split="test", num_tasks=None):
             off += n_tags
         pend_t.clear(); pend_i.clear(); pend_n.clear()
 
-    for text_emb, img_emb, tgts in val_loader:
+    for batch in val_loader:
+        text_emb, img_emb, tgts = batch[:3]
+        if len(batch) > 3:
+            clips.append(batch[3])
         n_tags = text_emb.shape[1]
         if pend_n and sum(pend_n) + n_tags > cap:
             flush()
-        text = text_emb.to(args.device)                     # [1, tags, S, E]
+        text = text_emb.to(args.device, non_blocking=True)  # [1, tags, S, E]
         pend_t.append(text.view(n_tags, 1, *text.shape[2:]))
-        pend_i.append(img_emb.to(args.device).unsqueeze(1).expand(1, n_tags, *img_emb.shape[1:])
-                      .reshape(n_tags, 1, *img_emb.shape[1:]))
+        pend_i.append(img_emb.to(args.device, non_blocking=True).unsqueeze(1)
+                      .expand(1, n_tags, *img_emb.shape[1:]).reshape(n_tags, 1, *img_emb.shape[1:]))
         pend_n.append(n_tags)
-        gold_l.append(tgts.to(args.device).view(-1))
+        gold_l.append(tgts.to(args.device, non_blocking=True).view(-1))
     flush()
     meter = AverageNDCGMeter()
     n = len(scores_l)
@@ -202,7 +211,11 @@ def evaluate(args, val_loader, step, split="test", num_tasks=None):
     for i, (s, g) in enumerate(zip(scores_l, gold_l)):
         scores[i, :s.numel()] = s
         labels[i, :g.numel()] = g
-    vals = meter.batch_ndcg(scores, labels, lens=lens)
+    want_cases = cases_path is not None and clips
+    res = meter.batch_ndcg(scores, labels, lens=lens, want_order=bool(want_cases))
+    vals, order = res if want_cases else (res, None)
+    if want_cases:
+        _dump_cases(cases_path, clips, vals.cpu(), order.cpu(), scores.cpu())
     if num_tasks and num_tasks > 1:
         gathered = [torch.zeros_like(vals) for _ in range(num_tasks)]
         dist.all_gather(gathered, vals)
@@ -215,6 +228,32 @@ def evaluate(args, val_loader, step, split="test", num_tasks=None):
             args.logger.info("".join("\nNDCG@{}={:.4f}".format(k, ndcg_value[k]) for k in sorted(ndcg_value.keys())))
         return ndcg_value[100000000]
     return None
+
+
+def _plain(v):
+    """A collated clip field -> what json.dump writes for it in the reference (lists of strings stay lists)."""
+    if torch.is_tensor(v):
+        return v.cpu().tolist()
+    return v
+
+
+def _dump_cases(path, clips, ndcg, order, scores):
+    """ppo_eval.py:441-459: one record per clip.  `clip` is the default_collate'd record (batch size 1): strings
+    arrive as 1-element lists, each tag's target as a 1-element tensor."""
+    import json
+    import os
+    results = []
+    for i, clip in enumerate(clips):
+        rec = {key: _plain(clip[key]) for key in ("filename", "id", "description")}
+        rec["tags"] = [{"tag": _plain(t["tag"]), "target": int(torch.as_tensor(t["target"]).view(-1)[0])}
+                       for t in clip["tags"]]
+        rec["ndcg"] = ndcg[i].tolist()
+        n = len(rec["tags"])
+        rec["predict"] = [(rec["tags"][j], float(scores[i, j])) for j in order[i, :n].tolist()]
+        results.append(rec)
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    with open(path, "w") as f:
+        json.dump(results, f)
 
 
 class GraphedStage3Step:
@@ -314,3 +353,180 @@ class PipelinedStage3Step(GraphedStage3Step):
         self.model.eval()
         self.opt.frozen_hyper = self.copt.frozen_hyper = frozen
         return stats
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's real loop shape (finetune/ppo.py:827-908): `update_timesteps` (200) rollout batches are collected,
+# each keeping CLONES of its fp32 text / image features in a Python list (:882-883, 31 MB per entry, 6.3 GB per
+# cycle), then train_model walks the list.  SURVEY.md §8(f) 1: a preallocated bf16 ring buffer instead.
+# ---------------------------------------------------------------------------------------------------------------------
+class RolloutMemory:
+    """Preallocated device ring of `capacity` rollout batches.  text / img are stored ONCE in bf16 -- the precision
+    every kernel of the path consumes them in, so nothing changes numerically: the engine's gather + cast of the
+    first forward simply happens here -- and all later forwards (the rollout's three models, the update's two) read
+    the slot in place.  img is stored un-repeated ([bs, 1, I, E]).  Per 24-query batch: 15.1 MB instead of the
+    reference's 31.3 MB of fp32 clones; a 200-batch cycle holds 3.0 GB instead of 6.3 GB.
+
+        mem = RolloutMemory(200, 24, 2, 196, 16, 768, device)
+        slot = mem.stage(text_fp32, img_fp32, tgts)          # cast into the next free slot, returns its views
+        entry = rollout(model, reward_model, *slot)          # runs on the bf16 views
+        mem.commit(entry)                                    # small tensors (state, scores, rewards, value) copied in
+        for entry in mem: update_batch(...)                  # entries in insertion order
+        mem.clear()
+    """
+
+    def __init__(self, capacity, bs, tags, S, I, E, device, n_prefix=2):
+        self.capacity, self.n = int(capacity), 0
+        kw = dict(device=device)
+        self.text = torch.empty((capacity, bs, tags, S, E), dtype=torch.bfloat16, **kw)
+        self.img = torch.empty((capacity, bs, 1, I, E), dtype=torch.bfloat16, **kw)
+        self.tgts = torch.zeros((capacity, bs, tags), dtype=torch.int64, **kw)
+        self.state = torch.zeros((capacity, bs, tags), dtype=torch.int64, **kw)
+        self.next_state = torch.zeros((capacity, bs, n_prefix + tags), dtype=torch.int64, **kw)
+        self.scores = torch.zeros((capacity, bs, tags), dtype=torch.float32, **kw)
+        self.rewards = torch.zeros((capacity, bs), dtype=torch.float32, **kw)
+        self.value = torch.zeros((capacity, bs), dtype=torch.float32, **kw)
+
+    def __len__(self):
+        return self.n
+
+    def bytes_per_entry(self):
+        return sum(t[0].numel() * t.element_size() for t in (self.text, self.img, self.tgts, self.state,
+                                                             self.next_state, self.scores, self.rewards, self.value))
+
+    def stage(self, text, img, tgts):
+        """Cast one fp32 (or copy one bf16) batch into the next slot; returns (text, img, tgts) views of the slot.
+        img: [bs, I, E] as the loader yields it, or [bs, 1, I, E]."""
+        if self.n >= self.capacity:
+            raise RuntimeError("RolloutMemory is full: run the update and clear() first")
+        k = self.n
+        img = img.view(img.shape[0], 1, *img.shape[-2:]) if img.dim() == 3 else img[:, :1]
+        for dst, src in ((self.text[k], text), (self.img[k], img)):
+            if src.dtype == torch.float32:
+                ops.to_bf16(src.contiguous(), out=dst)
+            else:
+                dst.copy_(src)
+        self.tgts[k].copy_(tgts)
+        return self.text[k], self.img[k], self.tgts[k]
+
+    def commit(self, entry):
+        """entry: the list rollout() returned for the staged slot."""
+        k = self.n
+        state, next_state, scores, rewards, value = entry[:5]
+        self.state[k].copy_(state); self.next_state[k].copy_(next_state); self.scores[k].copy_(scores)
+        self.rewards[k].copy_(rewards.view(-1)); self.value[k].copy_(value.view(-1))
+        self.n += 1
+
+    def entry(self, k):
+        return [self.state[k], self.next_state[k], self.scores[k], self.rewards[k], self.value[k], self.text[k],
+                self.img[k], self.tgts[k]]
+
+    def __iter__(self):
+        return (self.entry(k) for k in range(self.n))
+
+    def clear(self):
+        self.n = 0
+
+
+class GraphedCycle:
+    """The reference's cycle -- N rollout batches, then N update batches over the stored memory, schedulers stepped
+    once per cycle (finetune/ppo.py:845-908, 612-613) -- with both inner loops replayed from CUDA graphs:
+
+      * ONE rollout graph reading a static staging slot (the batch is cast into it, the graph writes its results into
+        static small tensors, both are then copied into the ring slot: 15 MB device-to-device per batch);
+      * ONE update graph reading a static "current entry" (an entry is copied in, the graph replays).
+
+    Statistics of the cycle are accumulated on the device and returned as the reference's ten averages."""
+
+    def __init__(self, args, model, reward_model, optimizer, critic_optim, capacity, bs, tags, S=196, I=16, E=768,
+                 grad_sync=None, warmup=2):
+        dev = next(model.parameters()).device
+        self.args, self.model, self.reward, self.grad_sync = args, model, reward_model, grad_sync
+        self.opt, self.copt = optimizer, critic_optim
+        self.memory = RolloutMemory(capacity, bs, tags, S, I, E, dev)
+        self.cur = RolloutMemory(1, bs, tags, S, I, E, dev)            # static entry both graphs work on
+        self.cur.n = 1
+        for e in (model.actor._engine, model.critic._engine):
+            e.persistent_grads = True
+        self._rollout_graph = self._update_graph = None
+        self._warm, self._eager_updates = warmup, 0
+        self.stats_sum = torch.zeros(10, device=dev)
+
+    # -- rollout ------------------------------------------------------------------------------------------------
+    def _rollout_eager(self):
+        text, img, tgts = self.cur.text[0], self.cur.img[0], self.cur.tgts[0]
+        entry = rollout(self.model, self.reward, text, img, tgts)
+        for dst, src in zip((self.cur.state[0], self.cur.next_state[0], self.cur.scores[0], self.cur.rewards[0],
+                             self.cur.value[0]), entry[:5]):
+            dst.copy_(src.view(dst.shape))
+
+    def rollout(self, text, img, tgts):
+        """One rollout batch (fp32 tensors as the loader yields them, already on the device) into the memory."""
+        self.cur.n = 0
+        self.cur.stage(text, img, tgts)
+        self.cur.n = 1
+        if self._rollout_graph is None:
+            self._rollout_graph = _capture(self._rollout_eager, self._warm)
+        self._rollout_graph.replay()
+        k = self.memory.n
+        if k >= self.memory.capacity:
+            raise RuntimeError("RolloutMemory is full: call update() first")
+        for name in ("text", "img", "tgts", "state", "next_state", "scores", "rewards", "value"):
+            getattr(self.memory, name)[k].copy_(getattr(self.cur, name)[0])
+        self.memory.n += 1
+
+    # -- update -------------------------------------------------------------------------------------------------
+    def _update_eager(self):
+        self.model.train()
+        stats = update_batch(self.args, self.model, self.opt, self.copt, self.cur.entry(0), self.grad_sync)
+        self.model.eval()
+        self.stats_sum += stats
+
+    def update(self, scheduler, critic_scheduler):
+        """train_model over the stored batches (finetune/ppo.py:501-617); returns the ten averages and clears."""
+        n = len(self.memory)
+        self.stats_sum.zero_()
+        for k in range(n):
+            for name in ("text", "img", "tgts", "state", "next_state", "scores", "rewards", "value"):
+                getattr(self.cur, name)[0].copy_(getattr(self.memory, name)[k])
+            if self._update_graph is None and self._eager_updates < 2:
+                # the first two updates of a run execute eagerly -- they ARE the updates of these entries, and they
+                # allocate everything the captured graph needs (persistent .grad buffers, optimizer tables)
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._update_eager()
+                torch.cuda.current_stream().wait_stream(side)
+                self._eager_updates += 1
+                continue
+            if self._update_graph is None:
+                torch.cuda.synchronize()
+                self.opt.frozen_hyper = self.copt.frozen_hyper = True
+                self._update_graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self._update_graph):       # records only: nothing executes during capture
+                    self._update_eager()
+            self.opt.update_hyper(); self.copt.update_hyper()
+            self._update_graph.replay()
+        total = self.stats_sum / max(n, 1)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            total = total / dist.get_world_size()
+            dist.all_reduce(total)
+        scheduler.step()
+        critic_scheduler.step()
+        self.memory.clear()
+        return list(total.unbind(0))
+
+
+def _capture(fn, warm):
+    """Warm `fn` up on a side stream, then capture one call in a CUDA graph."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warm):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fn()
+    return graph

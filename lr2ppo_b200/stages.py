@@ -146,8 +146,8 @@ def reward_evaluate(args, model, dataloader, num_tasks=None):
     model.eval()
     counts = torch.zeros(2, device=args.device)
     for text_emb, img_emb, tgts, chosen_index, reject_index in dataloader:
-        text = text_emb.to(args.device)
-        img = img_emb.unsqueeze(1).repeat(1, text.shape[1], 1, 1).to(args.device)
+        text = text_emb.to(args.device, non_blocking=True)
+        img = img_emb.unsqueeze(1).to(args.device, non_blocking=True)      # [bs, 1, I, E]: broadcast in the gather kernel
         t = tgts.to(args.device)
         c = model(text, img, t, chosen_index.to(args.device))
         r = model(text, img, t, reject_index.to(args.device))
@@ -165,8 +165,8 @@ def pointwise_evaluate(args, model, dataloader, num_tasks=None):
     model.eval()
     scores_l, gold_l = [], []
     for text_emb, img_emb, tgts in dataloader:
-        text = text_emb.to(args.device)
-        img = img_emb.unsqueeze(1).repeat(1, text.shape[1], 1, 1).to(args.device)
+        text = text_emb.to(args.device, non_blocking=True)
+        img = img_emb.unsqueeze(1).to(args.device, non_blocking=True)
         scores_l.append(model(text, img, None).view(-1))
         gold_l.append(tgts.to(args.device).view(-1))
     meter = AverageNDCGMeter()
