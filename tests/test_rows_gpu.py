@@ -57,6 +57,36 @@ def test_ndcg_ties_ragged_and_all_zero():
     assert (out == 1).all()
 
 
+@pytest.mark.parametrize("N", [7, 32, 33, 64, 200, 1024])
+@pytest.mark.parametrize("kind", ["short_runs", "long_runs", "signed_zero_and_ties", "mixed_lens"])
+def test_ndcg_truncated_key_repair_is_exact(N, kind):
+    """The 32-bit warp kernel sorts on the top 22 bits of the score key and repairs the order of colliding keys
+    (odd-even rounds, then a full-key shared-memory sort when runs are long).  Scores that differ only in their LOW
+    bits exercise every branch; the result must still be the stable descending order of the exact fp32 scores."""
+    rng = np.random.default_rng(N * 7 + len(kind))
+    B = 96
+    if kind == "short_runs":          # pairs / triples inside one 2^-13 relative bucket, plus ordinary scores
+        base = rng.standard_normal((B, N)).astype(np.float32)
+        twin = rng.integers(0, N, (B, N))
+        near = np.take_along_axis(base, twin, 1) * (1 + rng.integers(-3, 4, (B, N)).astype(np.float32) * np.float32(2 ** -21))
+        scores = np.where(rng.random((B, N)) < 0.3, near, base).astype(np.float32)
+    elif kind == "long_runs":         # hundreds of scores inside one bucket: forces the bail-out path
+        scores = (1.0 + rng.integers(0, 60, (B, N)) * np.float32(2 ** -20)).astype(np.float32)
+        scores[::2] *= -1
+    elif kind == "signed_zero_and_ties":
+        scores = rng.integers(-2, 3, (B, N)).astype(np.float32)
+        scores[scores == 0] = np.where(rng.random((scores == 0).sum()) < 0.5, -0.0, 0.0)
+    else:
+        scores = (rng.standard_normal((B, N)) * np.float32(1e-3) + 5).astype(np.float32)   # one exponent, dense
+    labels = rng.integers(0, 5, (B, N))
+    lens = rng.integers(1, N + 1, B).astype(np.int32) if kind == "mixed_lens" else None
+    ref, ref_order = restate.ndcg_at_k(scores, labels, KS, lens=lens, want_order=True)
+    out, order = ops.ndcg_at_k(cu(scores), cu(labels, torch.int64), KS,
+                               lens=None if lens is None else cu(lens, torch.int32), want_order=True)
+    assert np.array_equal(order.cpu().numpy(), ref_order)
+    assert out.cpu().numpy().tobytes() == ref.tobytes()
+
+
 @pytest.mark.parametrize("N", [48, 300, 1024])
 def test_ndcg_general_labels_ragged_unsorted_cuts(N):
     # labels outside [0, 62] in every other query (second register sort of the int64 label keys) next to
