@@ -15,6 +15,57 @@ import torch
 import torch.distributed as dist
 
 
+class RowParallel:
+    """out_layer.fc1 row-parallel over the data-parallel ranks (used by engine.FusionEngine when attached by
+    GradSync.attach(..., tensor_parallel=True)).
+
+    The row-sharded optimizer of round 1 kept a complete bf16 copy of the weight on every rank and re-assembled it
+    after every step: an all-gather of 1 GB per model per step (2 x 875 MB received per rank at 8 GPUs, the largest
+    exposed item of the 8-GPU step).  Row-parallel execution never needs foreign rows: rank r evaluates output
+    features [r0, r1) for the items of ALL ranks (forward: all-gather of the 15.6 MB activation rows, then a 37 KB
+    all-to-all of the results; backward: all-gather of dY, partial input gradients through the own rows, reduce-scatter).
+    Per model and step at 8 GPUs each rank now receives 3 x 109 MB instead of 875 + 109 MB, and streams 1/8 of the
+    weight from HBM in every forward / dgrad / wgrad pass.  `active = False` (after GradSync.gather_shadow) restores
+    replicated execution for code that is not run in lock-step by all ranks (evaluation)."""
+
+    def __init__(self, world, rank, rows, group=None):
+        self.world, self.rank, self.rows, self.group, self.active = world, rank, tuple(rows), group, True
+
+    def all_gather(self, t):
+        out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
+        return out
+
+    def all_to_all(self, t):
+        """t [world, ...]: block q goes to rank q; returns [world, ...] with block q received from rank q."""
+        out = torch.empty_like(t)
+        dist.all_to_all_single(out, t.contiguous(), group=self.group)
+        return out
+
+    def reduce_scatter_async(self, t):
+        """t [world * rows, D] -> handle; handle() waits and returns this rank's [rows, D] block of the sum."""
+        rows = t.shape[0] // self.world
+        if dist.get_backend(self.group) == "gloo":        # gloo has no reduce-scatter (CPU algebra tests): sum, slice
+            full = t.contiguous().clone()
+            dist.all_reduce(full, group=self.group)
+            return lambda: full[self.rank * rows:(self.rank + 1) * rows].clone()
+        out = torch.empty((rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+        work = dist.reduce_scatter_tensor(out, t.contiguous(), group=self.group, async_op=True)
+
+        def handle():
+            work.wait()
+            return out
+        return handle
+
+    def exchange_features(self, part, items):
+        """part [slots, world * items, R]: this rank's output features for the items of every rank (rank-major rows)
+        -> [slots, items, world * R]: all output features of this rank's own items (feature block q came from rank q)."""
+        slots, _, R = part.shape
+        send = part.view(slots, self.world, items, R).transpose(0, 1).contiguous()      # [world, slots, items, R]
+        recv = self.all_to_all(send)                                                    # [world(q), slots, items, R]
+        return recv.permute(1, 2, 0, 3).reshape(slots, items, self.world * R).contiguous()
+
+
 class GradSync:
     def __init__(self, world, group=None):
         self.world = world
@@ -62,7 +113,7 @@ class GradSync:
             return out
         return handle
 
-    def attach(self, module, optimizer, shard_fc1=None):
+    def attach(self, module, optimizer, shard_fc1=None, tensor_parallel=None):
         """Enable the activation-gather path for the module's out_layer.fc1 and fold 1/world into AdamW.
 
         shard_fc1 (default on, LR2_DP_SHARD=0 disables): ZeRO-1 style row sharding of out_layer.fc1 (97 % of the
@@ -75,6 +126,10 @@ class GradSync:
         import os
         if shard_fc1 is None:
             shard_fc1 = os.environ.get("LR2_DP_SHARD", "1") == "1"
+        if tensor_parallel is None:
+            # tensor_parallel (default on with the row sharding, LR2_DP_TP=0 disables): run out_layer.fc1 row-parallel
+            # (RowParallel above) instead of all-gathering the updated bf16 weight after every step
+            tensor_parallel = os.environ.get("LR2_DP_TP", "1") == "1"
         rank = dist.get_rank(self.group)
         for e in self._engines(module):
             e.dp_gather = self.gather_rows
@@ -88,6 +143,8 @@ class GradSync:
                 e.fc1_rows = (rank * rows, (rank + 1) * rows)
                 optimizer.set_window(w, rank, self.world)
                 self._sharded[id(module)] = (e, w)
+                e.tp = RowParallel(self.world, rank, e.fc1_rows, self.group) if tensor_parallel and rows % 128 == 0 \
+                    else None
                 if id(module) not in self._guarded:
                     # state_dict() of a module whose foreign rows are stale would silently save torn weights:
                     # refuse until consolidate() ran (checkpoint.save_sharded reads only the owned rows and opts out)
@@ -124,10 +181,44 @@ class GradSync:
         self._dirty.add(id(module))
         if id(module) in self._opt_of:
             self._dirty_opt.add(id(self._opt_of[id(module)]))
+        if e.tp is not None and e.tp.active:
+            return lambda: None              # row-parallel execution never reads foreign rows: nothing to gather
         shadow = e.bank.get(w)
         r0, r1 = e.fc1_rows
         work = dist.all_gather_into_tensor(shadow, shadow[r0:r1], group=self.group, async_op=True)
         return work.wait
+
+    def gather_shadow(self, module):
+        """All-gather the bf16 rows of a row-parallel out_layer.fc1 so that every rank holds the complete weight copy
+        again (blocking).  Needed before code that does not run in lock-step on all ranks."""
+        ent = self._sharded.get(id(module))
+        if ent is None:
+            return
+        e, w = ent
+        shadow = e.bank.get(w)
+        r0, r1 = e.fc1_rows
+        dist.all_gather_into_tensor(shadow, shadow[r0:r1].clone(), group=self.group)
+
+    def replicated(self, *modules):
+        """Context manager: inside it the given modules run replicated (complete bf16 weights, no collectives in
+        forward) -- e.g. evaluation, where ranks score different numbers of clips per forward."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def scope():
+            tps = []
+            for m in modules:
+                ent = self._sharded.get(id(m))
+                if ent is not None and ent[0].tp is not None:
+                    self.gather_shadow(m)
+                    ent[0].tp.active = False
+                    tps.append(ent[0].tp)
+            try:
+                yield
+            finally:
+                for tp in tps:
+                    tp.active = True
+        return scope()
 
     def row_shards(self, module):
         """{parameter name: (r0, r1)} of the rows of `module`'s row-sharded parameters that this rank owns

@@ -266,6 +266,7 @@ class FusionEngine:
         self.fc1_rows = None         # (r0, r1): rows of out_layer.fc1 this rank owns (row-sharded optimizer)
         self.fc1_grad_bf16 = None  # bf16 [out, in] gradient buffer of out_layer.fc1.weight (see enable_bf16_fc1_grad)
         self._zero_index = {}      # (bs, T, device) -> int64 zeros [bs, T]: broadcast index of un-repeated img_emb
+        self.tp = None             # dist.RowParallel: out_layer.fc1 row-parallel over the data-parallel ranks
 
     def begin_step(self):
         """Persistent-gradient mode: start of a new optimizer step (replaces model.zero_grad())."""
@@ -354,22 +355,30 @@ class FusionEngine:
                              regroup=(S, S + I, 0), seed_dev=seed_dev)
         ops.rows_copy(imf, I, 0, cat_rows, S + I, S, items, I, E)
         cat_all = None
-        if save and self.dp_gather_async is not None and self.fc1_grad_bf16 is not None:
-            cat_all = self.dp_gather_async(cat)      # wgrad operand X of out_layer.fc1, consumed in backward
-        # out_layer.fc1: weight is the 128-row MMA operand, items are N; split-K streams the weight once
         o1 = W["o1"]
         hid = o1.w.shape[0]
-        pre3 = torch.empty((items, hid), dtype=bf16, device=text.device) if save else None
-        if items <= 256:
-            bn = 64 if items <= 64 else (128 if items <= 128 else 256)
-            kblocks = (cat.shape[1] + 63) // 64
-            m_tiles = (hid + 127) // 128
-            splits = max(1, min(kblocks, 148 // m_tiles))
-            y1 = torch.empty((items, hid), dtype=bf16, device=text.device)
-            ops.gemm(o1.w, cat, out=y1, transposed_out=True, epilogue=EPI_BIAS_GELU, bias=o1.b, c2=pre3,
-                     splits=splits, block_n=bn)
+        tp = self.tp if (self.tp is not None and self.tp.active) else None
+        if tp is not None:
+            # out_layer.fc1 row-parallel over the data-parallel ranks (dist.GradSync, tensor_parallel): this rank holds
+            # (and updates) only rows [r0, r1) of the 3072 x 162816 weight, so it evaluates THOSE output features for
+            # the items of EVERY rank and the results are exchanged -- 37 KB per rank pair instead of all-gathering the
+            # updated 1 GB weight after every optimizer step.  HBM: the weight stream shrinks by `world` too.
+            y1, pre3, cat_all = self._fc1_forward_tp(tp, o1, cat, items, save)
         else:
-            y1 = ops.gemm(cat, o1.w, epilogue=EPI_BIAS_GELU, bias=o1.b, c2=pre3, splits=4)
+            if save and self.dp_gather_async is not None and self.fc1_grad_bf16 is not None:
+                cat_all = self.dp_gather_async(cat)      # wgrad operand X of out_layer.fc1, consumed in backward
+            # out_layer.fc1: weight is the 128-row MMA operand, items are N; split-K streams the weight once
+            pre3 = torch.empty((items, hid), dtype=bf16, device=text.device) if save else None
+            if items <= 256:
+                bn = 64 if items <= 64 else (128 if items <= 128 else 256)
+                kblocks = (cat.shape[1] + 63) // 64
+                m_tiles = (hid + 127) // 128
+                splits = max(1, min(kblocks, 148 // m_tiles))
+                y1 = torch.empty((items, hid), dtype=bf16, device=text.device)
+                ops.gemm(o1.w, cat, out=y1, transposed_out=True, epilogue=EPI_BIAS_GELU, bias=o1.b, c2=pre3,
+                         splits=splits, block_n=bn)
+            else:
+                y1 = ops.gemm(cat, o1.w, epilogue=EPI_BIAS_GELU, bias=o1.b, c2=pre3, splits=4)
         feat = ops.gemm(y1, W["o2"].w, epilogue=EPI_BIAS, bias=W["o2"].b)
         if reuse:
             feat = ops.gather_rows(feat.view(bs, Tsrc, E), index).view(bs * T, E)
@@ -383,7 +392,7 @@ class FusionEngine:
                 logits = _small_linear(feat, m.head, self.bank)
             if save:
                 ctx = dict(W=W, dims=(bs, T, S, I, E, items), c_tp=c_tp, c_ip=c_ip, c_x=c_x, cat=cat, pre3=pre3,
-                           y1=y1, feat=feat, imf=imf, cat_all=cat_all)
+                           y1=y1, feat=feat, imf=imf, cat_all=cat_all, tp=tp)
             return logits, ctx
         # critic / reward: + pos_emb, self-attention over the T items, head on the LAST token
         ops.add_pos_fwd(feat, m.pos_emb.weight.detach()[:T].contiguous(), bs, T)
@@ -391,8 +400,39 @@ class FusionEngine:
         logits = ops.rowdot_fwd(z, m.head.weight.detach().view(-1), m.head.bias.detach(), bs, T, T - 1)
         if save:
             ctx = dict(W=W, dims=(bs, T, S, I, E, items), c_tp=c_tp, c_ip=c_ip, c_x=c_x, cat=cat, pre3=pre3, y1=y1,
-                       feat=feat, imf=imf, c_t=c_t, z=z, cat_all=cat_all)
+                       feat=feat, imf=imf, c_t=c_t, z=z, cat_all=cat_all, tp=tp)
         return logits, ctx
+
+    def _fc1_forward_tp(self, tp, o1, cat, items, save):
+        """Row-parallel out_layer.fc1 forward.  Returns (y1 [items, hid], pre3 [items, hid] | None, X_all | None)."""
+        dev = cat.device
+        hid = o1.w.shape[0]
+        r0, r1 = tp.rows
+        R, total = r1 - r0, tp.world * items
+        x_all = tp.all_gather(cat)                                   # [world * items, K1], rank-major rows
+        # own output features for everybody's items; slot 0 = GELU output, slot 1 = pre-activation (for backward)
+        part = torch.empty((2 if save else 1, total, R), dtype=bf16, device=dev)
+        bn = 64 if total <= 64 else (128 if (total <= 128 or total > 256) else 256)
+        n_tiles = (total + bn - 1) // bn
+        kblocks = (cat.shape[1] + 63) // 64
+        splits = max(1, min(kblocks, 148 // (((R + 127) // 128) * n_tiles)))
+        ops.gemm(o1.w[r0:r1], x_all, out=part[0], transposed_out=True, epilogue=EPI_BIAS_GELU, bias=o1.b[r0:r1],
+                 c2=part[1] if save else None, splits=splits, block_n=bn)
+        full = tp.exchange_features(part, items)     # 37 KB per rank pair: everybody's features of MY items
+        return full[0], (full[1] if save else None), (x_all if save else None)
+
+    def _fc1_backward_tp(self, tp, o1, dy1p, x_all, items):
+        """Row-parallel out_layer.fc1 backward: weight gradient of the own rows from everybody's (dY, X); input gradient
+        as partial products over the own rows, summed over the ranks by a reduce-scatter."""
+        r0, r1 = tp.rows
+        dy_all = tp.all_gather(dy1p)                                 # [world * items, hid] (295 KB per rank)
+        dy_own = dy_all[:, r0:r1]                                    # strided view: pitch hid
+        # partial dX for EVERY rank's items through the own rows: [world * items, K1]
+        partial = ops.gemm(dy_own, o1.w[r0:r1], b_mn=True)
+        wait_dx = tp.reduce_scatter_async(partial)                   # NVLink transfer overlaps the wgrad GEMM below
+        bn = 128 if dy_all.shape[0] <= 256 else 256
+        ops.gemm(dy_own, x_all, a_mn=True, b_mn=True, out=self.fc1_grad_bf16[r0:r1], block_n=bn)
+        return wait_dx()                                             # [items, K1]: sum over the ranks of the partials
 
     def backward(self, ctx, dlogits):
         """Accumulates fp32 gradients into module.parameters().grad (allocating when None)."""
@@ -422,7 +462,15 @@ class FusionEngine:
         _wgrad(sink, W["o2"].mod, dfeat, ctx["y1"])
         dy1p = _dgrad(dfeat, W["o2"].w, epilogue=EPI_DGELU, aux=ctx["pre3"])
         deferred_fc1 = None
-        if self.fc1_stash is not None:
+        tp = ctx.get("tp")
+        if tp is not None:
+            sink.put_vec(W["o1"].mod.bias, ops.colsum(dy1p))      # own items only: summed over ranks with the small grads
+            dcat = self._fc1_backward_tp(tp, W["o1"], dy1p, ctx["cat_all"], items)
+        else:
+            dcat = None
+        if tp is not None:
+            pass
+        elif self.fc1_stash is not None:
             # fused mode: the optimizer consumes (dY, X) in lr2_gemm_wgrad_adamw; no 2 GB gradient is written
             self.fc1_stash.append((dy1p, ctx["cat"]))
             sink.put_vec(W["o1"].mod.bias, ops.colsum(dy1p))
@@ -440,12 +488,15 @@ class FusionEngine:
             _wgrad(sink, W["o1"].mod, self.dp_gather(dy1p), self.dp_gather(ctx["cat"]), bias_from=dy1p)
         else:
             _wgrad(sink, W["o1"].mod, dy1p, ctx["cat"])
-        dcat = torch.empty_like(ctx["cat"])
-        if items <= 256:
+        if dcat is not None:
+            pass
+        elif items <= 256:
+            dcat = torch.empty_like(ctx["cat"])
             bn = 64 if items <= 64 else (128 if items <= 128 else 256)
             # dcat^T[K1, items] = W1^T[K1, hid] @ dy1p^T : W1 is the MN-major A operand, output written transposed
             ops.gemm(W["o1"].w, dy1p, a_mn=True, out=dcat, transposed_out=True, block_n=bn)
         else:
+            dcat = torch.empty_like(ctx["cat"])
             ops.gemm(dy1p, W["o1"].w, b_mn=True, out=dcat)
         dcat_rows = dcat.view(items * (S + I), E)
         dimf = torch.empty((items * I, E), dtype=bf16, device=dcat.device)

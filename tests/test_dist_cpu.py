@@ -2,6 +2,8 @@
 The CUDA kernels are not involved; this checks the collective plumbing and the algebra that lets out_layer.fc1
 all-gather its wgrad operands instead of all-reducing the 2 GB gradient."""
 import os
+
+import pytest
 import tempfile
 
 import torch
@@ -206,3 +208,38 @@ def _shard_worker(rank, world, path, ckdir):
 def test_row_sharded_optimizer_and_sharded_checkpoint_world2_gloo():
     with tempfile.TemporaryDirectory() as d:
         mp.spawn(_shard_worker, args=(2, os.path.join(d, "rdzv"), os.path.join(d, "ck")), nprocs=2, join=True)
+
+
+# ---- row-parallel out_layer.fc1 (dist.RowParallel): the exchange algebra on CPU, world 2 and 4, gloo --------------
+def _tp_worker(rank, world, path):
+    from lr2ppo_b200.dist import RowParallel
+    dist.init_process_group("gloo", init_method=f"file://{path}", rank=rank, world_size=world)
+    items, K1, hid = 3, 40, 8 * world
+    R = hid // world
+    g = torch.Generator().manual_seed(1)                         # the same on every rank
+    W = torch.randn(hid, K1, generator=g, dtype=torch.float64)
+    X = [torch.randn(items, K1, generator=g, dtype=torch.float64) for _ in range(world)]
+    dY = [torch.randn(items, hid, generator=g, dtype=torch.float64) for _ in range(world)]
+    tp = RowParallel(world, rank, (rank * R, (rank + 1) * R))
+    r0, r1 = tp.rows
+    # forward: own features for everybody's items, then the exchange (slot 1 carries a second tensor, like pre3)
+    x_all = tp.all_gather(X[rank])
+    assert torch.equal(x_all, torch.cat(X))
+    part = torch.stack([x_all @ W[r0:r1].t(), 2 * (x_all @ W[r0:r1].t())])
+    full = tp.exchange_features(part, items)
+    ref = X[rank] @ W.t()
+    assert torch.allclose(full[0], ref) and torch.allclose(full[1], 2 * ref)
+    # backward: dX through the own rows, summed by the reduce-scatter; weight gradient of the own rows
+    dy_all = tp.all_gather(dY[rank])
+    dx = tp.reduce_scatter_async(dy_all[:, r0:r1] @ W[r0:r1])()
+    assert torch.allclose(dx, dY[rank] @ W)
+    g_own = dy_all[:, r0:r1].t() @ x_all
+    g_ref = sum(dY[q].t() @ X[q] for q in range(world))
+    assert torch.allclose(g_own, g_ref[r0:r1])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_row_parallel_exchange_algebra_gloo(world, tmp_path):
+    mp.spawn(_tp_worker, args=(world, str(tmp_path / "pg")), nprocs=world, join=True)

@@ -2,7 +2,7 @@
 one stages.reward_train_model step with dist.GradSync on two ranks (half of the pairs each) must give the update of
 ONE rank stepping on the whole batch: same loss (mean of the two rank means), Adam first moments equal within the
 bf16 tolerance (2e-2 of each tensor's scale; tile shapes differ with the row count).  Dropout off, lr = 1e-3 constant.
-Not yet run (written after the round-1 GPU budget was spent)."""
+Two steps are taken in both runs: the second step's loss only agrees if the forward weights followed the first update."""
 import argparse
 import os
 import sys
@@ -61,8 +61,10 @@ def main():
     sync = GradSync(world)
     sync.broadcast_params(model)
     sync.attach(model, opt)
-    loss_dp, _ = stages.reward_train_model(args, model, opt, sch, text[sl].to(dev), img[sl].to(dev), tgts[sl].to(dev),
-                                           chosen[sl].to(dev), reject[sl].to(dev), grad_sync=sync)
+    for _ in range(2):      # the SECOND step's loss is computed with the weights the first step produced
+        loss_dp, _ = stages.reward_train_model(args, model, opt, sch, text[sl].to(dev), img[sl].to(dev),
+                                               tgts[sl].to(dev), chosen[sl].to(dev), reject[sl].to(dev),
+                                               grad_sync=sync)
     loss_mean = loss_dp.detach().clone()
     dist.all_reduce(loss_mean)
     loss_mean /= world
@@ -71,8 +73,12 @@ def main():
     torch.cuda.empty_cache()
     # reference: one rank, whole batch, no synchronisation
     model, opt, sch = build(dev)
-    loss_1, _ = stages.reward_train_model(args, model, opt, sch, text.to(dev), img.to(dev), tgts.to(dev),
-                                          chosen.to(dev), reject.to(dev))
+    first = None
+    for _ in range(2):
+        loss_1, _ = stages.reward_train_model(args, model, opt, sch, text.to(dev), img.to(dev), tgts.to(dev),
+                                              chosen.to(dev), reject.to(dev))
+        first = loss_1.item() if first is None else first
+    assert abs(loss_1.item() - first) > 1e-4 * abs(first), "the second step did not see the updated weights"
     bad = []
     for n, p in model.named_parameters():
         a, b = m_dp[n].float(), opt.state[p]["exp_avg"].float()
