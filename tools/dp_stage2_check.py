@@ -1,7 +1,7 @@
 """2-GPU cross-check of data-parallel stage 2 (BASELINE configs[2]; torchrun --nproc-per-node 2 tools/dp_stage2_check.py):
 one stages.reward_train_model step with dist.GradSync on two ranks (half of the pairs each) must give the update of
 ONE rank stepping on the whole batch: same loss (mean of the two rank means), Adam first moments equal within the
-bf16 tolerance (2e-2 of each tensor's scale; tile shapes differ with the row count).  Dropout off, lr = 1e-3 constant.
+bf16 tolerance (tests/parity.py: 4e-2 of each tensor's scale, 0.12 on the pair-cancellation tensors; tile shapes differ with the row count).  Dropout off, lr = 1e-3 constant.
 Two steps are taken in both runs: the second step's loss only agrees if the forward weights followed the first update."""
 import argparse
 import os
@@ -86,7 +86,9 @@ def main():
         if scale == 0.0:
             continue
         err = (a - b).abs().max().item() / scale
-        if err > 2e-2:
+        # the bf16 bounds of tests/parity.py: 4e-2 per gradient tensor, 0.12 where the chosen / reject passes cancel
+        tol = 0.12 if any(k in n for k in ("pos_emb", "out_layer.fc2.bias", "xitt.")) else 4e-2
+        if err > tol:
             bad.append((n, err))
     lerr = abs(loss_mean.item() - loss_1.item()) / max(1e-6, abs(loss_1.item()))
     print(f"[rank {rank}] loss dp-mean {loss_mean.item():.6f} vs single {loss_1.item():.6f} (rel {lerr:.2e}); "
