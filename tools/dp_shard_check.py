@@ -102,13 +102,15 @@ def main():
           f"{moved:.3e}; stats {a['stats'][:3].tolist()} vs {b['stats'][:3].tolist()}", flush=True)
     # ---- tp vs replicated: bf16 tolerance
     worst = ("", 0.0)
+    top = {tag: max(a[k].float().abs().max().item() for k in a if k.startswith(tag) and k.endswith(".m"))
+           for tag in ("actor", "critic")}
     for k in a:
         if not k.endswith(".m") and k != "stats":
             continue
         ref, got = a[k].float(), c[k].float()
         scale = ref.abs().max().item()
-        if k != "stats" and scale < 1e-9:
-            continue                                   # mathematically-zero gradients (keys.bias, actor head.bias)
+        if k != "stats" and scale < 1e-4 * top[k.split(".")[0]]:
+            continue       # mathematically-zero gradients (keys.bias, the actor's head.bias): fp32 noise on both sides
         err = (ref - got).abs().max().item() / max(scale, 1e-30)
         if err > worst[1]:
             worst = (k, err)

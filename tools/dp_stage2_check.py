@@ -80,11 +80,12 @@ def main():
         first = loss_1.item() if first is None else first
     assert abs(loss_1.item() - first) > 1e-4 * abs(first), "the second step did not see the updated weights"
     bad = []
+    top = max(opt.state[p]["exp_avg"].abs().max().item() for p in model.parameters())
     for n, p in model.named_parameters():
         a, b = m_dp[n].float(), opt.state[p]["exp_avg"].float()
         scale = b.abs().max().item()
-        if scale == 0.0:
-            continue
+        if scale < 1e-4 * top:
+            continue          # mathematically-zero gradients (keys.bias: softmax is shift-invariant): noise on both sides
         err = (a - b).abs().max().item() / scale
         # the bf16 bounds of tests/parity.py: 4e-2 per gradient tensor, 0.12 where the chosen / reject passes cancel
         tol = 0.12 if any(k in n for k in ("pos_emb", "out_layer.fc2.bias", "xitt.")) else 4e-2
