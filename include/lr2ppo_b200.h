@@ -142,6 +142,11 @@ int lr2_embed_scatter_add(const long long* idx, const void* d_bf16, float* table
 /* im2col for Conv2d(k = s = ps, no bias): [B,C,H,W] f32 -> [B*(H/ps)*(W/ps), C*ps*ps] bf16
  * ref: embeddings/patch_embedding.py:18,27 */
 int lr2_patchify(const float* img, void* out_bf16, int B, int C, int Hh, int Ww, int ps, void* stream);
+/* out = gelu(bf16(x + bias)), pre (optional) = bf16(x + bias): the bias + exact-GELU epilogue of Mlp.fc1
+ * (finetune/ppo.py:164-166) applied to fp32 pre-activation sums that were reduced over the ranks (K-split
+ * out_layer.fc1, lr2ppo_b200/dist.py); same arithmetic as the LR2_EPI_BIAS_GELU epilogue.  x fp32 [rows, D]. */
+int lr2_bias_gelu_rows(const float* x, const float* bias, void* out_bf16, void* pre_bf16, long long rows, int D,
+                       void* stream);
 /* out = x * keep(seed, site, element index) / (1-p): elementwise dropout / its backward (n % 8 == 0) */
 int lr2_dropout_bf16(const void* x, void* out, long long n, float p, unsigned long long seed, unsigned int site,
                      const void* seed_dev, void* stream);
@@ -258,7 +263,9 @@ int lr2_ndcg_presorted(const long long* pred_rel, const long long* true_rel, con
  * ref: tencentpretrain/utils/optimizers.py:344-402.
  * The tensor table lives in device memory: for tensor t, ptrs[6*t+0..5] =
  *   {p f32, g, m f32, v f32, shadow bf16 or NULL, unused}; meta[4*t+0..3] = {n, wd (float bits), g_is_bf16, 0}.
- * chunks[2*c+0..1] = {tensor id, element offset}; each chunk covers lr2_adamw_chunk_elems() elements.
+ * chunks[2*c+0..1] = {tensor id | (length << 32), element offset}; length 0 = the default chunk of
+ * lr2_adamw_chunk_elems() elements (or up to the tensor's end); an explicit length (multiple of 4, at most the default)
+ * is a piece of a column block of a 2-D parameter (column-sharded data-parallel optimizer).
  * hyper (device, 8 floats) = {step_size, beta1, beta2, eps, 1-beta1, 1-beta2, grad_scale, lr_for_decay}
  * (step_size == lr when correct_bias is False, as in every LR2PPO script).
  */

@@ -42,6 +42,7 @@ SIGNATURES = {
     "lr2_embed_scatter_add": (i32, [vp, vp, vp, i64, i32, vp]),
     "lr2_patchify": (i32, [vp, vp, i32, i32, i32, i32, i32, vp]),
     "lr2_dropout_bf16": (i32, [vp, vp, i64, f32, u64, u32, vp, vp]),
+    "lr2_bias_gelu_rows": (i32, [vp, vp, vp, vp, i64, i32, vp]),
     "lr2_cast_gather_bf16": (i32, [vp, vp, vp, i32, i32, i32, i64, vp]),
     "lr2_gather_rows_bf16": (i32, [vp, vp, vp, i32, i32, i32, i64, vp]),
     "lr2_rows_copy_bf16": (i32, [vp, i64, i64, vp, i64, i64, i64, i64, i32, i32, vp]),

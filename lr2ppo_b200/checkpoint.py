@@ -199,6 +199,11 @@ def _state_index(optimizer, param):
     raise KeyError("parameter is not managed by this optimizer")
 
 
+def _block(desc):
+    """(r0, r1) -> (0, r0, r1): a row block; (dim, lo, hi) stays (K-split out_layer.fc1: a column block)."""
+    return (0,) + tuple(int(x) for x in desc) if len(desc) == 2 else tuple(int(x) for x in desc)
+
+
 def _shard_name(rank, world):
     return f"shard-{rank:05d}-of-{world:05d}.pt"
 
@@ -236,18 +241,19 @@ def save_sharded(dirpath, models, optimizers, schedulers, step, rank, world, row
                 osd = opt.state_dict()
             finally:
                 opt._lr2_sharded_save = False
-        for name, (r0, r1) in mine.items():
+        for name, desc in mine.items():
+            dim, r0, r1 = _block(desc)
             p = named[name]
-            shard["rows"].setdefault(key, {})[name] = (int(r0), int(r1))
-            shard["param"].setdefault(key, {})[name] = p.detach()[r0:r1]
+            shard["rows"].setdefault(key, {})[name] = (dim, r0, r1)
+            shard["param"].setdefault(key, {})[name] = p.detach().narrow(dim, r0, r1 - r0)
             common["sharded"].setdefault(key, {})[name] = list(p.shape)
             sd.pop(name)
             if opt is not None:
                 idx = _state_index(opt, p)
                 st = osd["state"].get(idx)
                 if st is not None:
-                    shard["exp_avg"].setdefault(key, {})[name] = st["exp_avg"][r0:r1]
-                    shard["exp_avg_sq"].setdefault(key, {})[name] = st["exp_avg_sq"][r0:r1]
+                    shard["exp_avg"].setdefault(key, {})[name] = st["exp_avg"].narrow(dim, r0, r1 - r0)
+                    shard["exp_avg_sq"].setdefault(key, {})[name] = st["exp_avg_sq"].narrow(dim, r0, r1 - r0)
                     osd["state"][idx] = {k: v for k, v in st.items() if k not in ("exp_avg", "exp_avg_sq")}
         if rank == 0:
             common["models"][key] = sd
@@ -282,17 +288,22 @@ def _read_sharded(dirpath, map_location="cpu"):
 
 
 def _assemble(shape, pieces):
-    """pieces: [((r0, r1), rows tensor)] -> complete tensor; the row ranges must tile [0, shape[0]) exactly."""
-    pieces = sorted(pieces, key=lambda x: x[0][0])
+    """pieces: [((r0, r1) | (dim, lo, hi), block tensor)] -> complete tensor; the blocks must tile [0, shape[dim])
+    exactly along one common dimension."""
+    pieces = sorted(((_block(d), t) for d, t in pieces), key=lambda x: x[0][1])
+    dims = {d[0] for d, _ in pieces}
+    if len(dims) != 1:
+        raise RuntimeError("shards of one parameter are split along different dimensions")
+    dim = dims.pop()
     at = 0
-    for (r0, r1), t in pieces:
-        if r0 != at or r1 <= r0 or t.shape[0] != r1 - r0:
-            raise RuntimeError(f"row shards do not tile the parameter: expected a piece starting at row {at}, "
-                               f"got rows [{r0}, {r1}) with {t.shape[0]} rows")
+    for (_, r0, r1), t in pieces:
+        if r0 != at or r1 <= r0 or t.shape[dim] != r1 - r0:
+            raise RuntimeError(f"row shards do not tile the parameter: expected a piece starting at index {at} of "
+                               f"dim {dim}, got [{r0}, {r1}) with extent {t.shape[dim]}")
         at = r1
-    if at != shape[0]:
-        raise RuntimeError(f"row shards cover {at} of {shape[0]} rows")
-    return torch.cat([t for _, t in pieces], dim=0).reshape(shape)
+    if at != shape[dim]:
+        raise RuntimeError(f"row shards cover {at} of {shape[dim]} entries of dim {dim}")
+    return torch.cat([t for _, t in pieces], dim=dim).reshape(shape)
 
 
 def load_sharded(dirpath, models, optimizers, schedulers, map_location="cpu"):

@@ -22,7 +22,12 @@ __device__ __forceinline__ void adamw_elem(float& p, float g, float& m, float& v
 __global__ void __launch_bounds__(AW_THREADS)
 adamw_multi_kernel(const void* const* __restrict__ ptrs, const long long* __restrict__ meta,
                    const long long* __restrict__ chunks, const float* __restrict__ hyper) {
-  const long long t = chunks[2 * (long long)blockIdx.x];
+  // chunks[2c] = tensor id | (length << 32): length 0 = a default chunk (AW_CHUNK elements or up to the tensor's end);
+  // an explicit length (a multiple of 4, <= AW_CHUNK) describes a piece of a COLUMN block of a 2-D parameter
+  // (column-sharded out_layer.fc1: each owned row segment is cut into such pieces)
+  const long long w0 = chunks[2 * (long long)blockIdx.x];
+  const long long t = w0 & 0xFFFFFFFFll;
+  const long long len = (w0 >> 32) & 0x7FFFFFFFll;
   const long long off = chunks[2 * (long long)blockIdx.x + 1];
   float* p = (float*)ptrs[6 * t + 0];
   const void* g = ptrs[6 * t + 1];
@@ -34,39 +39,41 @@ adamw_multi_kernel(const void* const* __restrict__ ptrs, const long long* __rest
   const bool g_bf16 = meta[4 * t + 2] != 0;
   const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], omb1 = hyper[4], omb2 = hyper[5],
               gscale = hyper[6], lr_decay = hyper[7];
-  const long long end = min(n, off + AW_CHUNK);
+  const long long end = len ? off + len : min(n, off + AW_CHUNK);
   const bool aligned = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(m) |
                          reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(g)) & 15) == 0 &&
-                       (sh == nullptr || (reinterpret_cast<uintptr_t>(sh) & 7) == 0);
+                       (sh == nullptr || (reinterpret_cast<uintptr_t>(sh) & 7) == 0) && (off & 3) == 0;
+  auto vec4 = [&](long long i) {
+    float4 pv = *reinterpret_cast<const float4*>(p + i);
+    float4 mv = *reinterpret_cast<const float4*>(m + i);
+    float4 vv = *reinterpret_cast<const float4*>(v + i);
+    float4 gv;
+    if (g_bf16) {
+      const uint2 u = *reinterpret_cast<const uint2*>((const bf16*)g + i);
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+      gv = make_float4(a.x, a.y, b.x, b.y);
+    } else {
+      gv = *reinterpret_cast<const float4*>((const float*)g + i);
+    }
+    adamw_elem(pv.x, gv.x * gscale, mv.x, vv.x, lr, b1, b2, eps, omb1, omb2, wd, lr_decay);
+    adamw_elem(pv.y, gv.y * gscale, mv.y, vv.y, lr, b1, b2, eps, omb1, omb2, wd, lr_decay);
+    adamw_elem(pv.z, gv.z * gscale, mv.z, vv.z, lr, b1, b2, eps, omb1, omb2, wd, lr_decay);
+    adamw_elem(pv.w, gv.w * gscale, mv.w, vv.w, lr, b1, b2, eps, omb1, omb2, wd, lr_decay);
+    *reinterpret_cast<float4*>(p + i) = pv;
+    *reinterpret_cast<float4*>(m + i) = mv;
+    *reinterpret_cast<float4*>(v + i) = vv;
+    if (sh != nullptr) {
+      uint2 o;
+      o.x = pack_bf16x2(pv.x, pv.y);
+      o.y = pack_bf16x2(pv.z, pv.w);
+      *reinterpret_cast<uint2*>(sh + i) = o;
+    }
+  };
   if (aligned && end - off == AW_CHUNK) {
 #pragma unroll
-    for (int it = 0; it < AW_CHUNK / (AW_THREADS * 4); ++it) {
-      const long long i = off + (long long)(it * AW_THREADS + threadIdx.x) * 4;
-      float4 pv = *reinterpret_cast<const float4*>(p + i);
-      float4 mv = *reinterpret_cast<const float4*>(m + i);
-      float4 vv = *reinterpret_cast<const float4*>(v + i);
-      float4 gv;
-      if (g_bf16) {
-        const uint2 u = *reinterpret_cast<const uint2*>((const bf16*)g + i);
-        const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
-        gv = make_float4(a.x, a.y, b.x, b.y);
-      } else {
-        gv = *reinterpret_cast<const float4*>((const float*)g + i);
-      }
-      adamw_elem(pv.x, gv.x * gscale, mv.x, vv.x, lr, b1, b2, eps, omb1, omb2, wd, lr_decay);
-      adamw_elem(pv.y, gv.y * gscale, mv.y, vv.y, lr, b1, b2, eps, omb1, omb2, wd, lr_decay);
-      adamw_elem(pv.z, gv.z * gscale, mv.z, vv.z, lr, b1, b2, eps, omb1, omb2, wd, lr_decay);
-      adamw_elem(pv.w, gv.w * gscale, mv.w, vv.w, lr, b1, b2, eps, omb1, omb2, wd, lr_decay);
-      *reinterpret_cast<float4*>(p + i) = pv;
-      *reinterpret_cast<float4*>(m + i) = mv;
-      *reinterpret_cast<float4*>(v + i) = vv;
-      if (sh != nullptr) {
-        uint2 o;
-        o.x = pack_bf16x2(pv.x, pv.y);
-        o.y = pack_bf16x2(pv.z, pv.w);
-        *reinterpret_cast<uint2*>(sh + i) = o;
-      }
-    }
+    for (int it = 0; it < AW_CHUNK / (AW_THREADS * 4); ++it) vec4(off + (long long)(it * AW_THREADS + threadIdx.x) * 4);
+  } else if (aligned && len && (len & 3) == 0) {
+    for (long long i = off + (long long)threadIdx.x * 4; i < end; i += AW_THREADS * 4) vec4(i);
   } else {
     for (long long i = off + threadIdx.x; i < end; i += AW_THREADS) {
       float pv = p[i], mv = m[i], vv = v[i];

@@ -69,6 +69,7 @@ struct GemmParams {
   int act;             // activation of the GELU epilogues: 0 = exact erf GELU, 1 = QuickGELU x*sigmoid(1.702x)
   int mode;            // EpiMode resolved on the host from (epi, act, drop_p, bias)
   int dbg;             // LR2_GEMM_DBG (profiling experiments only): 1 = skip the accumulator drain, 2 = skip the MMAs
+  int direct;          // 1: full bf16 chunks go TMEM -> registers -> 256-bit global stores (no smem staging)
   // LR2_EPI_ADAMW (fused wgrad + AdamW): C = fp32 parameter (in/out)
   float* adam_m; float* adam_v; bf16* adam_shadow; const float* adam_hyper; float adam_wd;
 };
@@ -387,6 +388,121 @@ __device__ __forceinline__ void chunk_rows(const GemmParams& q, const OutSel& o,
   }
 }
 
+// ---- direct drain (round 2): TMEM -> registers -> global, no shared-memory staging --------------------------------
+// tcgen05.ld.32x32b hands every lane ONE output row (32 consecutive fp32 columns).  The staged path above re-shapes
+// that through shared memory into 4-lanes-per-row groups so that a warp store covers whole 64-byte row pieces; with
+// the 256-bit global accesses of sm_100 (STG.E.ENL2.256 / LDG.E.ENL2.256) a lane moves 16 bf16 = one full 32-byte
+// sector of its row per instruction, so sector efficiency is the same and the staging round trip -- 8 STS.128 +
+// 8 LDS.128 per lane and chunk, 2 x 128 KB of shared-memory traffic per 128 x 256 tile on top of the UMMA operand
+// reads and TMA fills that already sit at ~110 B/clk/SM of the 128 B/clk the SM has -- disappears.  Used for full
+// 32 x 32 chunks of untransposed bf16 outputs in the host-resolved fast modes; everything else keeps the staged path.
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&u)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]),
+               "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* ptr, uint32_t (&u)[8]) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "l"(ptr));
+}
+__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+
+template <int MODE>
+__device__ __forceinline__ void chunk_direct(const GemmParams& q, uint32_t taddr_c, int lane, int m_base, int n_base) {
+  constexpr bool HAS_BIAS = MODE == EM_BIAS || MODE == EM_BIAS_GELU || MODE == EM_BIAS_GELU_DROP ||
+                            MODE == EM_BIAS_RES || MODE == EM_BIAS_DROP_RES;
+  constexpr bool HAS_AUX = MODE == EM_BIAS_RES || MODE == EM_BIAS_DROP_RES || MODE == EM_DGELU ||
+                           MODE == EM_DGELU_DROP || MODE == EM_ADD;
+  constexpr bool HAS_DROP = MODE == EM_BIAS_GELU_DROP || MODE == EM_BIAS_DROP_RES || MODE == EM_DGELU_DROP;
+  constexpr bool IS_GELU = MODE == EM_BIAS_GELU || MODE == EM_BIAS_GELU_DROP;
+  uint32_t r[32];
+  tmem_ld32(taddr_c, r);
+  const long long row = m_base + lane;
+  const long long off = row * q.ldc + n_base;
+  // everything that does not depend on the accumulator is issued while the TMEM load is in flight
+  uint32_t ax[2][8];
+  if constexpr (HAS_AUX) {
+    const bf16* ap = q.aux + row * q.ldaux + n_base;
+    ld_global_256(ap, ax[0]);
+    ld_global_256(ap + 16, ax[1]);
+  }
+  unsigned long long seed = 0;
+  if constexpr (HAS_DROP) seed = q.seed + (q.seed_dev ? *q.seed_dev : 0ull);
+  const bool want_pre = IS_GELU && q.C2 != nullptr;
+  tmem_ld_wait();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[16 * h + i]);
+    if constexpr (HAS_BIAS) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float4 b = __ldg(reinterpret_cast<const float4*>(q.bias + n_base + 16 * h + 4 * g));   // warp-uniform
+        v[4 * g] += b.x; v[4 * g + 1] += b.y; v[4 * g + 2] += b.z; v[4 * g + 3] += b.w;
+      }
+    }
+    float m[16];
+    if constexpr (HAS_DROP) {
+      float m0[8], m1[8];
+      dropout_mult8(seed, q.site, (uint64_t)(off + 16 * h) >> 3, q.drop_thresh, q.drop_scale, m0);
+      dropout_mult8(seed, q.site, ((uint64_t)(off + 16 * h) >> 3) + 1, q.drop_thresh, q.drop_scale, m1);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { m[i] = m0[i]; m[8 + i] = m1[i]; }
+    }
+    float a[16];
+    if constexpr (HAS_AUX) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a[2 * i] = bf16lo(ax[h][i]); a[2 * i + 1] = bf16hi(ax[h][i]); }
+    }
+    if constexpr (IS_GELU) {
+      // GELU of the bf16-rounded pre-activation: backward only has the stored bf16 copy
+      uint32_t pre[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) pre[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+      if (want_pre) st_global_256(q.C2 + off + 16 * h, pre);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float x0 = bf16lo(pre[i]), x1 = bf16hi(pre[i]);
+        v[2 * i] = HAS_DROP ? gelu_fast(x0) * m[2 * i] : gelu_fast(x0);
+        v[2 * i + 1] = HAS_DROP ? gelu_fast(x1) * m[2 * i + 1] : gelu_fast(x1);
+      }
+    } else if constexpr (MODE == EM_BIAS_RES || MODE == EM_ADD) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] += a[i];
+    } else if constexpr (MODE == EM_BIAS_DROP_RES) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], m[i], a[i]);
+    } else if constexpr (MODE == EM_DGELU || MODE == EM_DGELU_DROP) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] *= HAS_DROP ? gelu_fast_grad(a[i]) * m[i] : gelu_fast_grad(a[i]);
+    }
+    uint32_t u[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+    st_global_256((bf16*)q.C + off + 16 * h, u);
+  }
+}
+
+// -> true when the chunk was written by the direct path
+__device__ __forceinline__ bool chunk_direct_dispatch(const GemmParams& q, const OutSel& o, uint32_t taddr_c, int lane,
+                                                      int m_base, int n_base) {
+  switch (o.mode) {
+    case EM_NONE: chunk_direct<EM_NONE>(q, taddr_c, lane, m_base, n_base); return true;
+    case EM_BIAS: chunk_direct<EM_BIAS>(q, taddr_c, lane, m_base, n_base); return true;
+    case EM_BIAS_GELU: chunk_direct<EM_BIAS_GELU>(q, taddr_c, lane, m_base, n_base); return true;
+    case EM_BIAS_GELU_DROP: chunk_direct<EM_BIAS_GELU_DROP>(q, taddr_c, lane, m_base, n_base); return true;
+    case EM_BIAS_RES: chunk_direct<EM_BIAS_RES>(q, taddr_c, lane, m_base, n_base); return true;
+    case EM_BIAS_DROP_RES: chunk_direct<EM_BIAS_DROP_RES>(q, taddr_c, lane, m_base, n_base); return true;
+    case EM_DGELU: chunk_direct<EM_DGELU>(q, taddr_c, lane, m_base, n_base); return true;
+    case EM_DGELU_DROP: chunk_direct<EM_DGELU_DROP>(q, taddr_c, lane, m_base, n_base); return true;
+    case EM_ADD: chunk_direct<EM_ADD>(q, taddr_c, lane, m_base, n_base); return true;
+    default: return false;
+  }
+}
+
 // Returns false when (mode, output type) has no fast instantiation; the caller then takes the checked generic loop.
 __device__ __forceinline__ bool chunk_fast(const GemmParams& q, const OutSel& o, const float* stg, int lane, int m_base,
                                            int n_base) {
@@ -517,6 +633,12 @@ __device__ __forceinline__ void drain_tile(const GemmParams& q, const OutSel& o,
     if (q.transposed_out) {
       chunk_transposed(q, o, taddr + (uint32_t)c0, lane, m_base, n_base);
       continue;
+    }
+    if constexpr (!ADAMW) {
+      // full chunk, bf16 output, 32-byte aligned rows: straight from registers (see chunk_direct)
+      if (q.direct && !o.c_f32 && m_base + 32 <= q.M && n_base + 32 <= q.N &&
+          chunk_direct_dispatch(q, o, taddr + (uint32_t)c0, lane, m_base, n_base))
+        continue;
     }
     {
       uint32_t r[32];
@@ -1161,6 +1283,15 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   p.drop_thresh = dropout_thresh16(drop_p); p.drop_scale = dropout_scale16(drop_p);
   p.mode = resolve_mode(epilogue, act, drop_p, bias, c_is_f32, beta);
   { static int d = -1; if (d < 0) { const char* e = getenv("LR2_GEMM_DBG"); d = e ? atoi(e) : 0; } p.dbg = d; }
+  {
+    // direct drain needs 32-byte aligned row pieces: pitches and base pointers of C / C2 / aux multiples of 16 elements
+    static int dsel = -1;
+    if (dsel < 0) { const char* e = getenv("LR2_GEMM_DIRECT"); dsel = e ? atoi(e) : 1; }
+    const bool al = (ldc % 16 == 0) && ((reinterpret_cast<uintptr_t>(C) & 31) == 0) &&
+                    (C2 == nullptr || (reinterpret_cast<uintptr_t>(C2) & 31) == 0) &&
+                    (aux == nullptr || ((ldaux % 16 == 0) && (reinterpret_cast<uintptr_t>(aux) & 31) == 0));
+    p.direct = (dsel && al && !transposed_out && !c_is_f32 && splits == 1) ? 1 : 0;
+  }
   p.ws = reinterpret_cast<float*>(workspace);
   { static int r = -1; if (r < 0) { const char* e = getenv("LR2_GEMM_RASTER"); r = e ? atoi(e) : 0; } p.raster = r; }
   const long long out_rows = transposed_out ? N : M;

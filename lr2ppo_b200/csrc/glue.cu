@@ -443,6 +443,29 @@ __global__ void dropout_kernel(const bf16* __restrict__ x, bf16* __restrict__ ou
     st8f(out + i * 8, v);
   }
 }
+// out = gelu(bf16(x + bias)), pre = bf16(x + bias): the bias + erf-GELU epilogue of a Linear whose fp32 pre-activation
+// sums arrive from elsewhere (K-split out_layer.fc1: the per-rank partial products are summed by a reduce-scatter).
+// Same arithmetic as the GEMM epilogue EM_BIAS_GELU: GELU is evaluated on the bf16-rounded pre-activation.
+__global__ void bias_gelu_kernel(const float* __restrict__ x, const float* __restrict__ bias, bf16* __restrict__ out,
+                                 bf16* __restrict__ pre, long long rows, int D) {
+  const long long n8 = rows * (D / 8);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % (D / 8)) * 8;
+    const float4 a0 = *reinterpret_cast<const float4*>(x + i * 8), a1 = *reinterpret_cast<const float4*>(x + i * 8 + 4);
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + c)), b1 = __ldg(reinterpret_cast<const float4*>(bias + c + 4));
+    float v[8] = {a0.x + b0.x, a0.y + b0.y, a0.z + b0.z, a0.w + b0.w, a1.x + b1.x, a1.y + b1.y, a1.z + b1.z, a1.w + b1.w};
+    uint4 pr;
+    pr.x = pack_bf16x2(v[0], v[1]); pr.y = pack_bf16x2(v[2], v[3]);
+    pr.z = pack_bf16x2(v[4], v[5]); pr.w = pack_bf16x2(v[6], v[7]);
+    if (pre != nullptr) *reinterpret_cast<uint4*>(pre + i * 8) = pr;
+    float xr[8];
+    unpack8(pr, xr);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = gelu_fast(xr[k]);
+    st8f(out + i * 8, v);
+  }
+}
 }  // namespace lr2
 
 extern "C" int lr2_embed_sum(const long long* src, const long long* seg, const float* word, const float* pos,
@@ -475,6 +498,19 @@ extern "C" int lr2_dropout_bf16(const void* x, void* out, long long n, float p, 
   lr2::dropout_kernel<<<lr2::grid_for(n / 8, 256), 256, 0, S_(stream)>>>(
       reinterpret_cast<const lr2::bf16*>(x), reinterpret_cast<lr2::bf16*>(out), n, p, lr2::dropout_thresh16(p), seed, site,
       reinterpret_cast<const unsigned long long*>(seed_dev));
+  LR2_LAUNCHED(1);
+  LR2_RETURN_LAUNCH();
+}
+
+/* out = gelu(bf16(x + bias)), pre (optional) = bf16(x + bias); x fp32 [rows, D], D % 8 == 0 */
+extern "C" int lr2_bias_gelu_rows(const float* x, const float* bias, void* out_bf16, void* pre_bf16, long long rows, int D,
+                                  void* stream) {
+  if (rows <= 0 || D <= 0 || D % 8) return LR2_ERR_BAD_SHAPE;
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(out_bf16) |
+       reinterpret_cast<uintptr_t>(pre_bf16)) & 15)
+    return LR2_ERR_MISALIGNED;
+  lr2::bias_gelu_kernel<<<lr2::grid_for(rows * (D / 8), 256), 256, 0, S_(stream)>>>(
+      x, bias, reinterpret_cast<lr2::bf16*>(out_bf16), reinterpret_cast<lr2::bf16*>(pre_bf16), rows, D);
   LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }

@@ -15,55 +15,73 @@ import torch
 import torch.distributed as dist
 
 
-class RowParallel:
-    """out_layer.fc1 row-parallel over the data-parallel ranks (used by engine.FusionEngine when attached by
-    GradSync.attach(..., tensor_parallel=True)).
+class Fc1Parallel:
+    """out_layer.fc1 split along its INPUT dimension (K-split) over the data-parallel ranks; used by
+    engine.FusionEngine when attached by GradSync.attach(..., tensor_parallel=True).
 
-    The row-sharded optimizer of round 1 kept a complete bf16 copy of the weight on every rank and re-assembled it
-    after every step: an all-gather of 1 GB per model per step (2 x 875 MB received per rank at 8 GPUs, the largest
-    exposed item of the 8-GPU step).  Row-parallel execution never needs foreign rows: rank r evaluates output
-    features [r0, r1) for the items of ALL ranks (forward: all-gather of the 15.6 MB activation rows, then a 37 KB
-    all-to-all of the results; backward: all-gather of dY, partial input gradients through the own rows, reduce-scatter).
-    Per model and step at 8 GPUs each rank now receives 3 x 109 MB instead of 875 + 109 MB, and streams 1/8 of the
-    weight from HBM in every forward / dgrad / wgrad pass.  `active = False` (after GradSync.gather_shadow) restores
-    replicated execution for code that is not run in lock-step by all ranks (evaluation)."""
+    The row-sharded optimizer of round 1 kept a complete bf16 copy of the 3072 x 162816 weight on every rank and
+    re-assembled it after every step: an all-gather of 1 GB per model per step (2 x 875 MB received per rank at 8
+    GPUs), the largest exposed item of the 8-GPU step.  Here rank r owns -- fp32 master, Adam moments, bf16 copy --
+    the column block W[:, k0:k1) and nothing else of the weight is ever needed on it:
 
-    def __init__(self, world, rank, rows, group=None):
-        self.world, self.rank, self.rows, self.group, self.active = world, rank, tuple(rows), group, True
+      forward   every rank sends column block q of its activation rows X [items, 162816] to rank q (all-to-all,
+                (world-1)/world of 15.6 MB per rank); rank r multiplies everybody's block r by W[:, k0:k1)^T and the
+                fp32 partial pre-activations [world*items, 3072] are summed and scattered (reduce-scatter, 4.7 MB);
+                bias + GELU run on the own rows (lr2_bias_gelu_rows).
+      backward  dY rows are all-gathered (0.3 MB per rank); rank r computes dX[:, k0:k1) for everybody's items --
+                complete sums over the 3072 hidden units, no reduction -- and the all-to-all returns each rank its
+                rows; the weight gradient of the owned block is dY_all^T X_all[:, k0:k1), local.
+
+    Per model and step at 8 GPUs a rank exchanges ~45 MB instead of receiving ~1 GB, streams 1/8 of the weight from
+    HBM in every forward / dgrad / wgrad pass and updates 1/8 of the 500 M parameters.  (A row split would need the
+    whole X of every rank on every rank: an all-gather of 109 MB per forward; measured 7.83 ms/step at 8 GPUs against
+    8.41 ms with the shadow all-gather, both in profiles/r02_multi_gpu.md.)  `active = False` (GradSync.replicated)
+    restores replicated execution for code that the ranks do not run in lock-step (evaluation)."""
+
+    def __init__(self, world, rank, cols, group=None):
+        self.world, self.rank, self.cols, self.group, self.active = world, rank, tuple(cols), group, True
 
     def all_gather(self, t):
         out = torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
         dist.all_gather_into_tensor(out, t.contiguous(), group=self.group)
         return out
 
-    def all_to_all(self, t):
-        """t [world, ...]: block q goes to rank q; returns [world, ...] with block q received from rank q."""
+    def _all_to_all(self, t):
         out = torch.empty_like(t)
-        dist.all_to_all_single(out, t.contiguous(), group=self.group)
+        dist.all_to_all_single(out, t, group=self.group)
         return out
 
-    def reduce_scatter_async(self, t):
-        """t [world * rows, D] -> handle; handle() waits and returns this rank's [rows, D] block of the sum."""
+    def scatter_cols(self, x):
+        """x [items, world * Kb] -> [world * items, Kb]: block r of EVERY rank's rows (rank-major), on rank r."""
+        items = x.shape[0]
+        kb = x.shape[1] // self.world
+        send = x.view(items, self.world, kb).permute(1, 0, 2).contiguous()          # [dest, items, Kb]
+        return self._all_to_all(send).view(self.world * items, kb)
+
+    def gather_cols_async(self, t):
+        """Inverse of scatter_cols: t [world * items, Kb] (block `rank` of everybody's rows) -> handle; handle()
+        waits and returns [items, world * Kb], this rank's rows with every column block."""
+        items = t.shape[0] // self.world
+        kb = t.shape[1]
+        t = t.contiguous()
+        out = torch.empty_like(t)
+        work = dist.all_to_all_single(out, t, group=self.group, async_op=True)
+
+        def handle():
+            work.wait()
+            return out.view(self.world, items, kb).permute(1, 0, 2).reshape(items, self.world * kb)
+        return handle
+
+    def reduce_scatter(self, t):
+        """t [world * rows, D] -> this rank's [rows, D] block of the sum over the ranks."""
         rows = t.shape[0] // self.world
         if dist.get_backend(self.group) == "gloo":        # gloo has no reduce-scatter (CPU algebra tests): sum, slice
             full = t.contiguous().clone()
             dist.all_reduce(full, group=self.group)
-            return lambda: full[self.rank * rows:(self.rank + 1) * rows].clone()
+            return full[self.rank * rows:(self.rank + 1) * rows].clone()
         out = torch.empty((rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-        work = dist.reduce_scatter_tensor(out, t.contiguous(), group=self.group, async_op=True)
-
-        def handle():
-            work.wait()
-            return out
-        return handle
-
-    def exchange_features(self, part, items):
-        """part [slots, world * items, R]: this rank's output features for the items of every rank (rank-major rows)
-        -> [slots, items, world * R]: all output features of this rank's own items (feature block q came from rank q)."""
-        slots, _, R = part.shape
-        send = part.view(slots, self.world, items, R).transpose(0, 1).contiguous()      # [world, slots, items, R]
-        recv = self.all_to_all(send)                                                    # [world(q), slots, items, R]
-        return recv.permute(1, 2, 0, 3).reshape(slots, items, self.world * R).contiguous()
+        dist.reduce_scatter_tensor(out, t.contiguous(), group=self.group)
+        return out
 
 
 class GradSync:
@@ -127,8 +145,8 @@ class GradSync:
         if shard_fc1 is None:
             shard_fc1 = os.environ.get("LR2_DP_SHARD", "1") == "1"
         if tensor_parallel is None:
-            # tensor_parallel (default on with the row sharding, LR2_DP_TP=0 disables): run out_layer.fc1 row-parallel
-            # (RowParallel above) instead of all-gathering the updated bf16 weight after every step
+            # tensor_parallel (default, LR2_DP_TP=0 selects round 1's row sharding + shadow all-gather): out_layer.fc1
+            # split along its input dimension (Fc1Parallel above): the optimizer owns a COLUMN block per rank
             tensor_parallel = os.environ.get("LR2_DP_TP", "1") == "1"
         rank = dist.get_rank(self.group)
         for e in self._engines(module):
@@ -138,13 +156,19 @@ class GradSync:
             self._skip.add(id(w))
             e.fc1_rows = None
             rows = w.shape[0] // self.world
-            if shard_fc1 and self.world > 1 and w.shape[0] % self.world == 0 and (rows * w.shape[1]) % 4096 == 0 \
-                    and hasattr(optimizer, "set_window") and getattr(e, "fc1_grad_bf16", None) is not None:
+            kb = w.shape[1] // self.world
+            can_shard = shard_fc1 and self.world > 1 and getattr(e, "fc1_grad_bf16", None) is not None
+            e.tp = None
+            if can_shard and tensor_parallel and w.shape[1] % self.world == 0 and kb % 128 == 0 and \
+                    hasattr(optimizer, "set_col_window"):
+                e.tp = Fc1Parallel(self.world, rank, (rank * kb, (rank + 1) * kb), self.group)
+                optimizer.set_col_window(w, rank * kb, (rank + 1) * kb)
+                self._sharded[id(module)] = (e, w)
+            elif can_shard and w.shape[0] % self.world == 0 and (rows * w.shape[1]) % 4096 == 0 \
+                    and hasattr(optimizer, "set_window"):
                 e.fc1_rows = (rank * rows, (rank + 1) * rows)
                 optimizer.set_window(w, rank, self.world)
                 self._sharded[id(module)] = (e, w)
-                e.tp = RowParallel(self.world, rank, e.fc1_rows, self.group) if tensor_parallel and rows % 128 == 0 \
-                    else None
                 if id(module) not in self._guarded:
                     # state_dict() of a module whose foreign rows are stale would silently save torn weights:
                     # refuse until consolidate() ran (checkpoint.save_sharded reads only the owned rows and opts out)
@@ -181,8 +205,8 @@ class GradSync:
         self._dirty.add(id(module))
         if id(module) in self._opt_of:
             self._dirty_opt.add(id(self._opt_of[id(module)]))
-        if e.tp is not None and e.tp.active:
-            return lambda: None              # row-parallel execution never reads foreign rows: nothing to gather
+        if e.tp is not None:
+            return lambda: None              # K-split execution never reads foreign column blocks: nothing to gather
         shadow = e.bank.get(w)
         r0, r1 = e.fc1_rows
         work = dist.all_gather_into_tensor(shadow, shadow[r0:r1], group=self.group, async_op=True)
@@ -196,8 +220,19 @@ class GradSync:
             return
         e, w = ent
         shadow = e.bank.get(w)
+        if e.tp is not None:
+            self._gather_cols(shadow, e.tp.cols)
+            return
         r0, r1 = e.fc1_rows
         dist.all_gather_into_tensor(shadow, shadow[r0:r1].clone(), group=self.group)
+
+    def _gather_cols(self, t, cols):
+        """Complete the 2-D tensor t (every rank holds valid data in its own column block) on all ranks, in place."""
+        k0, k1 = cols
+        pieces = torch.empty((self.world, t.shape[0], k1 - k0), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(pieces, t[:, k0:k1].contiguous(), group=self.group)
+        for q in range(self.world):
+            t[:, q * (k1 - k0):(q + 1) * (k1 - k0)].copy_(pieces[q])
 
     def replicated(self, *modules):
         """Context manager: inside it the given modules run replicated (complete bf16 weights, no collectives in
@@ -230,7 +265,8 @@ class GradSync:
         e, w = ent
         for name, p in module.named_parameters():
             if p is w:
-                return {name: tuple(e.fc1_rows)}
+                # (r0, r1) = a row block; (dim, lo, hi) = a block along `dim` (K-split: columns)
+                return {name: (1,) + tuple(e.tp.cols) if e.tp is not None else tuple(e.fc1_rows)}
         return {}
 
     def consolidate(self, module, optimizer=None):
@@ -240,13 +276,16 @@ class GradSync:
         if ent is None:
             return
         e, w = ent
-        r0, r1 = e.fc1_rows
         tensors = [w.data]
         if optimizer is not None:
             st = optimizer.state_for(w)
             tensors += [st["exp_avg"], st["exp_avg_sq"]]
         for t in tensors:
-            dist.all_gather_into_tensor(t, t[r0:r1], group=self.group)
+            if e.tp is not None:
+                self._gather_cols(t, e.tp.cols)
+            else:
+                r0, r1 = e.fc1_rows
+                dist.all_gather_into_tensor(t, t[r0:r1], group=self.group)
         self._dirty.discard(id(module))          # master weight complete again: module.state_dict() is safe
         if optimizer is not None:
             self._dirty_opt.discard(id(optimizer))

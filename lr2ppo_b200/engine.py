@@ -266,7 +266,7 @@ class FusionEngine:
         self.fc1_rows = None         # (r0, r1): rows of out_layer.fc1 this rank owns (row-sharded optimizer)
         self.fc1_grad_bf16 = None  # bf16 [out, in] gradient buffer of out_layer.fc1.weight (see enable_bf16_fc1_grad)
         self._zero_index = {}      # (bs, T, device) -> int64 zeros [bs, T]: broadcast index of un-repeated img_emb
-        self.tp = None             # dist.RowParallel: out_layer.fc1 row-parallel over the data-parallel ranks
+        self.tp = None             # dist.Fc1Parallel: out_layer.fc1 K-split over the data-parallel ranks
 
     def begin_step(self):
         """Persistent-gradient mode: start of a new optimizer step (replaces model.zero_grad())."""
@@ -359,9 +359,9 @@ class FusionEngine:
         hid = o1.w.shape[0]
         tp = self.tp if (self.tp is not None and self.tp.active) else None
         if tp is not None:
-            # out_layer.fc1 row-parallel over the data-parallel ranks (dist.GradSync, tensor_parallel): this rank holds
-            # (and updates) only rows [r0, r1) of the 3072 x 162816 weight, so it evaluates THOSE output features for
-            # the items of EVERY rank and the results are exchanged -- 37 KB per rank pair instead of all-gathering the
+            # out_layer.fc1 split along its input dimension over the data-parallel ranks (dist.Fc1Parallel): this rank
+            # holds (and updates) only the column block W[:, k0:k1), multiplies that block of EVERY rank's rows and
+            # the partial sums are reduce-scattered -- ~20 MB exchanged per forward instead of all-gathering the
             # updated 1 GB weight after every optimizer step.  HBM: the weight stream shrinks by `world` too.
             y1, pre3, cat_all = self._fc1_forward_tp(tp, o1, cat, items, save)
         else:
@@ -404,35 +404,32 @@ class FusionEngine:
         return logits, ctx
 
     def _fc1_forward_tp(self, tp, o1, cat, items, save):
-        """Row-parallel out_layer.fc1 forward.  Returns (y1 [items, hid], pre3 [items, hid] | None, X_all | None)."""
-        dev = cat.device
+        """K-split out_layer.fc1 forward (dist.Fc1Parallel).  Returns (y1 [items, hid], pre3 | None, X block | None)."""
         hid = o1.w.shape[0]
-        r0, r1 = tp.rows
-        R, total = r1 - r0, tp.world * items
-        x_all = tp.all_gather(cat)                                   # [world * items, K1], rank-major rows
-        # own output features for everybody's items; slot 0 = GELU output, slot 1 = pre-activation (for backward)
-        part = torch.empty((2 if save else 1, total, R), dtype=bf16, device=dev)
+        k0, k1 = tp.cols
+        total = tp.world * items
+        x_k = tp.scatter_cols(cat)                                   # [world * items, Kb]: my column block, all rows
+        w_k = o1.w[:, k0:k1]                                         # strided view, pitch K1
+        part = torch.empty((total, hid), dtype=f32, device=cat.device)
         bn = 64 if total <= 64 else (128 if (total <= 128 or total > 256) else 256)
-        n_tiles = (total + bn - 1) // bn
-        kblocks = (cat.shape[1] + 63) // 64
-        splits = max(1, min(kblocks, 148 // (((R + 127) // 128) * n_tiles)))
-        ops.gemm(o1.w[r0:r1], x_all, out=part[0], transposed_out=True, epilogue=EPI_BIAS_GELU, bias=o1.b[r0:r1],
-                 c2=part[1] if save else None, splits=splits, block_n=bn)
-        full = tp.exchange_features(part, items)     # 37 KB per rank pair: everybody's features of MY items
-        return full[0], (full[1] if save else None), (x_all if save else None)
+        tiles = ((hid + 127) // 128) * ((total + bn - 1) // bn)
+        splits = max(1, min(((k1 - k0) + 63) // 64, 148 // tiles))
+        ops.gemm(w_k, x_k, out=part, transposed_out=True, splits=splits, block_n=bn)
+        y_sum = tp.reduce_scatter(part)                              # [items, hid] fp32: sum over the column blocks
+        y1, pre3 = ops.bias_gelu_rows(y_sum, o1.b, want_pre=save)
+        return y1, pre3, (x_k if save else None)
 
-    def _fc1_backward_tp(self, tp, o1, dy1p, x_all, items):
-        """Row-parallel out_layer.fc1 backward: weight gradient of the own rows from everybody's (dY, X); input gradient
-        as partial products over the own rows, summed over the ranks by a reduce-scatter."""
-        r0, r1 = tp.rows
-        dy_all = tp.all_gather(dy1p)                                 # [world * items, hid] (295 KB per rank)
-        dy_own = dy_all[:, r0:r1]                                    # strided view: pitch hid
-        # partial dX for EVERY rank's items through the own rows: [world * items, K1]
-        partial = ops.gemm(dy_own, o1.w[r0:r1], b_mn=True)
-        wait_dx = tp.reduce_scatter_async(partial)                   # NVLink transfer overlaps the wgrad GEMM below
+    def _fc1_backward_tp(self, tp, o1, dy1p, x_k, items):
+        """K-split out_layer.fc1 backward: dX of the own column block for everybody's rows (complete sums over the
+        hidden units), returned to the owners by an all-to-all that overlaps the weight-gradient GEMM of the block."""
+        k0, k1 = tp.cols
+        w_k = o1.w[:, k0:k1]
+        dy_all = tp.all_gather(dy1p)                                 # [world * items, hid] (0.3 MB per rank)
+        dx_k = ops.gemm(dy_all, w_k, b_mn=True)                      # [world * items, Kb]
+        wait_dx = tp.gather_cols_async(dx_k)
         bn = 128 if dy_all.shape[0] <= 256 else 256
-        ops.gemm(dy_own, x_all, a_mn=True, b_mn=True, out=self.fc1_grad_bf16[r0:r1], block_n=bn)
-        return wait_dx()                                             # [items, K1]: sum over the ranks of the partials
+        ops.gemm(dy_all, x_k, a_mn=True, b_mn=True, out=self.fc1_grad_bf16[:, k0:k1], block_n=bn)
+        return wait_dx().contiguous()                                # [items, K1]
 
     def backward(self, ctx, dlogits):
         """Accumulates fp32 gradients into module.parameters().grad (allocating when None)."""

@@ -537,6 +537,17 @@ def patchify(img, ps):
     return out
 
 
+def bias_gelu_rows(x, bias, want_pre=True):
+    """x f32 [rows, D] -> (gelu(bf16(x + bias)) bf16, bf16(x + bias) | None)."""
+    L = _L()
+    _cuda(x, f32, "x"); _cuda(bias, f32, "bias")
+    rows, D = x.shape
+    out = torch.empty((rows, D), dtype=bf16, device=x.device)
+    pre = torch.empty((rows, D), dtype=bf16, device=x.device) if want_pre else None
+    _lib.run(L.lr2_bias_gelu_rows, ptr(x), ptr(bias), ptr(out), ptr(pre), rows, D, _lib.stream())
+    return out, pre
+
+
 def dropout(x, p, seed, site, seed_dev=None):
     L = _L()
     _cuda(x, bf16)

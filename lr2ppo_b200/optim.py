@@ -87,6 +87,14 @@ class FusedAdamW(Optimizer):
         self._windows[id(p)] = (int(k), int(n))
         self._tables.clear()
 
+    def set_col_window(self, p, c0, c1):
+        """Data-parallel column sharding (dist.GradSync, K-split out_layer.fc1): this rank updates only columns
+        [c0, c1) of the 2-D parameter p; nothing else of p is ever launched here."""
+        if not hasattr(self, "_col_windows"):
+            self._col_windows = {}
+        self._col_windows[id(p)] = (int(c0), int(c1))
+        self._tables.clear()
+
     def _owned(self, tab, i):
         """Chunk range (start, count) of tensor id i that this rank updates."""
         a, n = tab["ranges"][i]
@@ -113,7 +121,7 @@ class FusedAdamW(Optimizer):
         L = _lib.load()
         chunk = L.lr2_adamw_chunk_elems()
         dev = ps[0].device
-        ptrs, meta, chunks, gptrs = [], [], [], []
+        ptrs, meta, chunks, gptrs, lens = [], [], [], [], []
         for t, p in enumerate(ps):
             if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
                 raise _lib.Lr2Error("FusedAdamW needs contiguous fp32 CUDA parameters (no CPU fallback)")
@@ -133,16 +141,31 @@ class FusedAdamW(Optimizer):
                      sh.data_ptr() if sh is not None else 0, 0]
             meta += [p.numel(), _f2i(group["weight_decay"]), int(g.dtype == torch.bfloat16), 0]
             gptrs.append(g.data_ptr())
-            offs = torch.arange(0, p.numel(), chunk, dtype=torch.int64)
-            chunks.append(torch.stack([torch.full_like(offs, t), offs], dim=1))
+            cw = getattr(self, "_col_windows", {}).get(id(p))
+            if cw is None:
+                offs = torch.arange(0, p.numel(), chunk, dtype=torch.int64)
+                lens.append(torch.clamp(p.numel() - offs, max=chunk))
+                chunks.append(torch.stack([torch.full_like(offs, t), offs], dim=1))
+            else:
+                # column-sharded 2-D parameter: this rank owns columns [c0, c1) of every row; each row segment is
+                # cut into pieces of at most `chunk` elements with explicit lengths (multiples of 4)
+                c0, c1 = cw
+                rows, cols = p.shape
+                if (c1 - c0) % 4 or c0 % 4 or cols % 4:
+                    raise _lib.Lr2Error("column window must be aligned to 4 elements")
+                seg = torch.arange(0, c1 - c0, chunk, dtype=torch.int64)
+                seg_len = torch.clamp((c1 - c0) - seg, max=chunk)
+                offs = (torch.arange(rows, dtype=torch.int64)[:, None] * cols + c0 + seg[None, :]).reshape(-1)
+                ln = seg_len[None, :].expand(rows, -1).reshape(-1)
+                lens.append(ln)
+                chunks.append(torch.stack([torch.full_like(offs, t) | (ln << 32), offs], dim=1))
         chunk_t = torch.cat(chunks, dim=0).contiguous()
         starts, acc = {}, 0
         for t, p in enumerate(ps):          # chunk range of every tensor (two-phase step: see step(first=...))
             starts[id(p)] = (acc, chunks[t].shape[0])
             acc += chunks[t].shape[0]
         # bytes moved by chunks [0, i): lets a profiling pass attribute algorithmic bytes to each launch (chunk span)
-        per_chunk = torch.cat([torch.clamp(p.numel() - chunks[t][:, 1], max=chunk) *
-                               self._bytes_per_element(p, self._grad_of(p)) for t, p in enumerate(ps)])
+        per_chunk = torch.cat([lens[t] * self._bytes_per_element(p, self._grad_of(p)) for t, p in enumerate(ps)])
         prefix = torch.cat([torch.zeros(1, dtype=torch.int64), torch.cumsum(per_chunk, 0)])
         tab = dict(params=ps, ids=[id(p) for p in ps], gptrs=gptrs, n_chunks=chunk_t.shape[0], ranges=starts,
                    byte_prefix=prefix,
@@ -203,7 +226,11 @@ class FusedAdamW(Optimizer):
             if g is None or id(p) in self._fused:
                 continue
             parts = getattr(self, "_windows", {}).get(id(p), (0, 1))[1]      # row-sharded: this rank moves 1/parts
-            total += p.numel() // parts * self._bytes_per_element(p, g)
+            n = p.numel() // parts
+            cw = getattr(self, "_col_windows", {}).get(id(p))
+            if cw is not None:
+                n = p.shape[0] * (cw[1] - cw[0])                             # column-sharded
+            total += n * self._bytes_per_element(p, g)
         return total
 
     def _bytes_per_element(self, p, g):

@@ -175,3 +175,50 @@ def test_replicated_model_through_sharded_api(tmp_path):
     m3, opt3, sched3 = _trained(3, steps=1)
     assert checkpoint.load_sharded(d, {"m": m3}, {"m": opt3}, {"m": sched3})[0] == 1
     assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m3.state_dict().values()))
+
+
+def test_sharded_checkpoint_with_column_blocks(tmp_path):
+    """K-split data parallel (dist.Fc1Parallel): every rank owns a COLUMN block of out_layer.fc1 -- descriptors
+    (dim, lo, hi) -- and the loader must reassemble complete tensors from them."""
+    import torch
+    from lr2ppo_b200 import checkpoint
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1 = torch.nn.Linear(12, 5)
+            self.head = torch.nn.Linear(5, 1)
+
+    torch.manual_seed(0)
+    truth = Net()
+    world, kb = 3, 4
+    full_m = torch.randn(5, 12)
+    d = str(tmp_path / "ck")
+    for rank in range(world):
+        net = Net()
+        net.load_state_dict(truth.state_dict())
+        opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9)
+        for p in net.parameters():
+            opt.state[p] = {"momentum_buffer": torch.zeros_like(p), "exp_avg": torch.zeros_like(p),
+                            "exp_avg_sq": torch.zeros_like(p)}
+        lo, hi = rank * kb, (rank + 1) * kb
+        with torch.no_grad():                                    # foreign column blocks are stale (poisoned)
+            mask = torch.ones(12, dtype=torch.bool); mask[lo:hi] = False
+            net.fc1.weight[:, mask] = float("nan")
+            opt.state[net.fc1.weight]["exp_avg"][:, lo:hi] = full_m[:, lo:hi]
+            opt.state[net.fc1.weight]["exp_avg"][:, mask] = float("nan")
+        sched = torch.optim.lr_scheduler.LambdaLR(opt, lambda s: 1.0)
+        checkpoint.save_sharded(d, {"m": net}, {"m": opt}, {"m": sched}, step=3, rank=rank, world=world,
+                                row_shards={"m": {"fc1.weight": (1, lo, hi)}},
+                                checkpointer=checkpoint.AsyncCheckpointer()).wait()
+    net2 = Net()
+    opt2 = torch.optim.SGD(net2.parameters(), lr=0.1, momentum=0.9)
+    for p in net2.parameters():
+        opt2.state[p] = {"momentum_buffer": torch.zeros_like(p), "exp_avg": torch.zeros_like(p),
+                         "exp_avg_sq": torch.zeros_like(p)}
+    sched2 = torch.optim.lr_scheduler.LambdaLR(opt2, lambda s: 1.0)
+    assert checkpoint.load_sharded(d, {"m": net2}, {"m": opt2}, {"m": sched2})[0] == 3
+    assert torch.equal(net2.fc1.weight.detach(), truth.fc1.weight.detach())
+    assert torch.equal(opt2.state[net2.fc1.weight]["exp_avg"], full_m)
+    sd = checkpoint.export_model(d, "m", str(tmp_path / "export.bin"))
+    assert torch.equal(sd["fc1.weight"], truth.fc1.weight.detach())

@@ -210,36 +210,36 @@ def test_row_sharded_optimizer_and_sharded_checkpoint_world2_gloo():
         mp.spawn(_shard_worker, args=(2, os.path.join(d, "rdzv"), os.path.join(d, "ck")), nprocs=2, join=True)
 
 
-# ---- row-parallel out_layer.fc1 (dist.RowParallel): the exchange algebra on CPU, world 2 and 4, gloo --------------
+# ---- K-split out_layer.fc1 (dist.Fc1Parallel): the exchange algebra on CPU, world 2 and 4, gloo -----------------
 def _tp_worker(rank, world, path):
-    from lr2ppo_b200.dist import RowParallel
+    from lr2ppo_b200.dist import Fc1Parallel
     dist.init_process_group("gloo", init_method=f"file://{path}", rank=rank, world_size=world)
-    items, K1, hid = 3, 40, 8 * world
-    R = hid // world
+    items, kb, hid = 3, 5, 7
+    K1 = kb * world
     g = torch.Generator().manual_seed(1)                         # the same on every rank
     W = torch.randn(hid, K1, generator=g, dtype=torch.float64)
     X = [torch.randn(items, K1, generator=g, dtype=torch.float64) for _ in range(world)]
     dY = [torch.randn(items, hid, generator=g, dtype=torch.float64) for _ in range(world)]
-    tp = RowParallel(world, rank, (rank * R, (rank + 1) * R))
-    r0, r1 = tp.rows
-    # forward: own features for everybody's items, then the exchange (slot 1 carries a second tensor, like pre3)
-    x_all = tp.all_gather(X[rank])
-    assert torch.equal(x_all, torch.cat(X))
-    part = torch.stack([x_all @ W[r0:r1].t(), 2 * (x_all @ W[r0:r1].t())])
-    full = tp.exchange_features(part, items)
-    ref = X[rank] @ W.t()
-    assert torch.allclose(full[0], ref) and torch.allclose(full[1], 2 * ref)
-    # backward: dX through the own rows, summed by the reduce-scatter; weight gradient of the own rows
+    tp = Fc1Parallel(world, rank, (rank * kb, (rank + 1) * kb))
+    k0, k1 = tp.cols
+    # forward: my column block of everybody's rows, partial products, sum + scatter
+    x_k = tp.scatter_cols(X[rank])
+    assert torch.equal(x_k, torch.cat([x[:, k0:k1] for x in X]))
+    y = tp.reduce_scatter(x_k @ W[:, k0:k1].t())
+    assert torch.allclose(y, X[rank] @ W.t())
+    # backward: dX of my column block for everybody's rows (complete sums), returned to the owners
     dy_all = tp.all_gather(dY[rank])
-    dx = tp.reduce_scatter_async(dy_all[:, r0:r1] @ W[r0:r1])()
+    assert torch.equal(dy_all, torch.cat(dY))
+    dx = tp.gather_cols_async(dy_all @ W[:, k0:k1])()
     assert torch.allclose(dx, dY[rank] @ W)
-    g_own = dy_all[:, r0:r1].t() @ x_all
+    # weight gradient of the owned column block = global-batch gradient restricted to it
+    g_own = dy_all.t() @ x_k
     g_ref = sum(dY[q].t() @ X[q] for q in range(world))
-    assert torch.allclose(g_own, g_ref[r0:r1])
+    assert torch.allclose(g_own, g_ref[:, k0:k1])
     dist.barrier()
     dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("world", [2, 4])
-def test_row_parallel_exchange_algebra_gloo(world, tmp_path):
+def test_fc1_k_split_exchange_algebra_gloo(world, tmp_path):
     mp.spawn(_tp_worker, args=(world, str(tmp_path / "pg")), nprocs=world, join=True)

@@ -3,11 +3,11 @@ identical models / batches, dropout off, constant lr = 1e-3, three eager stage-3
 
   replicated   every rank updates the whole out_layer.fc1 from all-gathered wgrad operands           (reference)
   gather       row-sharded optimizer + all-gather of the updated bf16 rows (round 1)                  == replicated, bit for bit
-  tp           row-sharded optimizer + row-PARALLEL fc1 (dist.RowParallel, the default)              ~= replicated
+  tp           column-sharded optimizer + K-split fc1 (dist.Fc1Parallel, the default)                ~= replicated
 
-`tp` changes the arithmetic in one place: the input gradient of fc1 is a bf16 sum over the ranks of per-rank partial
-products (reduce-scatter) instead of one fp32-accumulated GEMM, so it is held to the bf16 tolerance instead of
-bit-equality: statistics of the last step 2e-2, every Adam first moment 4e-2 of its scale (tests/parity.py), and --
+`tp` changes the arithmetic in one place: the pre-activation of fc1 is an fp32 sum over the ranks of per-rank partial
+products (reduce-scatter) instead of one split-K GEMM -- a different summation order, then the same bf16 rounding --
+so it is held to the bf16 tolerance instead of bit-equality: statistics of the last step 2e-2, every Adam first moment 4e-2 of its scale (tests/parity.py), and --
 because forward weights that silently stopped following the optimizer would pass a moments-only check -- the bf16
 weights every rank actually multiplies with must equal the rounded fp32 masters after consolidation."""
 import argparse
@@ -63,7 +63,7 @@ def main():
         sync.broadcast_params(model); sync.broadcast_params(reward)
         sync.attach(model.actor, opt, shard_fc1=mode != "replicated", tensor_parallel=mode == "tp")
         sync.attach(model.critic, copt, shard_fc1=mode != "replicated", tensor_parallel=mode == "tp")
-        assert (model.actor._engine.fc1_rows is not None) == (mode != "replicated")
+        assert (model.actor._engine.fc1_rows is not None) == (mode == "gather")
         assert (model.actor._engine.tp is not None) == (mode == "tp")
         stats = None
         for text, img, tgts in batches:
