@@ -40,3 +40,28 @@ def grad_sync_for(world):
         from ..dist import GradSync
         return GradSync(world)
     return None
+
+
+def replicated(sync, *modules):
+    """Context for code the ranks do not run in lock-step (evaluation): K-split modules temporarily run replicated."""
+    import contextlib
+    return sync.replicated(*modules) if sync is not None else contextlib.nullcontext()
+
+
+def save_if_best(args, sync, pairs, improved, model, path):
+    """Rank 0 decides (`improved`, evaluated on rank 0 only like the reference's `if args.is_master and result >
+    best_result`); with sharded data-parallel optimizers every rank must take part in completing the fp32 masters
+    (dist.GradSync.consolidate) before rank 0 writes the file, so the decision is broadcast first."""
+    import torch
+    import torch.distributed as dist
+    from .. import checkpoint
+    if sync is not None:
+        flag = torch.tensor([1 if (args.is_master and improved) else 0], device=args.device)
+        dist.broadcast(flag, 0)
+        improved = bool(flag.item())
+        if improved:
+            for module, optimizer in pairs:
+                sync.consolidate(module, optimizer)
+    if args.is_master and improved:
+        checkpoint.save_model(model, path)
+    return improved

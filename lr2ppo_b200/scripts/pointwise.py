@@ -52,15 +52,17 @@ def main(argv=None):
                         epoch, i + 1, total_loss / args.report_steps))
                     args.logger.info("Val set evaluation.")
                 total_loss = 0.0
-                ndcg = stages.pointwise_evaluate(args, model, val_loader, num_tasks=num_tasks)
+                with common.replicated(sync, model):
+                    ndcg = stages.pointwise_evaluate(args, model, val_loader, num_tasks=num_tasks)
+                result = float(ndcg[100000000]) if args.is_master else 0.0
                 if args.is_master:
-                    result = float(ndcg[100000000])
                     args.logger.info("NDCG:")
                     args.logger.info("".join("\nNDCG@{}={:.4f}".format(k, ndcg[k]) for k in sorted(ndcg.keys())))
-                    if result > best_result:
-                        best_result = result
-                        checkpoint.save_model(model, args.output_model_path)
-                        args.logger.info("Best NDCG until now!\n")
+                if common.save_if_best(args, sync, ((model, optimizer),), args.is_master and result > best_result,
+                                       model, args.output_model_path) and args.is_master:
+                    best_result = result
+                    args.logger.info("Best NDCG until now!\n")
+                if args.is_master:
                     args.logger.info("Best NDCG: {}".format(best_result))
                 model.train()
     checkpoint.wait()

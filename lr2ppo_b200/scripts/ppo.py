@@ -74,10 +74,12 @@ def main(argv=None):
                                     ragged, sync)
                     step += 1
                     _report(args, stats, step)
-                    result = ppo.evaluate(args, val_loader, step, split="val", num_tasks=num_tasks)
-                    if args.is_master and result > best_result:
+                    with common.replicated(sync, model.actor):
+                        result = ppo.evaluate(args, val_loader, step, split="val", num_tasks=num_tasks)
+                    improved = args.is_master and result > best_result
+                    if common.save_if_best(args, sync, ((model.actor, optimizer), (model.critic, critic_optimizer)),
+                                           improved, model, args.output_model_path) and args.is_master:
                         best_result = result
-                        checkpoint.save_model(model, args.output_model_path)
                         args.logger.info("Best val indicator until now!")
     checkpoint.wait()
     if torch.distributed.is_initialized():

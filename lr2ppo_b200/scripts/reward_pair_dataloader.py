@@ -56,14 +56,15 @@ def main(argv=None):
                 total_loss, total_acc, total_cnt = 0.0, 0.0, 0
                 if args.is_master:
                     args.logger.info("Evaluating...")
-                acc_val = stages.reward_evaluate(args, model, val_loader, num_tasks=num_tasks)
+                with common.replicated(sync, model):
+                    acc_val = float(stages.reward_evaluate(args, model, val_loader, num_tasks=num_tasks))
                 if args.is_master:
-                    acc_val = float(acc_val)
                     args.logger.info(f"val accuracy: {acc_val:.4f}")
-                    if acc_val > best_acc:
-                        best_acc = acc_val
-                        checkpoint.save_model(model, args.output_model_path)
-                        args.logger.info("Best Acc until now!\n")
+                if common.save_if_best(args, sync, ((model, optimizer),), args.is_master and acc_val > best_acc, model,
+                                       args.output_model_path) and args.is_master:
+                    best_acc = acc_val
+                    args.logger.info("Best Acc until now!\n")
+                if args.is_master:
                     args.logger.info("Best Acc: {}".format(best_acc))
                 model.train()
     checkpoint.wait()

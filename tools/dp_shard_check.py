@@ -1,5 +1,5 @@
 """Multi-GPU cross-check (torchrun --nproc-per-node 2|4|8) of the three data-parallel modes of dist.GradSync on
-identical models / batches, dropout off, constant lr = 1e-3, three eager stage-3 steps each:
+identical models / batches, dropout off, constant lr = 2e-5, three eager stage-3 steps each:
 
   replicated   every rank updates the whole out_layer.fc1 from all-gathered wgrad operands           (reference)
   gather       row-sharded optimizer + all-gather of the updated bf16 rows (round 1)                  == replicated, bit for bit
@@ -48,7 +48,9 @@ def main():
     torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
     dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
     dist.init_process_group("nccl", device_id=dev)
-    hp = argparse.Namespace(learning_rate=1e-3, critic_learning_rate=1e-3, optimizer="adamw", scheduler="constant",
+    # lr = 2e-5: large enough that every weight visibly moves in three steps, small enough that the sign-like first
+    # Adam steps do not amplify rounding differences between the modes into different trajectories
+    hp = argparse.Namespace(learning_rate=2e-5, critic_learning_rate=2e-5, optimizer="adamw", scheduler="constant",
                             train_steps=100, warmup=0.1, kl_div_loss_weight=0.001, entropy_weight=0.001,
                             value_clip=0.5, mode="reg", fc1_grad_bf16=True)
     g = torch.Generator().manual_seed(100 + rank)
