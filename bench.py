@@ -243,7 +243,8 @@ def workload_config(world, bf16_fc1_grad=True):
     """The `config` object of the JSON line: the same for the B200 arm and the reference arm."""
     return {"workload": "configs[3]: stage-3 full LR2PPO step (label-ranking rollout, reward scoring, "
                         "advantage, fused policy/value losses, 2x AdamW) on synthetic LRMovieNet-shaped "
-                        "data; per-GPU batch 24 queries x 2 tags, text [24,2,196,768], img [24,16,768] shared by the 2 tags, "
+                        "data; per-GPU batch 24 queries x 2 tags, text [24,2,196,768], img [24,16,768] shared by the 2 tags "
+                        "(fed in bf16 from pinned memory, as lr2ppo_b200.data's loader workers produce them), "
                         "fusion models 519M (actor) + 526M (critic) + 526M (reward) params, bf16 compute "
                         "/ fp32 master weights + fp32 Adam state"
                         + ("; out_layer.fc1 weight gradient kept in bf16" if bf16_fc1_grad else ""),
@@ -436,14 +437,16 @@ def main():
         sync.attach(model.actor, opt)
         sync.attach(model.critic, copt)
 
-    # synthetic LRMovieNet-shaped batches in PINNED host memory (text 28.9 MB, img 1.2 MB, tgts 384 B each); img_emb
+    # synthetic LRMovieNet-shaped batches in PINNED host memory (text, img, tgts); img_emb
     # is uploaded as the loader yields it ([bs, 1, 16, 768], one keyframe set per clip): the per-tag repeat of
     # finetune/ppo.py:831 is a broadcast inside the gather + cast kernel, never a tensor
     g = torch.Generator().manual_seed(100 + rank)
     pool = []
     for _ in range(4):
-        text = torch.randn(BS, TAGS, SEQ, FEAT, generator=g).pin_memory()
-        img = torch.randn(BS, 1, IMGS, FEAT, generator=g).pin_memory()
+        # features leave the loader workers in bf16 (lr2ppo_b200.data.feed_bf16: the cast is the first thing the
+        # device would do to a fp32 batch, bit for bit; done on the host it halves the upload): 14.5 + 0.6 MB / batch
+        text = torch.randn(BS, TAGS, SEQ, FEAT, generator=g).to(torch.bfloat16).pin_memory()
+        img = torch.randn(BS, 1, IMGS, FEAT, generator=g).to(torch.bfloat16).pin_memory()
         tgts = torch.randint(0, 3, (BS, TAGS), generator=g).pin_memory()
         pool.append((text, img, tgts))
     resident = [tuple(t.to(dev) for t in b) for b in pool]

@@ -169,10 +169,26 @@ def loader_workers():
     return int(os.environ.get("LR2_NUM_WORKERS", "32"))
 
 
+def feed_bf16():
+    """LR2_FEED_BF16 (default 1): the loader workers hand out text_emb / img_emb in bf16.  Every kernel of the path
+    consumes the features in bf16 -- the first device operation on a fp32 batch is the round-to-nearest cast -- so doing
+    that cast in the (parallel, CPU-side) workers changes no result bit and halves the pinned-memory upload
+    (SURVEY.md §8(f) 1).  0 keeps the reference's fp32 batches."""
+    return os.environ.get("LR2_FEED_BF16", "1") == "1"
+
+
+def _collate_bf16(batch):
+    from torch.utils.data import default_collate
+    out = default_collate(batch)
+    return type(out)(t.to(torch.bfloat16) if torch.is_tensor(t) and t.dtype == torch.float32 else t for t in out)
+
+
 def get_dataloader(args, dataset, num_tasks, global_rank, is_train=False, eval_batch_size=1):
     """DistributedSampler sharding as in every stage script (finetune/ppo.py:684-699): shuffled training shards of
     --batch_size, ordered evaluation shards of `eval_batch_size` (1 for NDCG, --batch_size for stage-2 accuracy),
-    drop_last=False so all ranks iterate equally.  Batches land in pinned memory for asynchronous upload."""
+    drop_last=False so all ranks iterate equally.  Batches land in pinned memory for asynchronous upload, features
+    already in bf16 (feed_bf16)."""
     sampler = DistributedSampler(dataset, num_replicas=num_tasks, rank=global_rank, shuffle=is_train)
     return DataLoader(dataset=dataset, batch_size=args.batch_size if is_train else eval_batch_size, sampler=sampler,
-                      num_workers=loader_workers(), drop_last=False, pin_memory=torch.cuda.is_available())
+                      num_workers=loader_workers(), drop_last=False, pin_memory=torch.cuda.is_available(),
+                      collate_fn=_collate_bf16 if feed_bf16() else None)

@@ -265,18 +265,39 @@ class FusionEngine:
         self.dp_gather_async = None  # optional callable(t) -> handle; handle() waits and returns the gathered rows
         self.fc1_rows = None         # (r0, r1): rows of out_layer.fc1 this rank owns (row-sharded optimizer)
         self.fc1_grad_bf16 = None  # bf16 [out, in] gradient buffer of out_layer.fc1.weight (see enable_bf16_fc1_grad)
+        self.fc1_passes, self._fc1_pending = 1, []   # backward passes per optimizer step (stage 2: 2) and their operands
         self._zero_index = {}      # (bs, T, device) -> int64 zeros [bs, T]: broadcast index of un-repeated img_emb
         self.tp = None             # dist.Fc1Parallel: out_layer.fc1 K-split over the data-parallel ranks
 
     def begin_step(self):
         """Persistent-gradient mode: start of a new optimizer step (replaces model.zero_grad())."""
         self._written.clear()
+        self._fc1_pending = []
 
-    def enable_bf16_fc1_grad(self, optimizer):
+    def _fc1_wgrad(self, dy_, x_, out, bn=None):
+        """out (bf16 block of the out_layer.fc1 gradient) = dY^T X over all rows collected for this optimizer step.
+        With fc1_passes == 2 (stage 2: chosen and reject forwards, one backward pass each) the operands of the first
+        pass are stashed and the second pass runs ONE GEMM over both -- K = 2 x rows -- instead of writing a 2 GB fp32
+        gradient and read-modify-writing it again."""
+        if self.fc1_passes > 1:
+            self._fc1_pending.append((dy_, x_))
+            if len(self._fc1_pending) < self.fc1_passes:
+                return
+            dy_ = torch.cat([a for a, _ in self._fc1_pending], dim=0)
+            x_ = torch.cat([b for _, b in self._fc1_pending], dim=0)
+            self._fc1_pending = []
+        if bn is None:
+            # K = rows: epilogue-bound -> single-CTA tiles; 128-wide (four TMEM accumulator buffers) up to K = 256,
+            # 256-wide beyond (operand traffic starts to matter: 460 vs 534 us at K = 384)
+            bn = 128 if dy_.shape[0] <= 256 else 256
+        ops.gemm(dy_, x_, a_mn=True, b_mn=True, out=out, block_n=bn)
+
+    def enable_bf16_fc1_grad(self, optimizer, passes=1):
         """Keep the gradient of out_layer.fc1.weight (97 % of the parameters) in a persistent bf16 buffer that
         FusedAdamW reads directly; `.grad` of that parameter stays None.  One backward per optimizer step only
         (no accumulation), i.e. stage 1 and stage 3."""
         w = self.m.out_layer.fc1.weight
+        self.fc1_passes, self._fc1_pending = int(passes), []
         self.fc1_grad_bf16 = torch.empty(w.shape, dtype=bf16, device=w.device)
         optimizer.register_shadow(w, self.bank.get(w))
         optimizer.register_grad(w, self.fc1_grad_bf16)
@@ -427,8 +448,7 @@ class FusionEngine:
         dy_all = tp.all_gather(dy1p)                                 # [world * items, hid] (0.3 MB per rank)
         dx_k = ops.gemm(dy_all, w_k, b_mn=True)                      # [world * items, Kb]
         wait_dx = tp.gather_cols_async(dx_k)
-        bn = 128 if dy_all.shape[0] <= 256 else 256
-        ops.gemm(dy_all, x_k, a_mn=True, b_mn=True, out=self.fc1_grad_bf16[:, k0:k1], block_n=bn)
+        self._fc1_wgrad(dy_all, x_k, self.fc1_grad_bf16[:, k0:k1])
         return wait_dx().contiguous()                                # [items, K1]
 
     def backward(self, ctx, dlogits):
@@ -510,16 +530,13 @@ class FusionEngine:
                 dy_, x_ = self.dp_gather(dy1p), self.dp_gather(ctx["cat"])
             else:
                 dy_, x_ = dy1p, ctx["cat"]
-            # K = world * items: epilogue-bound -> single-CTA tiles; 128-wide (four TMEM accumulator buffers) up to
-            # K = 256, 256-wide beyond (8 ranks: K = 384, operand traffic starts to matter: 460 vs 534 us)
-            bn = 128 if dy_.shape[0] <= 256 else 256
             rows = getattr(self, "fc1_rows", None)
             if rows is not None and handle is not None:
                 # row-sharded fc1 (dist.GradSync): only this rank's rows of the global-batch gradient
                 r0, r1 = rows
-                ops.gemm(dy_[:, r0:r1], x_, a_mn=True, b_mn=True, out=self.fc1_grad_bf16[r0:r1], block_n=bn)
+                self._fc1_wgrad(dy_[:, r0:r1], x_, self.fc1_grad_bf16[r0:r1])
             else:
-                ops.gemm(dy_, x_, a_mn=True, b_mn=True, out=self.fc1_grad_bf16, block_n=bn)
+                self._fc1_wgrad(dy_, x_, self.fc1_grad_bf16)
 
 
 def _to_items(src, index):

@@ -26,6 +26,7 @@ def main(argv=None):
     if args.is_master:
         args.logger.info("Batch size: {}".format(batch_size))
         args.logger.info("The number of training instances: {}".format(instances_num))
+    args.fc1_grad_bf16, args.fc1_passes = True, 2      # one dY^T X GEMM over both backward passes, bf16 gradient
     optimizer, scheduler = stages.build_optimizer(args, model)
     sync = common.grad_sync_for(num_tasks)
     if sync is not None:

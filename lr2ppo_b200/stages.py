@@ -17,9 +17,10 @@ def _all_trainable(model):
 def build_optimizer(args, model):
     """ref: finetune/pointwise.py:274-297 == finetune/reward_pair_dataloader.py:321-344 — AdamW (no decay for
     bias / gamma / beta, correct_bias=False) + the selected schedule.  Returns (optimizer, scheduler).  The fusion
-    engine's bf16 weight copies are registered with the optimizer, which refreshes them in its own pass; stage 1
-    (one backward per step) additionally keeps the out_layer.fc1 gradient in the bf16 side buffer when
-    args.fc1_grad_bf16 is set (stage 2 accumulates two backward passes in fp32 and must not)."""
+    engine's bf16 weight copies are registered with the optimizer, which refreshes them in its own pass.  With
+    args.fc1_grad_bf16 the out_layer.fc1 gradient lives in the bf16 side buffer FusedAdamW reads directly;
+    args.fc1_passes (stage 2: 2 -- chosen and reject forwards, one backward pass each) makes the engine compute it
+    with ONE dY^T X GEMM over the rows of all passes instead of accumulating a 2 GB fp32 gradient."""
     from .optim import attach_shadows, decay_groups, make_scheduler, str2optimizer
     opt_name = getattr(args, "optimizer", "adamw")
     if opt_name not in str2optimizer:
@@ -30,7 +31,7 @@ def build_optimizer(args, model):
     if eng is not None:
         attach_shadows(eng, optimizer)
         if getattr(args, "fc1_grad_bf16", False):
-            eng.enable_bf16_fc1_grad(optimizer)
+            eng.enable_bf16_fc1_grad(optimizer, passes=getattr(args, "fc1_passes", 1))
     return optimizer, make_scheduler(args, optimizer)
 
 
@@ -50,6 +51,8 @@ def _zero_grad(model):
         eng.begin_step()
     else:
         model.zero_grad()
+        if eng is not None:
+            eng._fc1_pending = []
 
 
 class GraphedTrainStep:

@@ -105,8 +105,9 @@ def test_stage12_train_step_baseline_size_train_mode(stage):
     model.load_state_dict(golden_util.make_state_dict("actor" if stage == 1 else "reward"), strict=True)
     model = model.cuda().train()
     model._engine.dropout_seed = c["mask_seed"]
+    # the shipped configurations: bf16 out_layer.fc1 gradient; stage 2 computes it with one GEMM over both passes
     hp = argparse.Namespace(learning_rate=golden_util.STEP_LR, optimizer="adamw", scheduler="constant",
-                            fc1_grad_bf16=(stage == 1))
+                            fc1_grad_bf16=True, fc1_passes=stage)
     opt, sch = stages.build_optimizer(hp, model)
     named = list(model.named_parameters())
     before = {n: p.detach().clone() for n, p in named}

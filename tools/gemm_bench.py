@@ -1,4 +1,6 @@
-"""Micro-benchmark of the LR2PPO GEMM shapes (stage-3, 48 items) through the C ABI. Run on the GPU box."""
+"""Micro-benchmark of the LR2PPO GEMM shapes (stage-3, 48 items) through the C ABI, with the library next to it:
+`cuBLAS` = torch.matmul on the same bf16 operands and layouts (GEMM only), `eager` = torch.matmul + the ATen kernels
+the fused epilogue replaces (bias add, exact GELU, dropout, residual, GELU backward).  Run on the GPU box."""
 import sys, os, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -88,12 +90,42 @@ def main():
             (f"fc1 wgrad 3072x162816 K=48 bf16 BN={bn}", 2 * items * H * K1, H * K1 * 2 + items * K1 * 2,
              lambda bn=bn: ops.gemm(dy1, cat, a_mn=True, b_mn=True, out=gWb, block_n=bn)),
         ]
+    import torch.nn.functional as F
+    # library equivalents by case-name prefix: (cuBLAS GEMM only, GEMM + unfused ATen epilogue)
+    lib = {
+        "fwd 9408x3072x768 plain": (lambda: torch.matmul(x, w1.t()), None),
+        "fwd 9408x3072x768 bias": (lambda: torch.matmul(x, w1.t()), lambda: F.linear(x, w1, b1.to(bf))),
+        "fwd 9408x3072x768 bias+gelu+pre": (lambda: torch.matmul(x, w1.t()), lambda: F.gelu(F.linear(x, w1, b1.to(bf)))),
+        "fwd 9408x3072x768 gelu+drop": (lambda: torch.matmul(x, w1.t()),
+                                        lambda: F.dropout(F.gelu(F.linear(x, w1, b1.to(bf))), 0.1, True)),
+        "fwd 9408x768x3072 bias": (lambda: torch.matmul(h, w2.t()), lambda: F.linear(h, w2, b2.to(bf))),
+        "fwd 9408x768x3072 bias+drop+res": (lambda: torch.matmul(h, w2.t()),
+                                            lambda: F.dropout(F.linear(h, w2, b2.to(bf)), 0.1, True) + res),
+        "fwd 9408x768x768 bias": (lambda: torch.matmul(x, wq.t()), lambda: F.linear(x, wq, b2.to(bf))),
+        "dgrad 9408x768x3072 (b_mn)": (lambda: torch.matmul(dh, w1), None),
+        "dgrad 9408x3072x768 dgelu (b_mn)": (lambda: torch.matmul(dy, w2),
+                                             lambda: torch.ops.aten.gelu_backward(torch.matmul(dy, w2), pre)),
+        "wgrad 3072x768 K=9408 f32": (lambda: torch.matmul(dh.t(), x), None),
+        "fc1 fwd 3072x48x162816 s6 T": (lambda: torch.matmul(cat, W.t()), lambda: F.gelu(F.linear(cat, W, bh.to(bf)))),
+        "fc1 dgrad 162816x48x3072 T": (lambda: torch.matmul(dy1, W), None),
+        "fc1 wgrad 3072x162816 K=48 f32": (lambda: torch.matmul(dy1.t(), cat), None),
+    }
     only = sys.argv[1] if len(sys.argv) > 1 else None
+    print(f"{'case':42s} {'ours us':>9s} {'TFLOP/s':>9s} {'GB/s':>9s} | {'cuBLAS us':>9s} {'ours/cuBLAS':>11s} | "
+          f"{'eager us':>9s} {'speed-up':>8s}")
     for name, flops, byts, fn in cases:
         if only and only not in name:
             continue
         us = timeit(fn)
-        print(f"{name:42s} {us:9.1f} us  {flops / us / 1e6:8.1f} TFLOP/s  {byts / us / 1e3:8.1f} GB/s", flush=True)
+        line = f"{name:42s} {us:9.1f} {flops / us / 1e6:9.1f} {byts / us / 1e3:9.1f}"
+        cub, eag = lib.get(name, (None, None))
+        if cub is not None:
+            uc = timeit(cub)
+            line += f" | {uc:9.1f} {uc / us:10.2f}x"
+            if eag is not None:
+                ue = timeit(eag)
+                line += f" | {ue:9.1f} {ue / us:7.2f}x"
+        print(line, flush=True)
     # AdamW on a 500M tensor
     from lr2ppo_b200.optim import FusedAdamW
     p = torch.nn.Parameter(torch.randn(H, K1, device=dev) * 0.02)

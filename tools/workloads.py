@@ -135,7 +135,8 @@ class Stage2Step:
                     mod.weight.fill_(1.0)
         self.model.train()
         self.hp = argparse.Namespace(learning_rate=2e-5, optimizer="adamw", scheduler="linear", warmup=0.1,
-                                     train_steps=68260 * 10 // pairs + 1, mode="reg")   # reward_pair_dataloader.sh
+                                     train_steps=68260 * 10 // pairs + 1, mode="reg",   # reward_pair_dataloader.sh
+                                     fc1_grad_bf16=True, fc1_passes=2)
         self.opt, self.sch = stages.build_optimizer(self.hp, self.model)
         self.sync = None
         if world > 1:
