@@ -1290,13 +1290,20 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
     const bool al = (ldc % 16 == 0) && ((reinterpret_cast<uintptr_t>(C) & 31) == 0) &&
                     (C2 == nullptr || (reinterpret_cast<uintptr_t>(C2) & 31) == 0) &&
                     (aux == nullptr || ((ldaux % 16 == 0) && (reinterpret_cast<uintptr_t>(aux) & 31) == 0));
-    p.direct = (dsel && al && !transposed_out && !c_is_f32 && splits == 1) ? 1 : 0;
+    // Measured on B200 (profiles/r02_gemm_shapes.txt): the direct drain wins on the plain pair-kernel GEMMs
+    // (9408x3072x768: 47.1 vs 50.6 us) and loses where the epilogue carries math or the rows are far apart (GELU
+    // +14 %, dropout +10 %, the K = 48 fc1 weight gradient 367 vs 274 us: 96 registers no longer hold a 32-column
+    // accumulator row plus the epilogue operands without spilling).  Default: plain epilogue only; LR2_GEMM_DIRECT=2
+    // forces it for every fast mode, 0 disables it.
+    const bool plain = (p.mode == EM_NONE);
+    p.direct = (dsel && al && !transposed_out && !c_is_f32 && splits == 1 && (dsel >= 2 || plain)) ? 1 : 0;
   }
   p.ws = reinterpret_cast<float*>(workspace);
   { static int r = -1; if (r < 0) { const char* e = getenv("LR2_GEMM_RASTER"); r = e ? atoi(e) : 0; } p.raster = r; }
   const long long out_rows = transposed_out ? N : M;
   p.ws_slab = out_rows * ldc;
 
+  if (!pair && p.direct && !(getenv("LR2_GEMM_DIRECT") && atoi(getenv("LR2_GEMM_DIRECT")) >= 2)) p.direct = 0;
   if (pair && BN == 256) rc = launch2_major<256>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
   else if (pair) rc = launch2_major<128>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
   else if (BN == 64) rc = launch_major<64>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
