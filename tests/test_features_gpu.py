@@ -53,3 +53,29 @@ def test_feature_shapes_padding_and_cyclic_image_pad():
     assert torch.equal(fx.pad_images(many, shuffle=False), many[0, :16])
     shuffled = fx.pad_images(img_emb, shuffle=True)
     assert sorted(shuffled[:3].sum(1).tolist()) == pytest.approx(sorted(img_emb[0].sum(1).tolist()))
+
+
+def test_features_vs_the_reference_towers_golden():
+    """Full 12-layer ViT-B/16 and RoBERTa-base towers with the weights and inputs of tests/golden/tower.pt (hidden
+    states produced by the reference's own tencentpretrain build_model): the feature extractor's outputs must be those
+    hidden states -- CLS position per keyframe for img_emb; for text_emb the real-token positions of every tag, which
+    padding the sequence to the fusion model's 196 positions (masked keys) must not change.  bf16: 2e-2 of scale."""
+    from tests import golden_util, parity
+    from tests.test_tower_gpu import GOLD, _build
+    vit, gold_v = _build("vit")
+    rob, gold_r = _build("roberta")
+    fx = FeatureExtractor(vit, rob)
+    frames, _ = golden_util.tower_inputs("vit")
+    img_emb = fx.image_features(frames.cuda())
+    assert img_emb.shape == (1, frames.shape[0], 768)
+    parity.check("features vs reference towers", "img_emb (ViT CLS)", parity.rel_err(img_emb[0], gold_v["hidden"][:, 0, :]), 2e-2)
+    tokens, seg = golden_util.tower_inputs("roberta")
+    lens = seg.sum(dim=1)
+    text_emb = fx.text_features(tokens.cuda(), lens.cuda())
+    assert text_emb.shape == (tokens.shape[0], 196, 768)
+    scale = gold_r["hidden"].abs().max().item()
+    worst = 0.0
+    for i, n in enumerate(lens.tolist()):
+        d = (text_emb[i, :n].float().cpu() - gold_r["hidden"][i, :n]).abs().max().item() / scale
+        worst = max(worst, d)
+    parity.check("features vs reference towers", "text_emb (RoBERTa, real-token positions)", worst, 2e-2)

@@ -64,3 +64,38 @@ def test_train_mode_restatement_vs_reference_with_replayed_masks():
         got = p.grad if ref.numel() == p.grad.numel() else golden_util.grad_sample(p.grad)
         scale = max(ref.abs().max().item(), gold["gnorm/" + name].item() / p.numel() ** 0.5)
         assert (got.reshape(-1) - ref.reshape(-1)).abs().max().item() <= 2e-5 * scale + 1e-9, name
+
+
+def test_rollout_memory_ring_semantics():
+    """ppo.RolloutMemory host logic (bf16 sources: no kernel involved): slots fill in order, entries come back in
+    insertion order with the reference's 8-field layout (finetune/ppo.py:878-883), the image set is stored
+    un-repeated, a full ring refuses another batch and clear() rewinds it."""
+    import pytest
+    from lr2ppo_b200 import ppo
+    bs, tags, S, I, E = 3, 2, 4, 5, 8
+    mem = ppo.RolloutMemory(2, bs, tags, S, I, E, "cpu")
+    g = torch.Generator().manual_seed(0)
+    batches = []
+    for k in range(2):
+        text = torch.randn(bs, tags, S, E, generator=g).bfloat16()
+        img = torch.randn(bs, I, E, generator=g).bfloat16()                       # as the loader yields it: [bs, I, E]
+        tgts = torch.randint(0, 3, (bs, tags), generator=g)
+        t, i, y = mem.stage(text, img, tgts)
+        assert i.shape == (bs, 1, I, E) and torch.equal(t, text) and torch.equal(i[:, 0], img) and torch.equal(y, tgts)
+        state = torch.arange(tags).repeat(bs, 1)
+        next_state = torch.randint(0, tags, (bs, 2 + tags), generator=g)
+        scores, rewards, value = torch.randn(bs, tags, generator=g), torch.randn(bs, 1, generator=g), torch.randn(bs, generator=g)
+        mem.commit([state, next_state, scores, rewards, value, t, i, y])
+        batches.append((state, next_state, scores, rewards.view(-1), value, text, img.unsqueeze(1), tgts))
+    assert len(mem) == 2
+    with pytest.raises(RuntimeError):
+        mem.stage(*[b for b in (batches[0][5], batches[0][6], batches[0][7])])
+    for got, want in zip(mem, batches):
+        assert len(got) == 8
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+    assert mem.bytes_per_entry() == bs * ((tags * S + I) * E * 2 + tags * 8 * 2 + (2 + tags) * 8 + tags * 4 + 8)
+    mem.clear()
+    assert len(mem) == 0 and len(list(mem)) == 0
+    mem.stage(batches[1][5], batches[1][6], batches[1][7])                          # [bs, 1, I, E] accepted as well
+    assert torch.equal(mem.text[0], batches[1][5])

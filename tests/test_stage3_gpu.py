@@ -152,3 +152,54 @@ def test_cuda_graph_step_equals_eager(sds):
     cg = model.critic.head.weight.detach().cpu()
     assert torch.allclose(st_g, st_e, rtol=1e-4, atol=1e-6), (st_g, st_e)
     assert torch.allclose(wg, we, rtol=0, atol=1e-7) and torch.allclose(cg, ce, rtol=0, atol=1e-7)
+
+
+def test_graphed_cycle_equals_the_eager_cycle(sds):
+    """ppo.GraphedCycle (what scripts/ppo.py runs: rollout graph + update graph over a bf16 RolloutMemory, schedulers
+    stepped once per cycle, learning rate fed to the replayed AdamW through update_hyper) == the reference's cycle
+    written eagerly (finetune/ppo.py:845-908: rollouts into a Python list, then train_model over it)."""
+    from lr2ppo_b200 import ppo
+    g = torch.Generator().manual_seed(9)
+    bs, n_batches, cycles = 4, 4, 2
+    data = [[(torch.randn(bs, 2, 196, 768, generator=g).cuda(), torch.randn(bs, 16, 768, generator=g).cuda(),
+              torch.randint(0, 3, (bs, 2), generator=g).cuda()) for _ in range(n_batches)] for _ in range(cycles)]
+
+    def build():
+        model, reward = _build_gpu(sds)
+        for m in model.modules():
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        hp = _hp(False, bf16_grad=True)
+        hp.learning_rate, hp.critic_learning_rate, hp.scheduler, hp.train_steps = 1e-7, 2e-7, "linear", 4
+        return (model, reward, hp) + tuple(ppo.build_optimizer(hp, model))
+
+    def snapshot(model, stats):
+        return (golden_util.grad_sample(model.actor.out_layer.fc1.weight.detach(), 1 << 16).cpu(),
+                model.critic.head.weight.detach().cpu().clone(), model.actor.text_proj.fc2.weight.detach().cpu().clone(),
+                torch.stack([s.detach().float().cpu() for s in stats]))
+
+    model, reward, hp, opt, copt, sch, csch = build()
+    for cyc in data:
+        mems = [ppo.rollout(model, reward, t, i.unsqueeze(1), y) for t, i, y in cyc]
+        model.train()
+        stats = ppo.train_model(hp, model, opt, copt, sch, csch, mems, 0)
+        model.eval()
+    lr_e = opt.param_groups[0]["lr"]
+    eager = snapshot(model, stats)
+    del model, reward, opt, copt, mems
+    torch.cuda.empty_cache()
+
+    model, reward, hp, opt, copt, sch, csch = build()
+    cycle = ppo.GraphedCycle(hp, model, reward, opt, copt, capacity=n_batches, bs=bs, tags=2)
+    for cyc in data:
+        for t, i, y in cyc:
+            cycle.rollout(t, i, y)
+        assert len(cycle.memory) == n_batches
+        stats = cycle.update(sch, csch)
+        assert len(cycle.memory) == 0
+    assert cycle._update_graph is not None and cycle._rollout_graph is not None      # the graphs really replayed
+    assert opt.param_groups[0]["lr"] == lr_e
+    graphed = snapshot(model, stats)
+    assert torch.allclose(graphed[3], eager[3], rtol=1e-4, atol=1e-6), (graphed[3], eager[3])
+    for a, b in zip(graphed[:3], eager[:3]):
+        assert torch.allclose(a, b, rtol=0, atol=1e-7)
