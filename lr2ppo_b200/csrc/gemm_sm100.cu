@@ -69,7 +69,7 @@ struct GemmParams {
   int act;             // activation of the GELU epilogues: 0 = exact erf GELU, 1 = QuickGELU x*sigmoid(1.702x)
   int mode;            // EpiMode resolved on the host from (epi, act, drop_p, bias)
   int dbg;             // LR2_GEMM_DBG (profiling experiments only): 1 = skip the accumulator drain, 2 = skip the MMAs
-  int direct;          // 1: full bf16 chunks go TMEM -> registers -> 256-bit global stores (no smem staging)
+  int direct;          // 1: launch the DIRECT instantiation of the pair kernel (plain bf16 output: TMEM -> registers -> 256-bit stores)
   // LR2_EPI_ADAMW (fused wgrad + AdamW): C = fp32 parameter (in/out)
   float* adam_m; float* adam_v; bf16* adam_shadow; const float* adam_hyper; float adam_wd;
 };
@@ -391,115 +391,31 @@ __device__ __forceinline__ void chunk_rows(const GemmParams& q, const OutSel& o,
 // ---- direct drain (round 2): TMEM -> registers -> global, no shared-memory staging --------------------------------
 // tcgen05.ld.32x32b hands every lane ONE output row (32 consecutive fp32 columns).  The staged path above re-shapes
 // that through shared memory into 4-lanes-per-row groups so that a warp store covers whole 64-byte row pieces; with
-// the 256-bit global accesses of sm_100 (STG.E.ENL2.256 / LDG.E.ENL2.256) a lane moves 16 bf16 = one full 32-byte
-// sector of its row per instruction, so sector efficiency is the same and the staging round trip -- 8 STS.128 +
-// 8 LDS.128 per lane and chunk, 2 x 128 KB of shared-memory traffic per 128 x 256 tile on top of the UMMA operand
-// reads and TMA fills that already sit at ~110 B/clk/SM of the 128 B/clk the SM has -- disappears.  Used for full
-// 32 x 32 chunks of untransposed bf16 outputs in the host-resolved fast modes; everything else keeps the staged path.
+// the 256-bit global stores of sm_100 (STG.E.ENL2.256) a lane moves 16 bf16 = one full 32-byte sector of its row per
+// instruction, so sector efficiency is the same and the staging round trip -- 8 STS.128 + 8 LDS.128 per lane and
+// chunk -- disappears.  Compiled ONLY into the DIRECT instantiation of the pair kernel, which the host selects for
+// plain (EM_NONE) untransposed bf16 outputs: measured on B200 it wins there (9408x3072x768: 47.1 vs 50.6 us) and
+// loses wherever the epilogue carries math (GELU +14 %, dropout +10 %; profiles/r02_gemm_shapes_direct_all.txt).
+// Keeping it out of every other instantiation matters: inlined next to the staged modes it pushed all GEMM kernels
+// over their 96-register budget (124-232 bytes of spills, ~10 % on every shape).
 __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t (&u)[8]) {
   asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]),
                "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
                : "memory");
 }
-__device__ __forceinline__ void ld_global_256(const void* ptr, uint32_t (&u)[8]) {
-  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
-               : "l"(ptr));
-}
-__device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
-template <int MODE>
-__device__ __forceinline__ void chunk_direct(const GemmParams& q, uint32_t taddr_c, int lane, int m_base, int n_base) {
-  constexpr bool HAS_BIAS = MODE == EM_BIAS || MODE == EM_BIAS_GELU || MODE == EM_BIAS_GELU_DROP ||
-                            MODE == EM_BIAS_RES || MODE == EM_BIAS_DROP_RES;
-  constexpr bool HAS_AUX = MODE == EM_BIAS_RES || MODE == EM_BIAS_DROP_RES || MODE == EM_DGELU ||
-                           MODE == EM_DGELU_DROP || MODE == EM_ADD;
-  constexpr bool HAS_DROP = MODE == EM_BIAS_GELU_DROP || MODE == EM_BIAS_DROP_RES || MODE == EM_DGELU_DROP;
-  constexpr bool IS_GELU = MODE == EM_BIAS_GELU || MODE == EM_BIAS_GELU_DROP;
+__device__ __forceinline__ void chunk_direct_plain(const GemmParams& q, uint32_t taddr_c, int lane, int m_base, int n_base) {
   uint32_t r[32];
   tmem_ld32(taddr_c, r);
-  const long long row = m_base + lane;
-  const long long off = row * q.ldc + n_base;
-  // everything that does not depend on the accumulator is issued while the TMEM load is in flight
-  uint32_t ax[2][8];
-  if constexpr (HAS_AUX) {
-    const bf16* ap = q.aux + row * q.ldaux + n_base;
-    ld_global_256(ap, ax[0]);
-    ld_global_256(ap + 16, ax[1]);
-  }
-  unsigned long long seed = 0;
-  if constexpr (HAS_DROP) seed = q.seed + (q.seed_dev ? *q.seed_dev : 0ull);
-  const bool want_pre = IS_GELU && q.C2 != nullptr;
+  bf16* dst = (bf16*)q.C + (long long)(m_base + lane) * q.ldc + n_base;
   tmem_ld_wait();
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    float v[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[16 * h + i]);
-    if constexpr (HAS_BIAS) {
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(q.bias + n_base + 16 * h + 4 * g));   // warp-uniform
-        v[4 * g] += b.x; v[4 * g + 1] += b.y; v[4 * g + 2] += b.z; v[4 * g + 3] += b.w;
-      }
-    }
-    float m[16];
-    if constexpr (HAS_DROP) {
-      float m0[8], m1[8];
-      dropout_mult8(seed, q.site, (uint64_t)(off + 16 * h) >> 3, q.drop_thresh, q.drop_scale, m0);
-      dropout_mult8(seed, q.site, ((uint64_t)(off + 16 * h) >> 3) + 1, q.drop_thresh, q.drop_scale, m1);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { m[i] = m0[i]; m[8 + i] = m1[i]; }
-    }
-    float a[16];
-    if constexpr (HAS_AUX) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { a[2 * i] = bf16lo(ax[h][i]); a[2 * i + 1] = bf16hi(ax[h][i]); }
-    }
-    if constexpr (IS_GELU) {
-      // GELU of the bf16-rounded pre-activation: backward only has the stored bf16 copy
-      uint32_t pre[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) pre[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-      if (want_pre) st_global_256(q.C2 + off + 16 * h, pre);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float x0 = bf16lo(pre[i]), x1 = bf16hi(pre[i]);
-        v[2 * i] = HAS_DROP ? gelu_fast(x0) * m[2 * i] : gelu_fast(x0);
-        v[2 * i + 1] = HAS_DROP ? gelu_fast(x1) * m[2 * i + 1] : gelu_fast(x1);
-      }
-    } else if constexpr (MODE == EM_BIAS_RES || MODE == EM_ADD) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] += a[i];
-    } else if constexpr (MODE == EM_BIAS_DROP_RES) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = fmaf(v[i], m[i], a[i]);
-    } else if constexpr (MODE == EM_DGELU || MODE == EM_DGELU_DROP) {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] *= HAS_DROP ? gelu_fast_grad(a[i]) * m[i] : gelu_fast_grad(a[i]);
-    }
     uint32_t u[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) u[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-    st_global_256((bf16*)q.C + off + 16 * h, u);
-  }
-}
-
-// -> true when the chunk was written by the direct path
-__device__ __forceinline__ bool chunk_direct_dispatch(const GemmParams& q, const OutSel& o, uint32_t taddr_c, int lane,
-                                                      int m_base, int n_base) {
-  switch (o.mode) {
-    case EM_NONE: chunk_direct<EM_NONE>(q, taddr_c, lane, m_base, n_base); return true;
-    case EM_BIAS: chunk_direct<EM_BIAS>(q, taddr_c, lane, m_base, n_base); return true;
-    case EM_BIAS_GELU: chunk_direct<EM_BIAS_GELU>(q, taddr_c, lane, m_base, n_base); return true;
-    case EM_BIAS_GELU_DROP: chunk_direct<EM_BIAS_GELU_DROP>(q, taddr_c, lane, m_base, n_base); return true;
-    case EM_BIAS_RES: chunk_direct<EM_BIAS_RES>(q, taddr_c, lane, m_base, n_base); return true;
-    case EM_BIAS_DROP_RES: chunk_direct<EM_BIAS_DROP_RES>(q, taddr_c, lane, m_base, n_base); return true;
-    case EM_DGELU: chunk_direct<EM_DGELU>(q, taddr_c, lane, m_base, n_base); return true;
-    case EM_DGELU_DROP: chunk_direct<EM_DGELU_DROP>(q, taddr_c, lane, m_base, n_base); return true;
-    case EM_ADD: chunk_direct<EM_ADD>(q, taddr_c, lane, m_base, n_base); return true;
-    default: return false;
+    for (int i = 0; i < 8; ++i)
+      u[i] = pack_bf16x2(__uint_as_float(r[16 * h + 2 * i]), __uint_as_float(r[16 * h + 2 * i + 1]));
+    st_global_256(dst + 16 * h, u);
   }
 }
 
@@ -620,7 +536,7 @@ __device__ __noinline__ void chunk_transposed(const GemmParams& q, const OutSel 
 
 // Drain one accumulator tile (this warp's TMEM lane quadrant and column part): TMEM -> registers -> per-warp smem
 // staging -> coalesced 8-wide groups through the fused epilogue.  Shared by the 1-CTA and 2-CTA kernels.
-template <int BN, bool ADAMW>
+template <int BN, bool ADAMW, bool DIRECT = false>
 __device__ __forceinline__ void drain_tile(const GemmParams& q, const OutSel& o, uint32_t taddr, int m_base, int nt,
                                            float* stg, int lane, int half) {
   constexpr int PARTS = EPI_WARPS / 4;
@@ -634,11 +550,12 @@ __device__ __forceinline__ void drain_tile(const GemmParams& q, const OutSel& o,
       chunk_transposed(q, o, taddr + (uint32_t)c0, lane, m_base, n_base);
       continue;
     }
-    if constexpr (!ADAMW) {
-      // full chunk, bf16 output, 32-byte aligned rows: straight from registers (see chunk_direct)
-      if (q.direct && !o.c_f32 && m_base + 32 <= q.M && n_base + 32 <= q.N &&
-          chunk_direct_dispatch(q, o, taddr + (uint32_t)c0, lane, m_base, n_base))
+    if constexpr (DIRECT) {
+      // host guarantees: plain epilogue, untransposed bf16 output, 32-byte aligned rows, no split-K
+      if (m_base + 32 <= q.M && n_base + 32 <= q.N) {
+        chunk_direct_plain(q, taddr + (uint32_t)c0, lane, m_base, n_base);
         continue;
+      }
     }
     {
       uint32_t r[32];
@@ -653,6 +570,8 @@ __device__ __forceinline__ void drain_tile(const GemmParams& q, const OutSel& o,
     __syncwarp();
     if constexpr (ADAMW) {
       chunk_checked_body<true>(q, o, stg, lane, m_base, n_base);
+    } else if constexpr (DIRECT) {
+      chunk_checked(q, o, stg, lane, m_base, n_base);          // ragged edge chunks only
     } else {
       if (!(m_base + 32 <= q.M && n_base + 32 <= q.N && chunk_fast(q, o, stg, lane, m_base, n_base)))
         chunk_checked(q, o, stg, lane, m_base, n_base);
@@ -889,7 +808,7 @@ struct SmemLayout2 {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024;
 };
 
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool DIRECT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
              const __grid_constant__ GemmParams p) {
@@ -1044,7 +963,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       if (p.splits > 1) {
         o.C = p.ws + (long long)split * p.ws_slab; o.c_f32 = 1; o.mode = EM_NONE; o.epi = LR2_EPI_NONE; o.beta = 0.f;
       }
-      if (!(p.dbg & 1)) drain_tile<BN, false>(p, o, taddr, m_base, nt, stg, lane, half);
+      if (!(p.dbg & 1)) drain_tile<BN, false, DIRECT>(p, o, taddr, m_base, nt, stg, lane, half);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[buf]), 0));
@@ -1162,12 +1081,12 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
 }
 
 // 2-CTA pair kernel: persistent over min(#tiles, resident clusters) CTA pairs.
-template <int BN, bool A_MN, bool B_MN>
+template <int BN, bool A_MN, bool B_MN, bool DIRECT>
 static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using L = SmemLayout2<BN>;
   static int max_pairs = 0;
   if (max_pairs == 0) {
-    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+    cudaError_t e = cudaFuncSetAttribute(gemm2_kernel<BN, A_MN, B_MN, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
     if (e != cudaSuccess) return LR2_ERR_CUDA;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(num_sms() & ~1); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = L::TOTAL;
@@ -1176,24 +1095,24 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    e = cudaOccupancyMaxActiveClusters(&n, gemm2_kernel<BN, A_MN, B_MN>, &cfg);
+    e = cudaOccupancyMaxActiveClusters(&n, gemm2_kernel<BN, A_MN, B_MN, DIRECT>, &cfg);
     if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms() / 2; }
     max_pairs = n < num_sms() / 2 ? n : num_sms() / 2;
   }
   const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = (p.N + BN - 1) / BN;
   const int total = m_tiles * n_tiles * p.splits;
   const int pairs = total < max_pairs ? total : max_pairs;
-  gemm2_kernel<BN, A_MN, B_MN><<<2 * pairs, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, p); LR2_LAUNCHED(1);
+  gemm2_kernel<BN, A_MN, B_MN, DIRECT><<<2 * pairs, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, p); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 
-template <int BN>
+template <int BN, bool DIRECT>
 static int launch2_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
                          cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch2<BN, false, false>(ta, tb, p, s);
-  if (!a_mn && b_mn) return launch2<BN, false, true>(ta, tb, p, s);
-  if (a_mn && !b_mn) return launch2<BN, true, false>(ta, tb, p, s);
-  return launch2<BN, true, true>(ta, tb, p, s);
+  if (!a_mn && !b_mn) return launch2<BN, false, false, DIRECT>(ta, tb, p, s);
+  if (!a_mn && b_mn) return launch2<BN, false, true, DIRECT>(ta, tb, p, s);
+  if (a_mn && !b_mn) return launch2<BN, true, false, DIRECT>(ta, tb, p, s);
+  return launch2<BN, true, true, DIRECT>(ta, tb, p, s);
 }
 
 template <int BN>
@@ -1284,28 +1203,21 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   p.mode = resolve_mode(epilogue, act, drop_p, bias, c_is_f32, beta);
   { static int d = -1; if (d < 0) { const char* e = getenv("LR2_GEMM_DBG"); d = e ? atoi(e) : 0; } p.dbg = d; }
   {
-    // direct drain needs 32-byte aligned row pieces: pitches and base pointers of C / C2 / aux multiples of 16 elements
+    // direct drain (pair kernel, 256-wide tiles): plain epilogue, untransposed bf16 output, no split-K, 32-byte aligned
+    // row pieces (pitch a multiple of 16 elements, 32-byte aligned base).  LR2_GEMM_DIRECT=0 keeps the staged drain.
     static int dsel = -1;
     if (dsel < 0) { const char* e = getenv("LR2_GEMM_DIRECT"); dsel = e ? atoi(e) : 1; }
-    const bool al = (ldc % 16 == 0) && ((reinterpret_cast<uintptr_t>(C) & 31) == 0) &&
-                    (C2 == nullptr || (reinterpret_cast<uintptr_t>(C2) & 31) == 0) &&
-                    (aux == nullptr || ((ldaux % 16 == 0) && (reinterpret_cast<uintptr_t>(aux) & 31) == 0));
-    // Measured on B200 (profiles/r02_gemm_shapes.txt): the direct drain wins on the plain pair-kernel GEMMs
-    // (9408x3072x768: 47.1 vs 50.6 us) and loses where the epilogue carries math or the rows are far apart (GELU
-    // +14 %, dropout +10 %, the K = 48 fc1 weight gradient 367 vs 274 us: 96 registers no longer hold a 32-column
-    // accumulator row plus the epilogue operands without spilling).  Default: plain epilogue only; LR2_GEMM_DIRECT=2
-    // forces it for every fast mode, 0 disables it.
-    const bool plain = (p.mode == EM_NONE);
-    p.direct = (dsel && al && !transposed_out && !c_is_f32 && splits == 1 && (dsel >= 2 || plain)) ? 1 : 0;
+    p.direct = (dsel && pair && BN == 256 && p.mode == EM_NONE && !transposed_out && !c_is_f32 && splits == 1 &&
+                (ldc % 16 == 0) && ((reinterpret_cast<uintptr_t>(C) & 31) == 0)) ? 1 : 0;
   }
   p.ws = reinterpret_cast<float*>(workspace);
   { static int r = -1; if (r < 0) { const char* e = getenv("LR2_GEMM_RASTER"); r = e ? atoi(e) : 0; } p.raster = r; }
   const long long out_rows = transposed_out ? N : M;
   p.ws_slab = out_rows * ldc;
 
-  if (!pair && p.direct && !(getenv("LR2_GEMM_DIRECT") && atoi(getenv("LR2_GEMM_DIRECT")) >= 2)) p.direct = 0;
-  if (pair && BN == 256) rc = launch2_major<256>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
-  else if (pair) rc = launch2_major<128>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
+  if (pair && BN == 256 && p.direct) rc = launch2_major<256, true>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
+  else if (pair && BN == 256) rc = launch2_major<256, false>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
+  else if (pair) rc = launch2_major<128, false>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
   else if (BN == 64) rc = launch_major<64>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
   else if (BN == 128) rc = launch_major<128>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
   else rc = launch_major<256>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
