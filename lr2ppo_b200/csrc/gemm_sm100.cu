@@ -764,13 +764,25 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Execution-only rendezvous of the pair (kernel end: neither CTA may exit or free TMEM while its peer still reads its
+// smem / TMEM).  No data is published through it, so the arrive is relaxed: a .release arrive would first wait for the
+// L2 acknowledgement of every output store of the CTA.
+__device__ __forceinline__ void cluster_sync_exec() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+}
 __device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// Arrive on a barrier of the pair's leader CTA.  Default semantics (.release.cta), as in the single-CTA kernel: the
+// only thing the MMA thread consumes after this arrive is the TMEM accumulator buffer, whose reads are ordered by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync.  A .release.cluster arrive made every epilogue warp wait for
+// the L2 acknowledgement of all its output stores first (MEMBAR.ALL.GPU + ERRBAR: 17 % of the kernel's stall
+// samples in profiles/r02_gemm_plain_sass.md) before the accumulator buffer was handed back.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint32_t leader_bar, int c0,
                                                  int c1) {
@@ -972,7 +984,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
 
   __syncwarp();
   tc_fence_before();
-  cluster_sync_all();      // neither CTA may exit (or free TMEM) while its pair still reads its smem / TMEM
+  cluster_sync_exec();     // neither CTA may exit (or free TMEM) while its pair still reads its smem / TMEM
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
