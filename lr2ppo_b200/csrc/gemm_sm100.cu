@@ -69,7 +69,7 @@ struct GemmParams {
   int act;             // activation of the GELU epilogues: 0 = exact erf GELU, 1 = QuickGELU x*sigmoid(1.702x)
   int mode;            // EpiMode resolved on the host from (epi, act, drop_p, bias)
   int dbg;             // LR2_GEMM_DBG (profiling experiments only): 1 = skip the accumulator drain, 2 = skip the MMAs
-  int direct;          // 1: launch the DIRECT instantiation of the pair kernel (plain bf16 output: TMEM -> registers -> 256-bit stores)
+  int direct;          // pair-kernel instantiation for plain bf16 outputs: 0 staged, 1 = 256-bit register stores, 2 = TMA store
   // LR2_EPI_ADAMW (fused wgrad + AdamW): C = fp32 parameter (in/out)
   float* adam_m; float* adam_v; bf16* adam_shadow; const float* adam_hyper; float adam_wd;
 };
@@ -419,6 +419,53 @@ __device__ __forceinline__ void chunk_direct_plain(const GemmParams& q, uint32_t
   }
 }
 
+// ---- TMA-store drain (DIRECT == 2) ------------------------------------------------------------------------------
+// The warp's 32 rows x 64 bf16 columns of the tile are packed into its 4 KB staging buffer in the 128-byte-swizzle
+// layout a {64, 32} box of the output tensor map expects (16-byte chunk c of row r at chunk c ^ (r & 7): the same
+// conflict-free pattern stg_chunk uses), then ONE lane hands the box to the TMA unit (cp.async.bulk.tensor ...
+// global.shared::cta, SASS UTMASTG).  The epilogue warps never wait on their own global stores, the TMA unit writes
+// whole 128-byte lines, and boxes that stick out of the tensor are clipped by the hardware, so this path has no
+// ragged-edge branch at all.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// 32 accumulator columns [c32*32, c32*32+32) of this lane's row -> bf16 -> chunks c32*4 .. c32*4+3 of the row
+__device__ __forceinline__ void stage_bf16_swizzled(uint8_t* stg, uint32_t taddr_c, int lane, int c32) {
+  uint32_t r[32];
+  tmem_ld32(taddr_c, r);
+  tmem_ld_wait();
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    uint4 u;
+    u.x = pack_bf16x2(__uint_as_float(r[8 * g + 0]), __uint_as_float(r[8 * g + 1]));
+    u.y = pack_bf16x2(__uint_as_float(r[8 * g + 2]), __uint_as_float(r[8 * g + 3]));
+    u.z = pack_bf16x2(__uint_as_float(r[8 * g + 4]), __uint_as_float(r[8 * g + 5]));
+    u.w = pack_bf16x2(__uint_as_float(r[8 * g + 6]), __uint_as_float(r[8 * g + 7]));
+    *reinterpret_cast<uint4*>(stg + lane * 128 + (((c32 * 4 + g) ^ (lane & 7)) << 4)) = u;
+  }
+}
+
+// One warp's share (32 rows x 64 columns starting at column c0 of the tile) of a 256-wide accumulator tile.
+__device__ __forceinline__ void drain_warp_tma(const CUtensorMap* tmap_c, uint8_t* stg, uint32_t taddr, int c0, int lane,
+                                               int m_base, int n_base) {
+  if (lane == 0) tma_store_wait_read();      // the previous box of this warp has left the staging buffer
+  __syncwarp();
+  stage_bf16_swizzled(stg, taddr + (uint32_t)c0, lane, 0);
+  stage_bf16_swizzled(stg, taddr + (uint32_t)(c0 + 32), lane, 1);
+  fence_proxy_async_smem();                  // generic-proxy writes -> visible to the async proxy (TMA)
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tmap_c, stg, n_base, m_base);   // rows >= M / columns >= N of the box are clipped by the TMA unit
+    tma_store_commit();
+  }
+}
+
 // Returns false when (mode, output type) has no fast instantiation; the caller then takes the checked generic loop.
 __device__ __forceinline__ bool chunk_fast(const GemmParams& q, const OutSel& o, const float* stg, int lane, int m_base,
                                            int n_base) {
@@ -536,7 +583,7 @@ __device__ __noinline__ void chunk_transposed(const GemmParams& q, const OutSel 
 
 // Drain one accumulator tile (this warp's TMEM lane quadrant and column part): TMEM -> registers -> per-warp smem
 // staging -> coalesced 8-wide groups through the fused epilogue.  Shared by the 1-CTA and 2-CTA kernels.
-template <int BN, bool ADAMW, bool DIRECT = false>
+template <int BN, bool ADAMW, int DIRECT = 0>
 __device__ __forceinline__ void drain_tile(const GemmParams& q, const OutSel& o, uint32_t taddr, int m_base, int nt,
                                            float* stg, int lane, int half) {
   constexpr int PARTS = EPI_WARPS / 4;
@@ -550,7 +597,7 @@ __device__ __forceinline__ void drain_tile(const GemmParams& q, const OutSel& o,
       chunk_transposed(q, o, taddr + (uint32_t)c0, lane, m_base, n_base);
       continue;
     }
-    if constexpr (DIRECT) {
+    if constexpr (DIRECT == 1) {
       // host guarantees: plain epilogue, untransposed bf16 output, 32-byte aligned rows, no split-K
       if (m_base + 32 <= q.M && n_base + 32 <= q.N) {
         chunk_direct_plain(q, taddr + (uint32_t)c0, lane, m_base, n_base);
@@ -570,7 +617,7 @@ __device__ __forceinline__ void drain_tile(const GemmParams& q, const OutSel& o,
     __syncwarp();
     if constexpr (ADAMW) {
       chunk_checked_body<true>(q, o, stg, lane, m_base, n_base);
-    } else if constexpr (DIRECT) {
+    } else if constexpr (DIRECT == 1) {
       chunk_checked(q, o, stg, lane, m_base, n_base);          // ragged edge chunks only
     } else {
       if (!(m_base + 32 <= q.M && n_base + 32 <= q.N && chunk_fast(q, o, stg, lane, m_base, n_base)))
@@ -820,10 +867,10 @@ struct SmemLayout2 {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + STG_BYTES + 1024;
 };
 
-template <int BN, bool A_MN, bool B_MN, bool DIRECT>
+template <int BN, bool A_MN, bool B_MN, int DIRECT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-             const __grid_constant__ GemmParams p) {
+             const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ GemmParams p) {
   using L = SmemLayout2<BN>;
   constexpr int STAGES = L::STAGES;
   constexpr int HB = L::HB;
@@ -834,13 +881,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   // identical offsets in both CTAs: the dynamic smem base is the same for every CTA of a launch
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // pointer arithmetic keeps the shared space
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES);
+  // staging first (1024-byte aligned per-warp 4 KB buffers: the TMA-store drain needs swizzle-atom alignment), then
+  // the barriers
+  float* stg_all = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE_BYTES + L::STG_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;
   uint64_t* tempty_bar = bars + 2 * STAGES + NBUF;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * NBUF);
-  float* stg_all = reinterpret_cast<float*>(smem + STAGES * L::STAGE_BYTES + L::BAR_BYTES);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -862,6 +911,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
     tma_prefetch_desc(&tmap_b);
+    if constexpr (DIRECT == 2) tma_prefetch_desc(&tmap_c);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -975,10 +1025,19 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       if (p.splits > 1) {
         o.C = p.ws + (long long)split * p.ws_slab; o.c_f32 = 1; o.mode = EM_NONE; o.epi = LR2_EPI_NONE; o.beta = 0.f;
       }
-      if (!(p.dbg & 1)) drain_tile<BN, false, DIRECT>(p, o, taddr, m_base, nt, stg, lane, half);
+      if constexpr (DIRECT == 2) {
+        static_assert(DIRECT != 2 || (BN == 256 && EPI_WARPS == 16), "TMA-store drain: 64 columns per warp");
+        if (!(p.dbg & 1) && m_base < p.M && nt * BN + half * 64 < p.N)      // warp-uniform: box not entirely outside
+          drain_warp_tma(&tmap_c, reinterpret_cast<uint8_t*>(stg), taddr, half * 64, lane, m_base, nt * BN + half * 64);
+      } else {
+        if (!(p.dbg & 1)) drain_tile<BN, false, DIRECT>(p, o, taddr, m_base, nt, stg, lane, half);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[buf]), 0));
+    }
+    if constexpr (DIRECT == 2) {
+      if (lane == 0) tma_store_wait_read();    // the staging buffer must outlive the last box read
     }
   }
 
@@ -1093,8 +1152,9 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams
 }
 
 // 2-CTA pair kernel: persistent over min(#tiles, resident clusters) CTA pairs.
-template <int BN, bool A_MN, bool B_MN, bool DIRECT>
-static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+template <int BN, bool A_MN, bool B_MN, int DIRECT>
+static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const GemmParams& p,
+                   cudaStream_t stream) {
   using L = SmemLayout2<BN>;
   static int max_pairs = 0;
   if (max_pairs == 0) {
@@ -1114,17 +1174,17 @@ static int launch2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParam
   const int m_tiles = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = (p.N + BN - 1) / BN;
   const int total = m_tiles * n_tiles * p.splits;
   const int pairs = total < max_pairs ? total : max_pairs;
-  gemm2_kernel<BN, A_MN, B_MN, DIRECT><<<2 * pairs, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, p); LR2_LAUNCHED(1);
+  gemm2_kernel<BN, A_MN, B_MN, DIRECT><<<2 * pairs, GEMM_THREADS, L::TOTAL, stream>>>(ta, tb, tc, p); LR2_LAUNCHED(1);
   LR2_RETURN_LAUNCH();
 }
 
-template <int BN, bool DIRECT>
-static int launch2_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                         cudaStream_t s) {
-  if (!a_mn && !b_mn) return launch2<BN, false, false, DIRECT>(ta, tb, p, s);
-  if (!a_mn && b_mn) return launch2<BN, false, true, DIRECT>(ta, tb, p, s);
-  if (a_mn && !b_mn) return launch2<BN, true, false, DIRECT>(ta, tb, p, s);
-  return launch2<BN, true, true, DIRECT>(ta, tb, p, s);
+template <int BN, int DIRECT>
+static int launch2_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                         const GemmParams& p, cudaStream_t s) {
+  if (!a_mn && !b_mn) return launch2<BN, false, false, DIRECT>(ta, tb, tc, p, s);
+  if (!a_mn && b_mn) return launch2<BN, false, true, DIRECT>(ta, tb, tc, p, s);
+  if (a_mn && !b_mn) return launch2<BN, true, false, DIRECT>(ta, tb, tc, p, s);
+  return launch2<BN, true, true, DIRECT>(ta, tb, tc, p, s);
 }
 
 template <int BN>
@@ -1214,22 +1274,34 @@ extern "C" int lr2_gemm_bf16(const void* A, long long lda, int a_mn_major, const
   p.drop_thresh = dropout_thresh16(drop_p); p.drop_scale = dropout_scale16(drop_p);
   p.mode = resolve_mode(epilogue, act, drop_p, bias, c_is_f32, beta);
   { static int d = -1; if (d < 0) { const char* e = getenv("LR2_GEMM_DBG"); d = e ? atoi(e) : 0; } p.dbg = d; }
+  CUtensorMap tc = ta;        // only read by the TMA-store instantiation
   {
-    // direct drain (pair kernel, 256-wide tiles): plain epilogue, untransposed bf16 output, no split-K, 32-byte aligned
-    // row pieces (pitch a multiple of 16 elements, 32-byte aligned base).  LR2_GEMM_DIRECT=0 keeps the staged drain.
+    // Plain bf16 outputs of the pair kernel (256-wide tiles, no split-K) skip the generic staged epilogue:
+    //   LR2_GEMM_DIRECT=2 (default)  TMA-store drain: {64, 32} boxes of an output tensor map (any 16-byte aligned pitch)
+    //   LR2_GEMM_DIRECT=1            256-bit register stores (needs 32-byte aligned row pieces)
+    //   LR2_GEMM_DIRECT=0            staged drain, as every other epilogue mode
     static int dsel = -1;
-    if (dsel < 0) { const char* e = getenv("LR2_GEMM_DIRECT"); dsel = e ? atoi(e) : 1; }
-    p.direct = (dsel && pair && BN == 256 && p.mode == EM_NONE && !transposed_out && !c_is_f32 && splits == 1 &&
-                (ldc % 16 == 0) && ((reinterpret_cast<uintptr_t>(C) & 31) == 0)) ? 1 : 0;
+    if (dsel < 0) { const char* e = getenv("LR2_GEMM_DIRECT"); dsel = e ? atoi(e) : 2; }
+    const bool plain = pair && BN == 256 && p.mode == EM_NONE && !transposed_out && !c_is_f32 && splits == 1;
+    p.direct = 0;
+    if (plain && dsel >= 2) {
+      rc = get_tmap(C, N, M, ldc, 64, 32, &tc);
+      if (rc != LR2_OK) return rc;
+      p.direct = 2;
+    } else if (plain && dsel == 1 && (ldc % 16 == 0) && ((reinterpret_cast<uintptr_t>(C) & 31) == 0)) {
+      p.direct = 1;
+    }
   }
   p.ws = reinterpret_cast<float*>(workspace);
   { static int r = -1; if (r < 0) { const char* e = getenv("LR2_GEMM_RASTER"); r = e ? atoi(e) : 0; } p.raster = r; }
   const long long out_rows = transposed_out ? N : M;
   p.ws_slab = out_rows * ldc;
 
-  if (pair && BN == 256 && p.direct) rc = launch2_major<256, true>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
-  else if (pair && BN == 256) rc = launch2_major<256, false>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
-  else if (pair) rc = launch2_major<128, false>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
+  const bool amn = a_mn_major != 0, bmn = b_mn_major != 0;
+  if (pair && BN == 256 && p.direct == 2) rc = launch2_major<256, 2>(amn, bmn, ta, tb, tc, p, stream);
+  else if (pair && BN == 256 && p.direct == 1) rc = launch2_major<256, 1>(amn, bmn, ta, tb, tc, p, stream);
+  else if (pair && BN == 256) rc = launch2_major<256, 0>(amn, bmn, ta, tb, tc, p, stream);
+  else if (pair) rc = launch2_major<128, 0>(amn, bmn, ta, tb, tc, p, stream);
   else if (BN == 64) rc = launch_major<64>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
   else if (BN == 128) rc = launch_major<128>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);
   else rc = launch_major<256>(a_mn_major != 0, b_mn_major != 0, ta, tb, p, stream);

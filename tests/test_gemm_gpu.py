@@ -202,3 +202,26 @@ def test_gemm_dropout_mask_shared_by_forward_and_backward_epilogues(bn):
     # same mask from the single-CTA 128-wide kernel
     h_ref = ops.gemm(a, w, epilogue=ops.EPI_BIAS_GELU, bias=bias, drop_p=p, seed=77, site=5, block_n=128)
     assert torch.equal((h_ref != 0)[live], keep_f)
+
+
+# ---- plain bf16 outputs of the pair kernel: TMA-store drain (default) / 256-bit stores (LR2_GEMM_DIRECT=1) ----
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (True, True), (False, True)])
+@pytest.mark.parametrize("M,N,K,pad", [(256, 256, 64, 0), (9408, 768, 192, 0), (304, 384, 192, 0), (1000, 768, 320, 64),
+                                        (3072, 2560, 48, 0), (257, 264, 80, 24)])
+def test_gemm_pair_plain_bf16_output_clipping_and_pitch(M, N, K, pad, a_mn, b_mn):
+    """Ragged M and N (boxes clipped by the TMA unit), a row pitch larger than N (columns beside the output must stay
+    untouched), K below one k-block (the out_layer.fc1 weight-gradient shape class)."""
+    g = torch.Generator(device="cuda").manual_seed(M + 3 * N + 5 * K)
+    a = _mk(M, K, a_mn, g)
+    b = _mk(N, K, b_mn, g)
+    full = torch.full((M + 3, N + pad), 7.0, device="cuda", dtype=torch.bfloat16)
+    out = full[:M, :N]
+    ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, out=out, block_n=2256)
+    ref = _ref(a, b, a_mn, b_mn)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 1e-2, f"rel err {_rel(out, ref)}"
+    assert torch.equal(out, ref.to(torch.bfloat16)) or _rel(out, ref.to(torch.bfloat16).float()) < 8e-3
+    assert (full[M:] == 7.0).all() and (full[:, N:] == 7.0).all()        # nothing written outside [M, N]
+    # the staged single-CTA kernel produces the same bits (same fp32 accumulation order per k-block, same rounding)
+    out1 = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, block_n=128)
+    assert _rel(out, out1.float()) < 8e-3
