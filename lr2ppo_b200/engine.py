@@ -17,6 +17,8 @@ Nothing here computes on the host and there is no fallback path.
 """
 import math
 
+import os
+
 import torch
 
 from . import ops
@@ -287,9 +289,10 @@ class FusionEngine:
             x_ = torch.cat([b for _, b in self._fc1_pending], dim=0)
             self._fc1_pending = []
         if bn is None:
-            # K = rows: epilogue-bound -> single-CTA tiles; 128-wide (four TMEM accumulator buffers) up to K = 256,
-            # 256-wide beyond (operand traffic starts to matter: 460 vs 534 us at K = 384)
-            bn = 128 if dy_.shape[0] <= 256 else 256
+            # K = rows: a pure output-write problem (1 GB of bf16 per 500 M-parameter matrix).  Pair kernel with the
+            # TMA-store drain: 215 us against 261 us for single-CTA 128-wide tiles with the staged drain (K = 48,
+            # profiles/r02_gemm_shapes.txt); LR2_FC1_WGRAD_BN overrides (128 / 256 = the round-1 choices)
+            bn = int(os.environ.get("LR2_FC1_WGRAD_BN", "2256"))
         ops.gemm(dy_, x_, a_mn=True, b_mn=True, out=out, block_n=bn)
 
     def enable_bf16_fc1_grad(self, optimizer, passes=1):
