@@ -8,6 +8,8 @@ loop :845-883), re-built on the fused engine:
     backward (the reference synchronises the host once per row at :563-568 and again at :52, :576);
   * the ten per-batch statistic all-reduces (:589-598) are packed into one.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -16,6 +18,23 @@ from .losses import RankLoss, clipped_value_loss, ppo_policy_loss  # noqa: F401 
 from .models import Actor, ActorCritic, Critic, Mlp, Reward  # noqa: F401
 from .ndcg import AverageNDCGMeter
 from .optim import attach_shadows, decay_groups, make_scheduler, str2optimizer, str2scheduler  # noqa: F401
+
+
+_SIDE = {}
+
+
+def _branch_stream(device):
+    """Second CUDA stream for the critic's branch of a step (LR2_DUAL_STREAM=1): the actor and the critic are
+    independent models whose only coupling inside a step is one [bs] vector (the adjusted rewards the value loss
+    regresses on), so their forwards / backwards / optimizer passes can run as two branches of the step's CUDA graph;
+    the launch-latency-bound kernels of one (LayerNorm, bias column sums, 2-4-token attention, tiny GEMMs) fill the
+    gaps of the other.  None = run the step on one stream, in the reference's order."""
+    if os.environ.get("LR2_DUAL_STREAM", "0") != "1" or device.type != "cuda":
+        return None
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
 
 
 def log(t, eps=1e-20):
@@ -59,6 +78,12 @@ def rollout(model, reward_model, text_emb_batch, img_emb_batch, tgts_batch, stat
     was_training = model.training
     model.eval()
     reward_model.eval()
+    side = _branch_stream(text_emb_batch.device) if before_critic is None else None
+    if side is not None:                # the value needs neither the actor's nor the reward model's result
+        main = torch.cuda.current_stream()
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            value = model.critic(text_emb_batch, img_emb_batch, tgts_batch, state)
     action_logits = model.actor.scores(text_emb_batch, img_emb_batch)
     if model.actor.mode == "cls":
         pr = action_logits.view(bs, tags_num, 3).softmax(dim=-1)
@@ -69,9 +94,12 @@ def rollout(model, reward_model, text_emb_batch, img_emb_batch, tgts_batch, stat
     # the tags_num sort indices reads its first tags_num entries (finetune/ppo.py:869-871)
     next_state = ops.ppo_rollout(action_scores.contiguous(), state[:, :tags_num].contiguous(), 2)
     rewards = reward_model(text_emb_batch, img_emb_batch, tgts_batch, next_state)
-    if before_critic is not None:
-        before_critic()
-    value = model.critic(text_emb_batch, img_emb_batch, tgts_batch, state)
+    if side is not None:
+        main.wait_stream(side)
+    else:
+        if before_critic is not None:
+            before_critic()
+        value = model.critic(text_emb_batch, img_emb_batch, tgts_batch, state)
     if was_training:
         model.train()
     return [state, next_state, action_scores, rewards, value, text_emb_batch, img_emb_batch, tgts_batch]
@@ -109,6 +137,9 @@ def update_batch(args, model, optimizer, critic_optim, memory, grad_sync=None, d
     else:
         model.zero_grad()
     bs, tags_num = old_action_prob.shape[:2]
+    side = _branch_stream(text.device) if grad_sync is None else None
+    if side is not None:
+        return _update_batch_two_branches(args, model, optimizer, critic_optim, memory, side, defer_critic_wait)
     action_logits = model.actor.scores(text, img)
     value = model.critic(text, img, tgts, state)
     if model.actor.mode == "cls":
@@ -131,6 +162,44 @@ def update_batch(args, model, optimizer, critic_optim, memory, grad_sync=None, d
     if defer_critic_wait:
         return stats, wait_critic
     wait_critic()
+    return stats
+
+
+def _update_batch_two_branches(args, model, optimizer, critic_optim, memory, side, defer_critic_wait):
+    """update_batch with the critic on its own stream: critic forward || actor forward; the value loss waits for the
+    policy-loss kernel (its regression target); critic backward + AdamW || actor backward + AdamW.  Same kernels,
+    same arithmetic, same results as the single-stream order."""
+    state, next_state, old_action_prob, rewards, old_value, text, img, tgts = memory
+    bs, tags_num = old_action_prob.shape[:2]
+    main = torch.cuda.current_stream()
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        value = model.critic(text, img, tgts, state)
+    action_logits = model.actor.scores(text, img)
+    if model.actor.mode == "cls":
+        pr = action_logits.view(bs, tags_num, 3).softmax(dim=-1)
+        action_scores = pr[:, :, 1] + 2 * pr[:, :, 2]
+    else:
+        action_scores = action_logits.view(bs, tags_num)
+    pair = next_state[:, -2:].contiguous()
+    loss, rank_loss, kl, ent, rewards_adj, adv = ppo_policy_loss(
+        action_scores, old_action_prob, rewards, old_value, pair, args.kl_div_loss_weight, args.entropy_weight,
+        0.01, -0.1)
+    target = rewards_adj.detach()
+    ready = torch.cuda.Event()
+    ready.record(main)
+    with torch.cuda.stream(side):
+        side.wait_event(ready)
+        value_loss = clipped_value_loss(value, target, old_value, args.value_clip)
+        value_loss.backward()
+        critic_optim.step()
+    loss.backward()
+    optimizer.step()
+    main.wait_stream(side)
+    stats = torch.stack([loss.detach(), value_loss.detach(), kl.mean(), old_value.mean(), value.detach().mean(),
+                         rewards.mean(), rewards_adj.mean(), adv.mean(), rank_loss, ent.mean()])
+    if defer_critic_wait:
+        return stats, (lambda: None)
     return stats
 
 
