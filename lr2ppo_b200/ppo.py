@@ -78,11 +78,13 @@ def rollout(model, reward_model, text_emb_batch, img_emb_batch, tgts_batch, stat
     was_training = model.training
     model.eval()
     reward_model.eval()
-    side = _branch_stream(text_emb_batch.device) if before_critic is None else None
+    side = _branch_stream(text_emb_batch.device)
     if side is not None:                # the value needs neither the actor's nor the reward model's result
         main = torch.cuda.current_stream()
         side.wait_stream(main)
         with torch.cuda.stream(side):
+            if before_critic is not None:
+                before_critic()
             value = model.critic(text_emb_batch, img_emb_batch, tgts_batch, state)
     action_logits = model.actor.scores(text_emb_batch, img_emb_batch)
     if model.actor.mode == "cls":
@@ -137,9 +139,10 @@ def update_batch(args, model, optimizer, critic_optim, memory, grad_sync=None, d
     else:
         model.zero_grad()
     bs, tags_num = old_action_prob.shape[:2]
-    side = _branch_stream(text.device) if grad_sync is None else None
+    side = _branch_stream(text.device)
     if side is not None:
-        return _update_batch_two_branches(args, model, optimizer, critic_optim, memory, side, defer_critic_wait)
+        return _update_batch_two_branches(args, model, optimizer, critic_optim, memory, side, grad_sync,
+                                          defer_critic_wait)
     action_logits = model.actor.scores(text, img)
     value = model.critic(text, img, tgts, state)
     if model.actor.mode == "cls":
@@ -165,10 +168,12 @@ def update_batch(args, model, optimizer, critic_optim, memory, grad_sync=None, d
     return stats
 
 
-def _update_batch_two_branches(args, model, optimizer, critic_optim, memory, side, defer_critic_wait):
+def _update_batch_two_branches(args, model, optimizer, critic_optim, memory, side, grad_sync, defer_critic_wait):
     """update_batch with the critic on its own stream: critic forward || actor forward; the value loss waits for the
     policy-loss kernel (its regression target); critic backward + AdamW || actor backward + AdamW.  Same kernels,
-    same arithmetic, same results as the single-stream order."""
+    same arithmetic, same results as the single-stream order.  Data parallel: every rank issues the collectives of the
+    two branches in the same program order, so they pair up across ranks exactly as before, and the communication of
+    one model overlaps the computation of the other."""
     state, next_state, old_action_prob, rewards, old_value, text, img, tgts = memory
     bs, tags_num = old_action_prob.shape[:2]
     main = torch.cuda.current_stream()
@@ -192,14 +197,18 @@ def _update_batch_two_branches(args, model, optimizer, critic_optim, memory, sid
         side.wait_event(ready)
         value_loss = clipped_value_loss(value, target, old_value, args.value_clip)
         value_loss.backward()
-        critic_optim.step()
+        wait_critic = _sync_and_step(grad_sync, model.critic, critic_optim)
     loss.backward()
-    optimizer.step()
+    wait_actor = _sync_and_step(grad_sync, model.actor, optimizer)
+    wait_actor()
+    if not defer_critic_wait:
+        with torch.cuda.stream(side):
+            wait_critic()
     main.wait_stream(side)
     stats = torch.stack([loss.detach(), value_loss.detach(), kl.mean(), old_value.mean(), value.detach().mean(),
                          rewards.mean(), rewards_adj.mean(), adv.mean(), rank_loss, ent.mean()])
     if defer_critic_wait:
-        return stats, (lambda: None)
+        return stats, wait_critic
     return stats
 
 
