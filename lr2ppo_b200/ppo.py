@@ -24,12 +24,13 @@ _SIDE = {}
 
 
 def _branch_stream(device):
-    """Second CUDA stream for the critic's branch of a step (LR2_DUAL_STREAM=1): the actor and the critic are
-    independent models whose only coupling inside a step is one [bs] vector (the adjusted rewards the value loss
-    regresses on), so their forwards / backwards / optimizer passes can run as two branches of the step's CUDA graph;
-    the launch-latency-bound kernels of one (LayerNorm, bias column sums, 2-4-token attention, tiny GEMMs) fill the
-    gaps of the other.  None = run the step on one stream, in the reference's order."""
-    if os.environ.get("LR2_DUAL_STREAM", "0") != "1" or device.type != "cuda":
+    """Second CUDA stream for the critic's branch of a step: the actor and the critic are independent models whose
+    only coupling inside a step is one [bs] vector (the adjusted rewards the value loss regresses on), so their
+    forwards / backwards / optimizer passes run as two branches of the step's CUDA graph; the launch-latency-bound
+    kernels of one (LayerNorm, bias column sums, 2-4-token attention, tiny GEMMs) and, data parallel, its collectives
+    fill the gaps of the other.  Measured on B200: 10.08 -> 9.78 ms/step at N = 1, 8.39 -> 7.89 ms at N = 2, results
+    bit-identical.  LR2_DUAL_STREAM=0 (-> None) runs the step on one stream, in the reference's order."""
+    if os.environ.get("LR2_DUAL_STREAM", "1") != "1" or device.type != "cuda":
         return None
     key = device.index if device.index is not None else torch.cuda.current_device()
     if key not in _SIDE:
