@@ -149,9 +149,12 @@ class GradSync:
             # split along its input dimension (Fc1Parallel above): the optimizer owns a COLUMN block per rank
             tensor_parallel = os.environ.get("LR2_DP_TP", "1") == "1"
         rank = dist.get_rank(self.group)
+        early = os.environ.get("LR2_DP_EARLY_REDUCE", "1") == "1"
         for e in self._engines(module):
             e.dp_gather = self.gather_rows
             e.dp_gather_async = self.gather_rows_async
+            if early and hasattr(e, "on_trunk_grads"):
+                e.on_trunk_grads = (lambda m=module: self._early_reduce(m))
             w = e.m.out_layer.fc1.weight
             self._skip.add(id(w))
             e.fc1_rows = None
@@ -302,34 +305,59 @@ class GradSync:
         params = [p for p in module.parameters() if p.grad is not None and id(p) not in self._skip]
         if not params:
             return lambda: None
+        # bucket order: first everything whose gradient is final before the backward reaches the input projections
+        # (head, xitt, out_layer, xit -- the "trunk"), then text_proj / img_proj; see _early_reduce
+        late = {id(p) for name in ("text_proj", "img_proj") if hasattr(module, name)
+                for p in getattr(module, name).parameters()}
+        params = [p for p in params if id(p) not in late] + [p for p in params if id(p) in late]
         grads = [p.grad for p in params]
         ent = self._flat.get(id(module))
         if ent is None or ent["shapes"] != [tuple(g.shape) for g in grads]:
-            offs, total = [], 0
-            for g in grads:
+            offs, total, split = [], 0, None
+            for p, g in zip(params, grads):
+                if split is None and id(p) in late:
+                    split = total
                 offs.append(total)
                 total += (g.numel() + 3) // 4 * 4
             flat = torch.zeros(total, dtype=torch.float32, device=grads[0].device)
-            ent = {"flat": flat, "shapes": [tuple(g.shape) for g in grads],
-                   "views": [flat[o:o + g.numel()] for o, g in zip(offs, grads)]}
+            ent = {"flat": flat, "shapes": [tuple(g.shape) for g in grads], "split": split or 0, "inplace": False,
+                   "early": None, "views": [flat[o:o + g.numel()] for o, g in zip(offs, grads)]}
             self._flat[id(module)] = ent
         flat, views = ent["flat"], ent["views"]
         inplace = all(g.data_ptr() == v.data_ptr() for g, v in zip(grads, views))
         copy_back = False
         if not inplace:
+            if ent["early"] is not None:                     # cannot happen: _early_reduce needs the in-place state
+                ent["early"].wait(); ent["early"] = None
             torch._foreach_copy_(views, [g.reshape(-1) for g in grads])
             if all(getattr(e, "persistent_grads", False) for e in self._engines(module)):
                 for p, v in zip(params, views):
                     p.grad = v.view(p.shape)             # from now on the backward writes straight into the bucket
+                inplace = True
             else:
                 copy_back = True
-        work = dist.all_reduce(flat, group=self.group, async_op=True)
+        ent["inplace"] = inplace
+        early, ent["early"] = ent["early"], None
+        # the trunk part may already be in flight (started inside backward); then only the projections are left
+        work = dist.all_reduce(flat[ent["split"]:] if early is not None else flat, group=self.group, async_op=True)
 
         def finish():
+            if early is not None:
+                early.wait()
             work.wait()
             if copy_back:
                 torch._foreach_copy_([g.view(-1) for g in grads], views)
         return finish
+
+    def _early_reduce(self, module):
+        """engine.on_trunk_grads: called inside backward when every gradient of the bucket's first part is final.
+        Only in the zero-copy state (persistent gradient buffers that ARE views of the bucket): the all-reduce of that
+        part (about half of the 19 M small parameters) then runs on NCCL's stream under the backward of the input
+        projections instead of after the whole backward.  LR2_DP_EARLY_REDUCE=0 disables it."""
+        ent = self._flat.get(id(module))
+        if ent is None or not ent["inplace"] or not ent["split"] or ent["early"] is not None:
+            return
+        ent["early"] = dist.all_reduce(ent["flat"][:ent["split"]], group=self.group, async_op=True)
 
     def early_params(self, module):
         """ids of the parameters whose gradients need no all-reduce (out_layer.fc1 of each engine)."""

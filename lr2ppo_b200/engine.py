@@ -270,11 +270,14 @@ class FusionEngine:
         self.fc1_passes, self._fc1_pending = 1, []   # backward passes per optimizer step (stage 2: 2) and their operands
         self._zero_index = {}      # (bs, T, device) -> int64 zeros [bs, T]: broadcast index of un-repeated img_emb
         self.tp = None             # dist.Fc1Parallel: out_layer.fc1 K-split over the data-parallel ranks
+        self.on_trunk_grads = None  # dist.GradSync: callback fired inside backward once all but the projections' grads are final
+        self._bwd_calls = 0        # backward passes since begin_step()
 
     def begin_step(self):
         """Persistent-gradient mode: start of a new optimizer step (replaces model.zero_grad())."""
         self._written.clear()
         self._fc1_pending = []
+        self._bwd_calls = 0
 
     def _fc1_wgrad(self, dy_, x_, out, bn=None):
         """out (bf16 block of the out_layer.fc1 gradient) = dY^T X over all rows collected for this optimizer step.
@@ -522,6 +525,11 @@ class FusionEngine:
         dimf = torch.empty((items * I, E), dtype=bf16, device=dcat.device)
         ops.rows_copy(dcat_rows, S + I, S, dimf, I, 0, items, I, E)
         dtf, dimf = xit_backward(W["xit"], ctx["c_x"], dcat_rows, sink, dy_extra=dimf)
+        self._bwd_calls += 1
+        if self.on_trunk_grads is not None and self._bwd_calls >= self.fc1_passes:
+            # every gradient except those of text_proj / img_proj is final (last backward pass of this optimizer
+            # step): data parallel, their all-reduce starts here and runs under the projections' backward
+            self.on_trunk_grads()
         mlp_backward(W["tp1"], W["tp2"], ctx["c_tp"], dtf, sink)
         mlp_backward(W["ip1"], W["ip2"], ctx["c_ip"], dimf, sink)
         if deferred_fc1 is not None:

@@ -14,6 +14,7 @@ import torch.multiprocessing as mp
 class _Eng:
     def __init__(self, m):
         self.m, self.dp_gather, self.bank = m, None, type("B", (), {"invalidate": lambda self: None})()
+        self.on_trunk_grads = None            # set by GradSync.attach (engine.FusionEngine.on_trunk_grads)
 
 
 class _Net(torch.nn.Module):
@@ -22,6 +23,7 @@ class _Net(torch.nn.Module):
         self.out_layer = torch.nn.Module()
         self.out_layer.fc1 = torch.nn.Linear(24, 8)
         self.other = torch.nn.Linear(8, 4)
+        self.text_proj = torch.nn.Linear(5, 3)            # an input projection: last gradients of a backward pass
         self._engine = _Eng(self)
 
 
@@ -84,6 +86,27 @@ def _worker(rank, world, path):
         assert torch.allclose(p.grad, torch.full_like(p, float(2 * sum(range(1, world + 1)))))
     assert torch.equal(net.out_layer.fc1.weight.grad, before)
     assert sync.early_params(net) == {id(net.out_layer.fc1.weight)}
+    # (4) early reduce: the bucket holds the trunk first, text_proj / img_proj last; the engine's hook starts the
+    # all-reduce of the trunk part inside backward, start() then only reduces the projections' part
+    proj = list(net.text_proj.parameters())
+    assert max(p.grad.data_ptr() for p in small if all(p is not q for q in proj)) < min(q.grad.data_ptr() for q in proj)
+    assert net._engine.on_trunk_grads is not None
+    for p in small:
+        p.grad.fill_(float(3 * (rank + 1)))
+    for q in proj:
+        q.grad.fill_(-1.0)                                                   # "not written yet" at hook time
+    net._engine.on_trunk_grads()                                             # trunk part in flight ...
+    for q in proj:
+        q.grad.fill_(float(5 * (rank + 1)))                                  # ... while the projections' backward runs
+    sync.start(net)()
+    tot = float(sum(range(1, world + 1)))
+    for p in small:
+        want = 5 * tot if any(p is q for q in proj) else 3 * tot             # every slot reduced exactly once
+        assert torch.allclose(p.grad, torch.full_like(p, want)), (want, p.grad.flatten()[:3])
+    net._engine.on_trunk_grads(); sync.start(net)()                         # and again (state resets every step)
+    for p in small:
+        want = 5 * tot * world if any(p is q for q in proj) else 3 * tot * world    # equal values on all ranks now
+        assert torch.allclose(p.grad, torch.full_like(p, want))
     dist.barrier()
     dist.destroy_process_group()
 
