@@ -599,7 +599,7 @@ def main():
         ach = sum(b for b, _ in big) / (sum(t for _, t in big) * 1e-3) / 1e9
         roofline = {"kernel": "adamw_multi_kernel", "bound": "hbm", "achieved": ach, "peak": hbm_peak,
                     "unit": "GB/s", "frac": ach / hbm_peak,
-                    "traffic": ncu_traffic("r01_adamw_full.md") if world == 1 else None,
+                    "traffic": ncu_traffic("r02_adamw_full.md") if world == 1 else None,
                     "peak_source": hbm_src, "share_of_step": gp["ms_per_step"] / total_ms,
                     "algorithmic_bytes_per_launch": sum(b for b, _ in big) / len(big),
                     "launch_ms": sum(t for _, t in big) / len(big), "launches_per_step": len(big) / args.profile_steps,

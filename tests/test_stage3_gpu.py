@@ -203,3 +203,39 @@ def test_graphed_cycle_equals_the_eager_cycle(sds):
     assert torch.allclose(graphed[3], eager[3], rtol=1e-4, atol=1e-6), (graphed[3], eager[3])
     for a, b in zip(graphed[:3], eager[:3]):
         assert torch.allclose(a, b, rtol=0, atol=1e-7)
+
+
+def test_two_branch_step_equals_the_single_stream_step(sds, monkeypatch):
+    """LR2_DUAL_STREAM (default on: the critic's forward / backward / AdamW run on a second stream, ppo._branch_stream)
+    only re-orders independent work: rollout results, the ten statistics and the updated weights are bit-identical to
+    the single-stream order."""
+    from lr2ppo_b200 import ppo
+    g = torch.Generator().manual_seed(11)
+    bs = 4
+    batch = (torch.randn(bs, 2, 196, 768, generator=g).cuda(), torch.randn(bs, 1, 16, 768, generator=g).cuda(),
+             torch.randint(0, 3, (bs, 2), generator=g).cuda())
+    results = []
+    for dual in ("1", "0"):
+        monkeypatch.setenv("LR2_DUAL_STREAM", dual)
+        assert (ppo._branch_stream(batch[0].device) is not None) == (dual == "1")
+        model, reward = _build_gpu(sds)
+        for e in (model.actor._engine, model.critic._engine):
+            e.dropout_seed = 4711                    # same masks in both runs (train-mode update)
+        hp = _hp(False, bf16_grad=True)
+        opt, copt, _, _ = ppo.build_optimizer(hp, model)
+        for _ in range(2):
+            mem = ppo.rollout(model, reward, *batch)
+            model.train(); stats = ppo.update_batch(hp, model, opt, copt, mem); model.eval()
+        torch.cuda.synchronize()
+        results.append(([t.detach().cpu().clone() for t in mem[:5]], stats.cpu(),
+                        golden_util.grad_sample(model.actor.out_layer.fc1.weight.detach(), 1 << 16).cpu(),
+                        golden_util.grad_sample(model.critic.out_layer.fc1.weight.detach(), 1 << 16).cpu(),
+                        dict(model.critic.named_parameters())["xitt.0.0.0.fn.1.queries.weight"].detach().cpu().clone()))
+        del model, reward, opt, copt
+        torch.cuda.empty_cache()
+    (mem_a, st_a, wa_a, wc_a, q_a), (mem_b, st_b, wa_b, wc_b, q_b) = results
+    for a, b in zip(mem_a, mem_b):
+        assert torch.equal(a, b)
+    assert torch.equal(st_a, st_b)
+    assert torch.equal(wa_a, wa_b) and torch.equal(wc_a, wc_b)
+    assert torch.equal(q_a, q_b)
