@@ -92,12 +92,12 @@ def work(tmp_path_factory):
     return path
 
 
-def _launch(work, name, text, port):
+def _launch(work, name, text, port, gpus=1, exp="t1", **extra_env):
     sh = os.path.join(work, name)
     with open(sh, "w") as f:
         f.write(text)
-    env = dict(os.environ, LR2_NUM_WORKERS="2")
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "dropin", "launch.py"), sh, "t1", "--gpus", "1",
+    env = dict(os.environ, LR2_NUM_WORKERS="2", **extra_env)
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "dropin", "launch.py"), sh, exp, "--gpus", str(gpus),
                         "--master-port", str(port)], cwd=work, env=env, capture_output=True, text=True, timeout=900)
     assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-6000:]
     return p
@@ -141,6 +141,29 @@ def test_ppo_sh_then_ppo_eval_sh_through_main(work):
         assert len(c["ndcg"]) == 6 and len(c["predict"]) == len(v["tags"])
         scores = [s for _, s in c["predict"]]
         assert scores == sorted(scores, reverse=True)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_ppo_sh_on_two_gpus_with_gradient_sync(work):
+    """ppo.sh on 2 ranks with LR2_GRAD_SYNC=1: the K-split out_layer.fc1 (dist.Fc1Parallel), replicated evaluation and
+    the collective consolidate before rank 0 saves -- the checkpoint must again be the reference's complete fp32 file."""
+    text = SH.format(train="first_second_stage_data.json", stage="ppo", epochs=2, bs=2, report=100, max_tags=4,
+                     extra_train="    --critic_learning_rate 1e-3\n    --learning_rate 1e-3\n", script="ppo",
+                     ppo_block=PPO_BLOCK.format(pre=""), ppo_use='                                   "${ppo_args[@]}" \\\n')
+    _launch(work, "ppo2.sh", text, 29621, gpus=2, exp="t2", LR2_GRAD_SYNC="1")
+    log = open(os.path.join(work, "ppo_logs", "t2", "t2.txt")).read()
+    # 24 training instances over 2 ranks = 12 per rank = 6 batches of 2 = 1 full cycle of update_timesteps 4 per epoch
+    assert "Training step: 1" in log and "Policy loss:" in log and "NDCG@100000000=" in log
+    sd = torch.load(os.path.join(work, "ppo_ckpt", "t2", "finetuned_model.bin"), map_location="cpu")
+    want = _reference_keys(("actor", "critic"))
+    assert list(sd.keys()) == [n for n, _ in want]
+    for n, shape in want:
+        assert tuple(sd[n].shape) == tuple(shape) and sd[n].dtype == torch.float32 and torch.isfinite(sd[n]).all(), n
+    # every column block of the K-split weight was updated by its owner and gathered back: no block is left at its
+    # initial value on rank 0's copy (lr 1e-3 moves every element that has a gradient)
+    w = sd["actor.out_layer.fc1.weight"]
+    half = w.shape[1] // 2
+    assert w[:, :half].abs().sum() > 0 and w[:, half:].abs().sum() > 0
 
 
 @pytest.mark.parametrize("stage", ["pointwise", "reward_pair_dataloader"])
