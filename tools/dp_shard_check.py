@@ -9,16 +9,21 @@ identical models / batches, dropout off, constant lr = 2e-5, three eager stage-3
 products (reduce-scatter) instead of one split-K GEMM -- a different summation order, then the same bf16 rounding --
 so it is held to the bf16 tolerance instead of bit-equality: statistics of the last step 2e-2, every Adam first moment 4e-2 of its scale (tests/parity.py), and --
 because forward weights that silently stopped following the optimizer would pass a moments-only check -- the bf16
-weights every rank actually multiplies with must equal the rounded fp32 masters after consolidation."""
+weights every rank actually multiplies with must equal the rounded fp32 masters after consolidation.
+
+Both sharded modes also write a per-rank sharded checkpoint (checkpoint.save_sharded with GradSync.row_shards: row
+blocks in gather mode, column blocks in tp mode) before consolidating; rank 0 reassembles the files and compares
+them bit for bit with the consolidated master weights and Adam moments."""
 import argparse
 import os
+import shutil
 import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.distributed as dist
 
-from lr2ppo_b200 import ppo
+from lr2ppo_b200 import checkpoint, ppo
 from lr2ppo_b200.dist import GradSync
 
 
@@ -57,7 +62,11 @@ def main():
     batches = [(torch.randn(24, 2, 196, 768, generator=g).to(dev),
                 torch.randn(24, 1, 16, 768, generator=g).repeat(1, 2, 1, 1).to(dev),
                 torch.randint(0, 3, (24, 2), generator=g).to(dev)) for _ in range(3)]
-    results = {}
+    results, ck_bad = {}, []
+    ck_root = os.environ.get("LR2_CHECK_DIR", "/tmp/lr2_dp_shard_check")
+    if rank == 0:
+        shutil.rmtree(ck_root, ignore_errors=True)
+    dist.barrier()
     for mode in ("replicated", "gather", "tp"):
         model, reward = build(7, dev)
         opt, copt, sch, csch = ppo.build_optimizer(hp, model)
@@ -74,7 +83,17 @@ def main():
             stats = ppo.update_batch(hp, model, opt, copt, mem, sync)
             model.eval()
         torch.cuda.synchronize()
+        ck_dir = None
         if mode != "replicated":
+            # sharded checkpoint on real ranks: every rank writes its own block of out_layer.fc1 (rows in gather mode,
+            # columns in tp mode) BEFORE any consolidation; rank 0 adds the replicated rest.  Read back below.
+            ck_dir = os.path.join(ck_root, mode)
+            # (the actor only: 6 GB of weights + moments per mode is enough disk traffic for a check)
+            shards = {"actor": sync.row_shards(model.actor)}
+            assert all(len(v) == 1 for v in shards.values()), shards
+            checkpoint.save_sharded(ck_dir, {"actor": model.actor}, {"actor": opt}, {"actor": sch}, step=3, rank=rank,
+                                    world=world, row_shards=shards).wait()
+            dist.barrier()
             sync.consolidate(model.actor, opt); sync.consolidate(model.critic, copt)
         if mode == "tp":
             sync.gather_shadow(model.actor); sync.gather_shadow(model.critic)
@@ -88,11 +107,30 @@ def main():
             rec[f"{tag}.fc1.shadow"] = mod._engine.bank.get(w).clone()
             rec[f"{tag}.fc1.master"] = w.detach().clone()
             rec[f"{tag}.fc1.m"] = o.state_for(w)["exp_avg"].clone()
+        if ck_dir is not None and rank == 0:
+            # the shard files reassemble to exactly the consolidated tensors: master weights and both Adam moments
+            common, parts = checkpoint._read_sharded(ck_dir, "cpu")
+            for tag, mod, o in (("actor", model.actor, opt),):
+                name = "out_layer.fc1.weight"
+                assert list(common["sharded"][tag]) == [name] and name not in common["models"][tag]
+                w = mod.out_layer.fc1.weight
+                want = {"param": w.detach().cpu(), "exp_avg": o.state_for(w)["exp_avg"].cpu(),
+                        "exp_avg_sq": o.state_for(w)["exp_avg_sq"].cpu()}
+                for kind, ref in want.items():
+                    got = checkpoint._assemble(list(w.shape), [(sh["rows"][tag][name], sh[kind][tag][name]) for sh in parts])
+                    if not torch.equal(got, ref):
+                        ck_bad.append((f"{mode}:{tag}.{kind} from shard files != consolidated", 1.0))
+                dims = {checkpoint._block(sh["rows"][tag][name])[0] for sh in parts}
+                assert dims == ({1} if mode == "tp" else {0}), dims            # tp: column blocks, gather: row blocks
+            del common, parts
+            shutil.rmtree(ck_dir, ignore_errors=True)
+            print(f"[rank 0] {mode}: sharded checkpoint of {world} ranks reassembles to the consolidated fc1 weights "
+                  f"and moments: {not ck_bad}", flush=True)
         results[mode] = rec
         del model, reward, opt, copt, sync
         torch.cuda.empty_cache()
     a, b, c = results["replicated"], results["gather"], results["tp"]
-    bad = []
+    bad = list(ck_bad)
     for k in a:
         if a[k] is None:
             continue
