@@ -234,6 +234,44 @@ def other_configs(torch, dist, dev, world, rank, peaks):
     return out
 
 
+def loop_shape(torch, hp, model, reward, opt, copt, sch, csch, resident, n=16, cycles=2):
+    """The reference's real loop shape (finetune/ppo.py:845-908) on the same models: n rollout batches into the bf16
+    RolloutMemory ring, THEN n updates over the stored batches, schedulers stepped once per cycle -- one rollout graph
+    and one update graph replayed n times each (ppo.GraphedCycle, what scripts/ppo.py runs).  The headline `value`
+    times the amortised form (rollout k, update k, ...), which does the same work per batch."""
+    from lr2ppo_b200 import ppo
+    opt.frozen_hyper = copt.frozen_hyper = False
+    cyc = ppo.GraphedCycle(hp, model, reward, opt, copt, capacity=n, bs=BS, tags=TAGS, S=SEQ, I=IMGS, E=FEAT)
+
+    def one_cycle(ev=None):
+        for b in range(n):
+            cyc.rollout(*resident[b % len(resident)])
+        if ev is not None:
+            ev.record()
+        cyc.update(sch, csch)
+
+    one_cycle()                                   # two eager updates, both captures, first replays
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mids = [torch.cuda.Event(enable_timing=True) for _ in range(cycles)]
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(cycles)]
+    e0.record()
+    for c in range(cycles):
+        starts[c].record()
+        one_cycle(mids[c])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    roll = sum(starts[c].elapsed_time(mids[c]) for c in range(cycles)) / (cycles * n)
+    out = {"what": f"{cycles} cycles of {n} rollout batches then {n} update batches over the bf16 RolloutMemory ring "
+                   f"(rollout graph + update graph, ppo.GraphedCycle); 24 queries per batch",
+           "queries_per_s": BS * n * cycles / (ms * 1e-3), "ms_per_batch": ms / (n * cycles),
+           "rollout_ms_per_batch": roll, "update_ms_per_batch": ms / (n * cycles) - roll,
+           "ring_bytes_per_batch": cyc.memory.bytes_per_entry()}
+    del cyc
+    return out
+
+
 def _launches():
     from lr2ppo_b200 import _lib
     return _lib.launch_count()
@@ -626,6 +664,16 @@ def main():
                                   "tensor_frac_of_" + tf_src.replace(" ", "_"): round(
                                       gemm_flops / (gemm_ms * 1e-3) / 1e12 / tf_peak, 3) if gemm_ms else None}
 
+    # ---- (3a) the reference's loop shape (N rollouts, then N updates) on the same models, N = 1 only ----------
+    loop = None
+    if world == 1 and use_graph and not args.no_other_configs:
+        try:
+            loop = loop_shape(torch, hp, model, reward, opt, copt, sch, csch, resident)
+        except Exception as e:
+            import traceback
+            traceback.print_exc()
+            loop = {"error": repr(e)}
+
     # ---- (3b) the other BASELINE configs, measured in the same run ------------------------------------------
     others = None
     if not args.no_other_configs:
@@ -676,6 +724,8 @@ def main():
         if eager is not None:
             line["eager_b200"] = eager
             line["speedup_vs_eager_b200"] = value / eager["value"]
+        if loop is not None:
+            line["loop_shape_200_200"] = loop
         if others is not None:
             line["other_configs"] = others
         print(json.dumps(line))
