@@ -332,9 +332,11 @@ class FusionEngine:
             W["xitt"] = XitWeights(bank, m.xitt)
         return W
 
-    def forward(self, text, img, index=None, train=False, save=False, seed=None):
+    def forward(self, text, img, index=None, train=False, save=False, seed=None, trunk_only=False):
         """text [bs, Tsrc, S, E] fp32, img [bs, Tsrc, I, E] fp32, index [bs, T] int64 or None.
-        Returns (logits fp32, ctx).  actor: logits [bs*T, n_out]; critic: [bs]."""
+        Returns (logits fp32, ctx).  actor: logits [bs*T, n_out]; critic: [bs].
+        trunk_only (inference, index None): stop after out_layer and return (pooled item features [bs*Tsrc, E] bf16,
+        None) -- everything of a critic / reward forward that does not depend on the index; tail() finishes it."""
         m = self.m
         W = self._weights()
         bs, Tsrc, S, E = text.shape
@@ -407,6 +409,10 @@ class FusionEngine:
             else:
                 y1 = ops.gemm(cat, o1.w, epilogue=EPI_BIAS_GELU, bias=o1.b, c2=pre3, splits=4)
         feat = ops.gemm(y1, W["o2"].w, epilogue=EPI_BIAS, bias=W["o2"].b)
+        if trunk_only:
+            if train or save or index is not None:
+                raise RuntimeError("trunk_only is the inference-only first half of forward(index=...)")
+            return feat, None
         if reuse:
             feat = ops.gather_rows(feat.view(bs, Tsrc, E), index).view(bs * T, E)
             items = bs * T
@@ -429,6 +435,20 @@ class FusionEngine:
             ctx = dict(W=W, dims=(bs, T, S, I, E, items), c_tp=c_tp, c_ip=c_ip, c_x=c_x, cat=cat, pre3=pre3, y1=y1,
                        feat=feat, imf=imf, c_t=c_t, z=z, cat_all=cat_all, tp=tp)
         return logits, ctx
+
+    def tail(self, feat_items, index):
+        """Second half of an inference forward of a critic / reward model from the pooled item features of
+        forward(trunk_only=True): gather by index [bs, T], + pos_emb, self-attention over the T items, head on the last
+        token -- exactly the operations forward(index=...) runs after out_layer in its item-reuse mode."""
+        m = self.m
+        W = self._weights()
+        bs, T = index.shape
+        E = feat_items.shape[-1]
+        Tsrc = feat_items.shape[0] // bs
+        feat = ops.gather_rows(feat_items.view(bs, Tsrc, E), index).view(bs * T, E)
+        ops.add_pos_fwd(feat, m.pos_emb.weight.detach()[:T].contiguous(), bs, T)
+        z, _ = xit_forward(W["xitt"], feat, feat, bs, T, T, False, 0, 3, False)
+        return ops.rowdot_fwd(z, m.head.weight.detach().view(-1), m.head.bias.detach(), bs, T, T - 1)
 
     def _fc1_forward_tp(self, tp, o1, cat, items, save):
         """K-split out_layer.fc1 forward (dist.Fc1Parallel).  Returns (y1 [items, hid], pre3 | None, X block | None)."""

@@ -165,7 +165,26 @@ class Critic(nn.Module):
 
 class Reward(Critic):
     """Same architecture and forward as Critic; index is the 4-slot [0, 1, pi(0), pi(1)] layout
-    (finetune/ppo.py:300-350)."""
+    (finetune/ppo.py:300-350).
+
+    The frozen reward model scores a permutation of items whose features do not depend on the permutation, so its
+    inference forward can be cut in two (ppo.rollout runs the first half beside the actor, on its own stream):
+    item_features(text, img) -> pooled features of every (clip, tag) item; from_item_features(feat, index) -> rewards.
+    from_item_features(item_features(t, i), idx) == forward(t, i, tgts, idx) bit for bit in eval mode."""
+
+    @torch.no_grad()
+    def item_features(self, text_emb, img_emb):
+        _check_inputs(text_emb, img_emb)
+        if self.training:
+            raise RuntimeError("item_features is inference-only (model.eval())")
+        return self._engine.forward(text_emb.contiguous(), img_emb.contiguous(), None, train=False, save=False,
+                                    trunk_only=True)[0]
+
+    @torch.no_grad()
+    def from_item_features(self, feat, index):
+        if index.shape[1] > self.pos_emb.weight.shape[0]:
+            raise RuntimeError("index longer than pos_emb")
+        return self._engine.tail(feat, index.to(torch.int64).contiguous())
 
 
 class PairClassifier(Critic):

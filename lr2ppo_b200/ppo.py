@@ -23,6 +23,16 @@ from .optim import attach_shadows, decay_groups, make_scheduler, str2optimizer, 
 _SIDE = {}
 
 
+def _reward_stream(device):
+    """Third stream of the rollout (only with the two-branch step on): the reward model's item features."""
+    if _branch_stream(device) is None or os.environ.get("LR2_REWARD_STREAM", "1") != "1":
+        return None
+    key = ("reward", device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=device)
+    return _SIDE[key]
+
+
 def _branch_stream(device):
     """Second CUDA stream for the critic's branch of a step: the actor and the critic are independent models whose
     only coupling inside a step is one [bs] vector (the adjusted rewards the value loss regresses on), so their
@@ -87,6 +97,13 @@ def rollout(model, reward_model, text_emb_batch, img_emb_batch, tgts_batch, stat
             if before_critic is not None:
                 before_critic()
             value = model.critic(text_emb_batch, img_emb_batch, tgts_batch, state)
+    # the reward model scores a permutation of items whose pooled features do not depend on it: that part (all of the
+    # forward up to out_layer) runs on a third stream beside the actor; only gather + xitt + head wait for next_state
+    rstream = _reward_stream(text_emb_batch.device) if hasattr(reward_model, "item_features") else None
+    if rstream is not None:
+        rstream.wait_stream(main)
+        with torch.cuda.stream(rstream):
+            item_feat = reward_model.item_features(text_emb_batch, img_emb_batch)
     action_logits = model.actor.scores(text_emb_batch, img_emb_batch)
     if model.actor.mode == "cls":
         pr = action_logits.view(bs, tags_num, 3).softmax(dim=-1)
@@ -96,7 +113,11 @@ def rollout(model, reward_model, text_emb_batch, img_emb_batch, tgts_batch, stat
     # timestep > 0 passes the previous next_state (prefix + permutation) as state: the reference's index_select with
     # the tags_num sort indices reads its first tags_num entries (finetune/ppo.py:869-871)
     next_state = ops.ppo_rollout(action_scores.contiguous(), state[:, :tags_num].contiguous(), 2)
-    rewards = reward_model(text_emb_batch, img_emb_batch, tgts_batch, next_state)
+    if rstream is not None:
+        main.wait_stream(rstream)
+        rewards = reward_model.from_item_features(item_feat, next_state)
+    else:
+        rewards = reward_model(text_emb_batch, img_emb_batch, tgts_batch, next_state)
     if side is not None:
         main.wait_stream(side)
     else:
