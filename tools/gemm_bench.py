@@ -65,6 +65,9 @@ def main():
          lambda: ops.gemm(W, dy1, a_mn=True, out=dcat, transposed_out=True, block_n=64)),
         ("fc1 wgrad 3072x162816 K=48 f32", 2 * items * H * K1, H * K1 * 4 + items * K1 * 2,
          lambda: ops.gemm(dy1, cat, a_mn=True, b_mn=True, out=gW)),
+        # what the training step runs: bf16 gradient buffer, pair kernel + TMA-store drain (engine._fc1_wgrad)
+        ("fc1 wgrad 3072x162816 K=48 bf16 (step)", 2 * items * H * K1, H * K1 * 2 + items * K1 * 2,
+         lambda: ops.gemm(dy1, cat, a_mn=True, b_mn=True, out=gWb, block_n=2256)),
     ]
     for bn in [int(v) for v in os.environ.get("BENCH_BNS", "").split(",") if v]:
         cases += [
@@ -109,6 +112,7 @@ def main():
         "fc1 fwd 3072x48x162816 s6 T": (lambda: torch.matmul(cat, W.t()), lambda: F.gelu(F.linear(cat, W, bh.to(bf)))),
         "fc1 dgrad 162816x48x3072 T": (lambda: torch.matmul(dy1, W), None),
         "fc1 wgrad 3072x162816 K=48 f32": (lambda: torch.matmul(dy1.t(), cat), None),
+        "fc1 wgrad 3072x162816 K=48 bf16 (step)": (lambda: torch.matmul(dy1.t(), cat), None),
     }
     only = sys.argv[1] if len(sys.argv) > 1 else None
     print(f"{'case':42s} {'ours us':>9s} {'TFLOP/s':>9s} {'GB/s':>9s} | {'cuBLAS us':>9s} {'ours/cuBLAS':>11s} | "
