@@ -62,6 +62,9 @@ void lr2_note_launches(int n);
  * (lr2_gemm_workspace_bytes).  block_n in {0 (auto), 64, 128, 256} selects the single-CTA kernel's N tile;
  * 2128 / 2256 select the cta_group::2 pair kernel (a two-CTA cluster computes 256 x 128 / 256 x 256 tiles).  Auto uses the
  * pair kernel for untransposed problems with N % 256 == 0, K > 128 and at least 37 pair tiles (x splits).
+ * Plain bf16 outputs of the 256-wide pair kernel (no epilogue, no split-K) leave through a TMA store
+ * (cp.async.bulk.tensor global <- shared, {64, 32} boxes clipped at the matrix edges); every other case through
+ * the staged register epilogue.
  * Dropout (all epilogues, lr2_layernorm_bwd, lr2_dropout_bf16): ONE Philox4x32-7 call per aligned group of 8 output
  * elements (linear index r*ldc + c), 16 random bits per element; p is quantised to round(p * 65536) / 65536 and the
  * survivors are scaled by exactly 65536 / (65536 - round(p * 65536)), so the mask is a pure function of
