@@ -99,3 +99,13 @@ def test_rollout_memory_ring_semantics():
     assert len(mem) == 0 and len(list(mem)) == 0
     mem.stage(batches[1][5], batches[1][6], batches[1][7])                          # [bs, 1, I, E] accepted as well
     assert torch.equal(mem.text[0], batches[1][5])
+
+
+def test_branch_streams_are_cuda_only_and_env_gated(monkeypatch):
+    """The multi-branch step (ppo._branch_stream / _reward_stream) never engages off CUDA, and LR2_DUAL_STREAM=0 /
+    LR2_REWARD_STREAM=0 switch it off: the single-stream order of the reference remains one variable away."""
+    from lr2ppo_b200 import ppo
+    cpu = torch.device("cpu")
+    assert ppo._branch_stream(cpu) is None and ppo._reward_stream(cpu) is None
+    monkeypatch.setenv("LR2_DUAL_STREAM", "0")
+    assert ppo._branch_stream(torch.device("cuda", 0)) is None and ppo._reward_stream(torch.device("cuda", 0)) is None
